@@ -1,0 +1,131 @@
+// Shared device helpers and internal launcher declarations for libmarlc.
+// sm_100a only (B200).  No torch types anywhere in this library.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#define MARLC_SMS 148
+
+namespace marlc {
+
+// ---- error plumbing (C-ABI returns int, message via marlc_last_error) -----
+void set_error(const char* fmt, ...);
+#define MARLC_FAIL(...)            \
+    do {                           \
+        marlc::set_error(__VA_ARGS__); \
+        return 1;                  \
+    } while (0)
+#define MARLC_CHECK(cond, ...)     \
+    do {                           \
+        if (!(cond)) MARLC_FAIL(__VA_ARGS__); \
+    } while (0)
+#define MARLC_CUDA(expr)                                                         \
+    do {                                                                         \
+        cudaError_t e__ = (expr);                                                \
+        if (e__ != cudaSuccess)                                                  \
+            MARLC_FAIL("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+extern int g_launch_count;  // kernels launched through this library (bench accounting)
+#define MARLC_LAUNCH_CHECK()             \
+    do {                                 \
+        ++marlc::g_launch_count;         \
+        MARLC_CUDA(cudaGetLastError());  \
+    } while (0)
+#define MARLC_TRY(expr)        \
+    do {                       \
+        int r__ = (expr);      \
+        if (r__) return r__;   \
+    } while (0)
+
+// ---- math ------------------------------------------------------------------
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float siluf_(float x) { return x * sigmoidf_(x); }
+// d/dz [z * sigmoid(z)]
+__device__ __forceinline__ float silu_grad_(float z) {
+    float s = sigmoidf_(z);
+    return s * (1.0f + z * (1.0f - s));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---- Philox4x32-10 (counter-based RNG; own implementation) ------------------
+struct Philox {
+    uint32_t k0, k1;
+    __device__ Philox(uint64_t seed) : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)) {}
+    __device__ uint4 operator()(uint64_t ctr, uint64_t stream) const {
+        uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = (uint32_t)stream, c3 = (uint32_t)(stream >> 32);
+        uint32_t a = k0, b = k1;
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+            uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+            uint32_t n0 = hi1 ^ c1 ^ a, n1 = lo1, n2 = hi0 ^ c3 ^ b, n3 = lo0;
+            c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+            a += 0x9E3779B9u; b += 0xBB67AE85u;
+        }
+        return make_uint4(c0, c1, c2, c3);
+    }
+};
+// uniform in [0,1) with 24 bits
+__device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+
+// ---- generic fp32 GEMM (SIMT), gemm_simt.cu ----------------------------------
+// C[m,n] (+)= sum_k A(m,k) B(k,n) [+ sum_k2 A2(m,k2) B2(k2,n)] + bias[n] + bias2[n]
+// A(m,k) = A[m*sam + k*sak]; B(k,n) = B[k*sbk + n*sbn]; C[m*ldc + n].
+struct GemmProblem {
+    const float* A; long sam, sak;
+    const float* B; long sbk, sbn;
+    const float* A2; long sam2, sak2;
+    const float* B2; long sbk2, sbn2;
+    const float* bias; const float* bias2;
+    float* C; long ldc;
+    int M, N, K, K2;
+    int accumulate;  // 1: C += result
+};
+struct GemmGroup {
+    GemmProblem p[4];
+    int count;
+};
+int gemm_group(const GemmGroup& g, cudaStream_t s);
+// Y[M,N] = X[M,K] W[N,K]^T (+ bias)       (nn.Linear forward)
+int gemm_nt(const float* X, long ldx, const float* W, long ldw, const float* bias, float* Y, long ldy, int M, int N,
+            int K, int accumulate, cudaStream_t s);
+// dX[M,K] (+)= dY[M,N] W[N,K]              (input gradient)
+int gemm_nn(const float* dY, long lddy, const float* W, long ldw, float* dX, long lddx, int M, int N, int K,
+            int accumulate, cudaStream_t s);
+// dW[N,K] (+)= dY[R,N]^T X[R,K]            (weight gradient, reduction over rows)
+int gemm_tn(const float* dY, long lddy, const float* X, long ldx, float* dW, long lddw, int R, int N, int K,
+            int accumulate, cudaStream_t s);
+
+// ---- row-wise kernels, rowwise.cu --------------------------------------------
+int ln_silu_fwd(const float* Y, long ldy, const float* gamma, const float* beta, float* S, long lds, int R, int N,
+                cudaStream_t s);
+// dY = d(LN->SiLU)/dY * dS ; accumulates dgamma/dbeta/dbias (column sums) atomically
+int ln_silu_bwd(const float* dS, long ldds, const float* Y, long ldy, const float* gamma, const float* beta, float* dY,
+                long lddy, float* dgamma, float* dbeta, float* dbias, int R, int N, cudaStream_t s);
+int colsum_add(const float* X, long ldx, float* out, int R, int N, cudaStream_t s);
+int msg_mean(const float* msg, float* coll, int Na, int Nb, int n, cudaStream_t s);  // also its own adjoint
+int pos_features_fwd(const float* npos, const float* W, const float* b, const float* gamma, const float* beta,
+                     float* y_pre, float* out, long ldo, int R, int nd, cudaStream_t s);
+int lstm_cell_fwd(float* gates /*[M,4n] pre -> post activations*/, const float* c_prev, float* c_new, float* h_new,
+                  int M, int n, cudaStream_t s);
+int lstm_cell_bwd(const float* dh, const float* dh2 /*nullable, added*/, const float* dc_next, const float* gates,
+                  const float* c_prev, const float* c_new, float* dgates, float* dc_prev, int M, int n, cudaStream_t s);
+int add_inplace(float* dst, const float* src, long n, cudaStream_t s);
+
+}  // namespace marlc

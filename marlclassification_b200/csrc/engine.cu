@@ -1,0 +1,727 @@
+// Episode engine: flat parameter layout, workspace carving, and the host-side
+// orchestration of one rollout (forward), the fused loss and the BPTT sweep.
+// This file is the C ABI of libmarlc (see include/marlc.h).
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include <string>
+#include <vector>
+
+#include "../../include/marlc.h"
+#include "kernels.cuh"
+
+namespace marlc {
+
+int g_launch_count = 0;
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+struct ParamInfo {
+    std::string name;
+    int64_t offset;  // floats
+    int ndim;
+    int64_t shape[4];
+    int64_t numel;
+};
+struct BufInfo {
+    std::string name;
+    size_t offset, bytes;
+};
+
+}  // namespace marlc
+
+using namespace marlc;
+
+struct marlc_engine {
+    marlc_config cfg;
+    int M, TM, F, Kin, L;
+    CnnDesc cnn;  // dims; pointers filled at bind
+    int cnn_sz[MAX_CNN_LAYERS];  // cout*hout^2
+    std::vector<ParamInfo> params;
+    int64_t param_floats = 0;
+    std::vector<BufInfo> bufs;
+    size_t ws_bytes = 0;
+    char* ws = nullptr;
+    float* P = nullptr;
+    float* G = nullptr;
+    int last_launches = 0;
+
+    // ---- layout helpers
+    void add_param(const std::string& name, std::initializer_list<int64_t> shape) {
+        ParamInfo p;
+        p.name = "_ModelsWrapper__" + name;
+        p.ndim = (int)shape.size();
+        p.numel = 1;
+        int i = 0;
+        for (int k = 0; k < 4; ++k) p.shape[k] = 1;
+        for (auto s : shape) { p.shape[i++] = s; p.numel *= s; }
+        p.offset = param_floats;
+        param_floats += (p.numel + 63) / 64 * 64;  // 256-byte aligned slots (TMA / vector friendly)
+        params.push_back(p);
+    }
+    void add_buf(const std::string& name, size_t bytes) {
+        BufInfo b{name, ws_bytes, bytes};
+        ws_bytes += (bytes + 255) / 256 * 256;
+        bufs.push_back(b);
+    }
+    const ParamInfo* find_param(const std::string& suffix) const {
+        for (auto& p : params)
+            if (p.name == "_ModelsWrapper__" + suffix) return &p;
+        return nullptr;
+    }
+    float* prm(const std::string& suffix) const { return P + find_param(suffix)->offset; }
+    float* grd(const std::string& suffix) const { return G + find_param(suffix)->offset; }
+    template <typename T = float>
+    T* buf(const std::string& name) const {
+        for (auto& b : bufs)
+            if (b.name == name) return reinterpret_cast<T*>(ws + b.offset);
+        return nullptr;
+    }
+};
+
+static const char* CNN_PREFIX = "map_obs._Generic2dCnnModule__layers.";
+static const char* LSTM_B = "belief_unit._LSTMCellWrapper__lstm.";
+static const char* LSTM_A = "action_unit._LSTMCellWrapper__lstm.";
+
+static void add_block(marlc_engine* e, const std::string& name, int i, int n_in, int n_out, bool norm) {
+    e->add_param(name + "." + std::to_string(i) + ".weight", {n_out, n_in});
+    e->add_param(name + "." + std::to_string(i) + ".bias", {n_out});
+    if (norm) {
+        e->add_param(name + "." + std::to_string(i + 1) + ".weight", {n_out});
+        e->add_param(name + "." + std::to_string(i + 1) + ".bias", {n_out});
+    }
+}
+
+extern "C" int marlc_version(void) { return 1; }
+extern "C" const char* marlc_last_error(void) { return g_err; }
+
+extern "C" int marlc_engine_create(const marlc_config* c, marlc_engine** out) {
+    MARLC_CHECK(c && out, "null argument");
+    MARLC_CHECK(c->na >= 1 && c->nb >= 1 && c->T >= 1, "bad episode geometry na=%d nb=%d T=%d", c->na, c->nb, c->T);
+    MARLC_CHECK(c->f >= 1 && c->f < c->H && c->f < c->W, "window f=%d does not fit image %dx%d (need f < size)", c->f,
+                c->H, c->W);
+    MARLC_CHECK(c->n_actions >= 1 && c->n_actions <= MARLC_MAX_ACTIONS, "nb_action=%d out of range", c->n_actions);
+    MARLC_CHECK(c->cnn_layers >= 1 && c->cnn_layers <= MARLC_MAX_CNN_LAYERS, "cnn_layers=%d out of range", c->cnn_layers);
+    MARLC_CHECK(c->cnn_cin[0] <= c->C, "CNN wants %d input channels, image has %d", c->cnn_cin[0], c->C);
+    marlc_engine* e = new marlc_engine();
+    e->cfg = *c;
+    e->M = c->na * c->nb;
+    e->TM = e->M * c->T;
+    e->L = c->cnn_layers;
+    CnnDesc& d = e->cnn;
+    memset(&d, 0, sizeof(d));
+    d.L = e->L;
+    d.f = c->f;
+    d.img_c = c->C;
+    int h = c->f;
+    for (int l = 0; l < e->L; ++l) {
+        d.cin[l] = c->cnn_cin[l];
+        d.cout[l] = c->cnn_cout[l];
+        d.groups[l] = c->cnn_groups[l];
+        if (d.cout[l] % d.groups[l] != 0 || (l > 0 && d.cin[l] != d.cout[l - 1])) {
+            delete e;
+            MARLC_FAIL("inconsistent CNN description at layer %d", l);
+        }
+        d.hin[l] = h;
+        h = (h - 1) / 2 + 1;  // k=3, s=2, p=1 (vision.py:31-33,41-43)
+        d.hout[l] = h;
+        e->cnn_sz[l] = d.cout[l] * h * h;
+    }
+    d.out_size = e->cnn_sz[e->L - 1];
+    e->F = d.out_size;
+    e->Kin = e->F + c->n_m_o + c->n_d;
+
+    // ---- parameters, in the reference's registration order (models.py:55-76)
+    for (int l = 0; l < e->L; ++l) {
+        e->add_param(CNN_PREFIX + std::to_string(3 * l) + ".weight", {d.cout[l], d.cin[l], 3, 3});
+        e->add_param(CNN_PREFIX + std::to_string(3 * l) + ".bias", {d.cout[l]});
+        e->add_param(CNN_PREFIX + std::to_string(3 * l + 1) + ".weight", {d.cout[l]});
+        e->add_param(CNN_PREFIX + std::to_string(3 * l + 1) + ".bias", {d.cout[l]});
+    }
+    add_block(e, "map_pos", 0, 2, c->n_d, true);
+    add_block(e, "encode_msg", 0, c->n_b, 2 * c->n_m, true);
+    add_block(e, "encode_msg", 3, 2 * c->n_m, c->n_m, true);
+    add_block(e, "decode_msg", 0, c->n_m, 2 * c->n_m, true);
+    add_block(e, "decode_msg", 3, 2 * c->n_m, c->n_m_o, true);
+    for (int k = 0; k < 2; ++k) {
+        const std::string pre = k ? LSTM_A : LSTM_B;
+        const int n = k ? c->n_a : c->n_b;
+        e->add_param(pre + "weight_ih", {4 * n, e->Kin});
+        e->add_param(pre + "weight_hh", {4 * n, n});
+        e->add_param(pre + "bias_ih", {4 * n});
+        e->add_param(pre + "bias_hh", {4 * n});
+    }
+    add_block(e, "policy", 0, c->n_a, c->nl_a, true);
+    add_block(e, "policy", 3, c->nl_a, c->n_actions, false);
+    add_block(e, "critic", 0, c->n_a, c->nl_a, true);
+    add_block(e, "critic", 3, c->nl_a, 1, false);
+    add_block(e, "predict", 0, c->n_b, c->nl_b, true);
+    add_block(e, "predict", 3, c->nl_b, c->nb_class, false);
+
+    // ---- workspace
+    const size_t M = e->M, TM = e->TM, T = c->T, F4 = sizeof(float);
+    e->add_buf("rng_state", 2 * sizeof(uint64_t));
+    e->add_buf("pos_hist", (T + 1) * M * 2 * sizeof(int));
+    e->add_buf("npos", (T + 1) * M * 2 * F4);
+    e->add_buf("act", TM * sizeof(int));
+    e->add_buf("zero_act", M * sizeof(int64_t));  // must stay zero (workspace is zero-initialised by the caller)
+    e->add_buf("step_pos", TM * 2 * sizeof(int64_t));
+    for (int l = 0; l < e->L; ++l) e->add_buf("cnn_y" + std::to_string(l), TM * e->cnn_sz[l] * F4);
+    e->add_buf("U", TM * e->Kin * F4);
+    e->add_buf("msg", (T + 1) * M * c->n_m * F4);
+    e->add_buf("coll", TM * c->n_m * F4);
+    e->add_buf("dec_y1", TM * 2 * c->n_m * F4);
+    e->add_buf("dec_s1", TM * 2 * c->n_m * F4);
+    e->add_buf("dec_y2", TM * c->n_m_o * F4);
+    e->add_buf("pos_y", TM * c->n_d * F4);
+    e->add_buf("H", (T + 1) * M * c->n_b * F4);
+    e->add_buf("Cb", (T + 1) * M * c->n_b * F4);
+    e->add_buf("Hc", (T + 1) * M * c->n_a * F4);
+    e->add_buf("Cc", (T + 1) * M * c->n_a * F4);
+    e->add_buf("gates_b", TM * 4 * c->n_b * F4);
+    e->add_buf("gates_a", TM * 4 * c->n_a * F4);
+    e->add_buf("enc_y1", TM * 2 * c->n_m * F4);
+    e->add_buf("enc_s1", TM * 2 * c->n_m * F4);
+    e->add_buf("enc_y2", TM * c->n_m * F4);
+    e->add_buf("pol_y1", TM * c->nl_a * F4);
+    e->add_buf("pol_s1", TM * c->nl_a * F4);
+    e->add_buf("probs", TM * c->n_actions * F4);
+    e->add_buf("cri_y1", TM * c->nl_a * F4);
+    e->add_buf("cri_s1", TM * c->nl_a * F4);
+    e->add_buf("prd_y1", TM * c->nl_b * F4);
+    e->add_buf("prd_s1", TM * c->nl_b * F4);
+    e->add_buf("step_preds", TM * c->nb_class * F4);
+    e->add_buf("step_log_probas", TM * F4);
+    e->add_buf("step_values", TM * F4);
+    // loss
+    e->add_buf("rewards", TM * F4);
+    e->add_buf("returns", TM * F4);
+    e->add_buf("adv", TM * F4);
+    e->add_buf("loss_stats", 16 * sizeof(double));
+    e->add_buf("loss_out", 8 * F4);
+    e->add_buf("d_preds", TM * c->nb_class * F4);
+    e->add_buf("d_logp", TM * F4);
+    e->add_buf("d_values", TM * F4);
+    // backward
+    const size_t nl_max = (size_t)std::max(c->nl_a, c->nl_b);
+    e->add_buf("d_pol_logits", TM * c->n_actions * F4);
+    e->add_buf("scratchS", TM * nl_max * F4);
+    e->add_buf("scratchY", TM * nl_max * F4);
+    e->add_buf("dH_heads", TM * c->n_b * F4);
+    e->add_buf("dHc_heads", TM * c->n_a * F4);
+    e->add_buf("dgates_b", TM * 4 * c->n_b * F4);
+    e->add_buf("dgates_a", TM * 4 * c->n_a * F4);
+    e->add_buf("dU", TM * e->Kin * F4);
+    e->add_buf("d_enc_y2", TM * c->n_m * F4);
+    e->add_buf("d_enc_y1", TM * 2 * c->n_m * F4);
+    e->add_buf("d_dec_y2", TM * c->n_m_o * F4);
+    e->add_buf("d_dec_y1", TM * 2 * c->n_m * F4);
+    e->add_buf("d_pos_y", TM * c->n_d * F4);
+    e->add_buf("tmpS", M * 2 * c->n_m * F4);
+    e->add_buf("dcoll", M * c->n_m * F4);
+    e->add_buf("dmsg", M * c->n_m * F4);
+    e->add_buf("dh", M * c->n_b * F4);
+    e->add_buf("dc0", M * c->n_b * F4);
+    e->add_buf("dc1", M * c->n_b * F4);
+    e->add_buf("dhc", M * c->n_a * F4);
+    e->add_buf("dcc0", M * c->n_a * F4);
+    e->add_buf("dcc1", M * c->n_a * F4);
+    for (int l = 0; l < e->L; ++l) {
+        const size_t npos = (size_t)d.hout[l] * d.hout[l];
+        e->add_buf("cnn_dY" + std::to_string(l), TM * npos * d.cout[l] * F4);
+        e->add_buf("cnn_col" + std::to_string(l), TM * npos * d.cin[l] * 9 * F4);
+        e->add_buf("cnn_gnpart" + std::to_string(l), TM * 2 * d.cout[l] * F4);
+    }
+    *out = e;
+    return 0;
+}
+
+extern "C" void marlc_engine_destroy(marlc_engine* e) { delete e; }
+extern "C" int marlc_engine_param_count(const marlc_engine* e) { return (int)e->params.size(); }
+extern "C" int64_t marlc_engine_param_floats(const marlc_engine* e) { return e->param_floats; }
+extern "C" int marlc_engine_param_info(const marlc_engine* e, int idx, char* name, int64_t* offset, int* ndim,
+                                       int64_t* shape) {
+    MARLC_CHECK(idx >= 0 && idx < (int)e->params.size(), "param index %d out of range", idx);
+    const ParamInfo& p = e->params[idx];
+    strncpy(name, p.name.c_str(), 127);
+    name[127] = 0;
+    *offset = p.offset;
+    *ndim = p.ndim;
+    for (int k = 0; k < 4; ++k) shape[k] = p.shape[k];
+    return 0;
+}
+extern "C" size_t marlc_engine_workspace_bytes(const marlc_engine* e) { return e->ws_bytes; }
+extern "C" int marlc_engine_buffer(const marlc_engine* e, const char* name, size_t* offset, size_t* nbytes) {
+    for (auto& b : e->bufs)
+        if (b.name == name) {
+            *offset = b.offset;
+            *nbytes = b.bytes;
+            return 0;
+        }
+    MARLC_FAIL("unknown workspace buffer '%s'", name);
+}
+
+extern "C" int marlc_engine_bind(marlc_engine* e, void* workspace, float* params, float* grads) {
+    MARLC_CHECK(workspace && params, "bind: null workspace / params");
+    MARLC_CHECK(((uintptr_t)workspace & 255) == 0 && ((uintptr_t)params & 255) == 0, "bind: buffers must be 256-byte aligned");
+    e->ws = (char*)workspace;
+    e->P = params;
+    e->G = grads;
+    for (int l = 0; l < e->L; ++l) {
+        e->cnn.w[l] = e->prm(CNN_PREFIX + std::to_string(3 * l) + ".weight");
+        e->cnn.b[l] = e->prm(CNN_PREFIX + std::to_string(3 * l) + ".bias");
+        e->cnn.gn_w[l] = e->prm(CNN_PREFIX + std::to_string(3 * l + 1) + ".weight");
+        e->cnn.gn_b[l] = e->prm(CNN_PREFIX + std::to_string(3 * l + 1) + ".bias");
+    }
+    return 0;
+}
+
+__global__ void seed_kernel(uint64_t* st, uint64_t seed) { st[0] = seed; st[1] = 0; }
+extern "C" int marlc_engine_seed(marlc_engine* e, uint64_t seed, void* stream) {
+    MARLC_CHECK(e->ws, "engine not bound");
+    seed_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(e->buf<uint64_t>("rng_state"), seed);
+    MARLC_LAUNCH_CHECK();
+    return 0;
+}
+
+// Linear -> LN -> SiLU block forward on R rows (message.py:26-33 etc.)
+static int block_fwd(marlc_engine* e, const std::string& name, int i, const float* X, long ldx, int R, int n_in,
+                     int n_out, float* y_pre, float* S, long lds, cudaStream_t s) {
+    const std::string a = name + "." + std::to_string(i), b = name + "." + std::to_string(i + 1);
+    MARLC_TRY(gemm_nt(X, ldx, e->prm(a + ".weight"), n_in, e->prm(a + ".bias"), y_pre, n_out, R, n_out, n_in, 0, s));
+    MARLC_TRY(ln_silu_fwd(y_pre, n_out, e->prm(b + ".weight"), e->prm(b + ".bias"), S, lds, R, n_out, s));
+    return 0;
+}
+
+// One step of every network for all M rows (models.py:78-138) up to the policy
+// block-0 activations.  Slot t of the workspace receives everything backward needs.
+// Inputs are explicit so that the same code serves the fused episode (workspace
+// slots) and the stand-alone ModelsWrapper.forward (caller tensors).
+static int step_networks(marlc_engine* e, int t, const float* img, const int* pos, const float* patch,
+                         const float* msg_in, const float* npos_in, const float* h_in, const float* c_in,
+                         const float* hc_in, const float* cc_in, cudaStream_t s) {
+    const marlc_config& c = e->cfg;
+    const int M = e->M, Kin = e->Kin, F = e->F;
+    float* Ut = e->buf("U") + (size_t)t * M * Kin;
+    float* H = e->buf("H");
+    float* Cb = e->buf("Cb");
+    float* Hc = e->buf("Hc");
+    float* Cc = e->buf("Cc");
+    // b_t: gather + CNN straight into u_t[:, 0:F]                (models.py:92-94)
+    float* ysave[MAX_CNN_LAYERS];
+    for (int l = 0; l < e->L; ++l) ysave[l] = e->buf("cnn_y" + std::to_string(l)) + (size_t)t * M * e->cnn_sz[l];
+    MARLC_TRY(cnn_fwd(e->cnn, img, pos, patch, c.nb, c.H, c.W, M, ysave, Ut, Kin, s));
+    // d_bar_t: message mean + decoder into u_t[:, F:F+n_m_o]     (models.py:97-98)
+    float* coll = e->buf("coll") + (size_t)t * M * c.n_m;
+    MARLC_TRY(msg_mean(msg_in, coll, c.na, c.nb, c.n_m, s));
+    float* dec_s1 = e->buf("dec_s1") + (size_t)t * M * 2 * c.n_m;
+    MARLC_TRY(block_fwd(e, "decode_msg", 0, coll, c.n_m, M, c.n_m, 2 * c.n_m,
+                        e->buf("dec_y1") + (size_t)t * M * 2 * c.n_m, dec_s1, 2 * c.n_m, s));
+    MARLC_TRY(block_fwd(e, "decode_msg", 3, dec_s1, 2 * c.n_m, M, 2 * c.n_m, c.n_m_o,
+                        e->buf("dec_y2") + (size_t)t * M * c.n_m_o, Ut + F, Kin, s));
+    // lambda_t into u_t[:, F+n_m_o:]                             (models.py:101)
+    MARLC_TRY(pos_features_fwd(npos_in, e->prm("map_pos.0.weight"), e->prm("map_pos.0.bias"),
+                               e->prm("map_pos.1.weight"), e->prm("map_pos.1.bias"),
+                               e->buf("pos_y") + (size_t)t * M * c.n_d, Ut + F + c.n_m_o, Kin, M, c.n_d, s));
+    // both LSTM cells share u_t                                   (models.py:107-123)
+    float* gb = e->buf("gates_b") + (size_t)t * M * 4 * c.n_b;
+    float* ga = e->buf("gates_a") + (size_t)t * M * 4 * c.n_a;
+    GemmGroup gg;
+    memset(&gg, 0, sizeof(gg));
+    gg.count = 2;
+    for (int k = 0; k < 2; ++k) {
+        const std::string pre = k ? LSTM_A : LSTM_B;
+        const int n = k ? c.n_a : c.n_b;
+        GemmProblem& p = gg.p[k];
+        p.A = Ut; p.sam = Kin; p.sak = 1;
+        p.B = e->prm(pre + "weight_ih"); p.sbk = 1; p.sbn = Kin;
+        p.A2 = k ? hc_in : h_in; p.sam2 = n; p.sak2 = 1;
+        p.B2 = e->prm(pre + "weight_hh"); p.sbk2 = 1; p.sbn2 = n;
+        p.bias = e->prm(pre + "bias_ih"); p.bias2 = e->prm(pre + "bias_hh");
+        p.C = k ? ga : gb; p.ldc = 4 * n;
+        p.M = M; p.N = 4 * n; p.K = Kin; p.K2 = n;
+    }
+    MARLC_TRY(gemm_group(gg, s));
+    MARLC_TRY(lstm_cell_fwd(gb, c_in, Cb + (size_t)(t + 1) * M * c.n_b, H + (size_t)(t + 1) * M * c.n_b, M, c.n_b, s));
+    MARLC_TRY(lstm_cell_fwd(ga, cc_in, Cc + (size_t)(t + 1) * M * c.n_a, Hc + (size_t)(t + 1) * M * c.n_a, M, c.n_a, s));
+    // message for the next step                                   (models.py:114-116)
+    float* enc_s1 = e->buf("enc_s1") + (size_t)t * M * 2 * c.n_m;
+    MARLC_TRY(block_fwd(e, "encode_msg", 0, H + (size_t)(t + 1) * M * c.n_b, c.n_b, M, c.n_b, 2 * c.n_m,
+                        e->buf("enc_y1") + (size_t)t * M * 2 * c.n_m, enc_s1, 2 * c.n_m, s));
+    MARLC_TRY(block_fwd(e, "encode_msg", 3, enc_s1, 2 * c.n_m, M, 2 * c.n_m, c.n_m,
+                        e->buf("enc_y2") + (size_t)t * M * c.n_m, e->buf("msg") + (size_t)(t + 1) * M * c.n_m, c.n_m, s));
+    // policy block 0                                              (models.py:126-128)
+    MARLC_TRY(block_fwd(e, "policy", 0, Hc + (size_t)(t + 1) * M * c.n_a, c.n_a, M, c.n_a, c.nl_a,
+                        e->buf("pol_y1") + (size_t)t * M * c.nl_a, e->buf("pol_s1") + (size_t)t * M * c.nl_a, c.nl_a, s));
+    return 0;
+}
+
+// policy tail -> action -> transition  (policy.py:15-16, agent.py:51-61, environment.py:56-66)
+static int step_act(marlc_engine* e, int t, const int64_t* act_in, cudaStream_t s) {
+    const marlc_config& c = e->cfg;
+    const int M = e->M;
+    int* pos_hist = e->buf<int>("pos_hist");
+    PolicyActArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.s1 = e->buf("pol_s1") + (size_t)t * M * c.nl_a;
+    pa.W3 = e->prm("policy.3.weight");
+    pa.b3 = e->prm("policy.3.bias");
+    pa.act_in = act_in;
+    pa.rng_state = e->buf<uint64_t>("rng_state");
+    pa.pos_in = pos_hist + (size_t)t * M * 2;
+    pa.probs = e->buf("probs") + (size_t)t * M * c.n_actions;
+    pa.logp = e->buf("step_log_probas") + (size_t)t * M;
+    pa.act_out = e->buf<int>("act") + (size_t)t * M;
+    pa.pos_out = pos_hist + (size_t)(t + 1) * M * 2;
+    pa.step_pos = e->buf<int64_t>("step_pos") + (size_t)t * M * 2;
+    pa.npos_out = e->buf("npos") + (size_t)(t + 1) * M * 2;
+    for (int j = 0; j < c.n_actions; ++j) { pa.moves[2 * j] = c.actions[j][0]; pa.moves[2 * j + 1] = c.actions[j][1]; }
+    pa.M = M; pa.nl = c.nl_a; pa.nA = c.n_actions; pa.t = t; pa.f = c.f; pa.H = c.H; pa.W = c.W;
+    return policy_act(pa, s);
+}
+
+// critic and prediction heads on R rows starting at state slot 1 (models.py:131-134)
+static int value_pred_heads(marlc_engine* e, int R, cudaStream_t s) {
+    const marlc_config& c = e->cfg;
+    const int M = e->M;
+    MARLC_TRY(block_fwd(e, "critic", 0, e->buf("Hc") + (size_t)M * c.n_a, c.n_a, R, c.n_a, c.nl_a, e->buf("cri_y1"),
+                        e->buf("cri_s1"), c.nl_a, s));
+    MARLC_TRY(gemm_nt(e->buf("cri_s1"), c.nl_a, e->prm("critic.3.weight"), c.nl_a, e->prm("critic.3.bias"),
+                      e->buf("step_values"), 1, R, 1, c.nl_a, 0, s));
+    MARLC_TRY(block_fwd(e, "predict", 0, e->buf("H") + (size_t)M * c.n_b, c.n_b, R, c.n_b, c.nl_b, e->buf("prd_y1"),
+                        e->buf("prd_s1"), c.nl_b, s));
+    MARLC_TRY(gemm_nt(e->buf("prd_s1"), c.nl_b, e->prm("predict.3.weight"), c.nl_b, e->prm("predict.3.bias"),
+                      e->buf("step_preds"), c.nb_class, R, c.nb_class, c.nl_b, 0, s));
+    return 0;
+}
+
+extern "C" int marlc_episode_forward(marlc_engine* e, const float* img, const int64_t* pos0,
+                                     const float* const* hidden0, const int64_t* actions, void* stream) {
+    MARLC_CHECK(e && e->ws, "engine not bound");
+    MARLC_CHECK(img, "null image batch");
+    cudaStream_t s = (cudaStream_t)stream;
+    const marlc_config& c = e->cfg;
+    const int M = e->M, T = c.T;
+    const int start = g_launch_count;
+
+    int* pos_hist = e->buf<int>("pos_hist");
+    float* npos = e->buf("npos");
+    float* msg = e->buf("msg");
+    float* H = e->buf("H");
+    float* Cb = e->buf("Cb");
+    float* Hc = e->buf("Hc");
+    float* Cc = e->buf("Cc");
+    uint64_t* rng = e->buf<uint64_t>("rng_state");
+
+    EpisodeInitArgs ia;
+    ia.pos0 = pos0;
+    for (int k = 0; k < 4; ++k) ia.hidden0[k] = hidden0 ? hidden0[k] : nullptr;
+    ia.rng_state = rng;
+    ia.pos = pos_hist;
+    ia.npos = npos;
+    ia.hidden[0] = H; ia.hidden[1] = Cb; ia.hidden[2] = Hc; ia.hidden[3] = Cc;
+    ia.msg0 = msg;
+    ia.width[0] = ia.width[1] = c.n_b;
+    ia.width[2] = ia.width[3] = c.n_a;
+    ia.M = M; ia.n_m = c.n_m; ia.H = c.H; ia.W = c.W; ia.f = c.f;
+    MARLC_TRY(episode_init(ia, s));
+
+    for (int t = 0; t < T; ++t) {
+        MARLC_TRY(step_networks(e, t, img, pos_hist + (size_t)t * M * 2, nullptr, msg + (size_t)t * M * c.n_m,
+                                npos + (size_t)t * M * 2, H + (size_t)t * M * c.n_b, Cb + (size_t)t * M * c.n_b,
+                                Hc + (size_t)t * M * c.n_a, Cc + (size_t)t * M * c.n_a, s));
+        MARLC_TRY(step_act(e, t, actions ? actions + (size_t)t * M : nullptr, s));
+    }
+    // critic and prediction heads do not feed back into the trajectory: batch them
+    // over all T steps (R = T*M rows)
+    MARLC_TRY(value_pred_heads(e, e->TM, s));
+    MARLC_TRY(rng_advance(rng, s));
+    e->last_launches = g_launch_count - start;
+    return 0;
+}
+
+// ModelsWrapper.forward, models.py:78-138: one step on caller-provided tensors.
+// Outputs land in workspace slot 0/1: probs[0:M], step_values[0:M], step_preds[0:M],
+// msg[1], H[1], Cb[1], Hc[1], Cc[1].
+extern "C" int marlc_model_step(marlc_engine* e, const float* patch, const float* msg, const float* npos,
+                                const float* const* hidden, void* stream) {
+    MARLC_CHECK(e && e->ws, "engine not bound");
+    MARLC_CHECK(patch && msg && npos && hidden && hidden[0] && hidden[1] && hidden[2] && hidden[3],
+                "model_step: null input");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int start = g_launch_count;
+    MARLC_TRY(step_networks(e, 0, nullptr, nullptr, patch, msg, npos, hidden[0], hidden[1], hidden[2], hidden[3], s));
+    // the tail also needs an action to form log p[a]; use the all-zero index buffer
+    // (only probs are read back by ModelsWrapper.forward)
+    MARLC_TRY(step_act(e, 0, e->buf<int64_t>("zero_act"), s));
+    MARLC_TRY(value_pred_heads(e, e->M, s));
+    e->last_launches = g_launch_count - start;
+    return 0;
+}
+
+static LossArgs loss_args(marlc_engine* e, const int64_t* targets) {
+    LossArgs a;
+    a.preds = e->buf("step_preds");
+    a.logp = e->buf("step_log_probas");
+    a.values = e->buf("step_values");
+    a.targets = targets;
+    a.rewards = e->buf("rewards");
+    a.returns = e->buf("returns");
+    a.adv = e->buf("adv");
+    a.stats = e->buf<double>("loss_stats");
+    a.d_preds = e->buf("d_preds");
+    a.d_logp = e->buf("d_logp");
+    a.d_values = e->buf("d_values");
+    a.loss_out = e->buf("loss_out");
+    a.T = e->cfg.T; a.Na = e->cfg.na; a.Nb = e->cfg.nb; a.Nc = e->cfg.nb_class;
+    a.gamma = e->cfg.gamma;
+    return a;
+}
+
+extern "C" int marlc_loss_phase_a(marlc_engine* e, const int64_t* targets, void* stream) {
+    MARLC_CHECK(e && e->ws && targets, "loss: engine not bound / null targets");
+    const int start = g_launch_count;
+    MARLC_TRY(loss_phase_a(loss_args(e, targets), (cudaStream_t)stream));
+    e->last_launches = g_launch_count - start;
+    return 0;
+}
+extern "C" int marlc_loss_phase_b(marlc_engine* e, void* stream) {
+    MARLC_CHECK(e && e->ws, "loss: engine not bound");
+    const int start = g_launch_count;
+    MARLC_TRY(loss_phase_b(loss_args(e, nullptr), (cudaStream_t)stream));
+    e->last_launches = g_launch_count - start;
+    return 0;
+}
+
+// Backward of a Linear->LN->SiLU block given dS; leaves dY (pre-norm grad) in dY
+// and accumulates dgamma/dbeta/dbias.  Weight grads are done by the caller (batched).
+static int block_bwd_norm(marlc_engine* e, const std::string& name, int i, const float* dS, long ldds,
+                          const float* y_pre, int R, int n_out, float* dY, cudaStream_t s) {
+    const std::string a = name + "." + std::to_string(i), b = name + "." + std::to_string(i + 1);
+    return ln_silu_bwd(dS, ldds, y_pre, n_out, e->prm(b + ".weight"), e->prm(b + ".bias"), dY, n_out,
+                       e->grd(b + ".weight"), e->grd(b + ".bias"), e->grd(a + ".bias"), R, n_out, s);
+}
+
+// Head backward, batched over all T*M rows: final Linear (N outputs) <- Linear->LN->SiLU <- state
+static int head_bwd(marlc_engine* e, const std::string& name, const float* dOut, int N, const float* s1,
+                    const float* y1, const float* state, int n_state, int nl, float* dState, int accumulate_state,
+                    cudaStream_t s) {
+    const int TM = e->TM;
+    float* S = e->buf("scratchS");
+    float* Y = e->buf("scratchY");
+    MARLC_TRY(colsum_add(dOut, N, e->grd(name + ".3.bias"), TM, N, s));
+    MARLC_TRY(gemm_tn(dOut, N, s1, nl, e->grd(name + ".3.weight"), nl, TM, N, nl, 1, s));
+    MARLC_TRY(gemm_nn(dOut, N, e->prm(name + ".3.weight"), nl, S, nl, TM, N, nl, 0, s));
+    MARLC_TRY(block_bwd_norm(e, name, 0, S, nl, y1, TM, nl, Y, s));
+    MARLC_TRY(gemm_tn(Y, nl, state, n_state, e->grd(name + ".0.weight"), n_state, TM, nl, n_state, 1, s));
+    MARLC_TRY(gemm_nn(Y, nl, e->prm(name + ".0.weight"), n_state, dState, n_state, TM, nl, n_state, accumulate_state, s));
+    return 0;
+}
+
+extern "C" int marlc_episode_backward(marlc_engine* e, const float* img, int accumulate, void* stream) {
+    MARLC_CHECK(e && e->ws && e->G, "backward: engine not bound (need a grads buffer)");
+    MARLC_CHECK(img, "null image batch");
+    cudaStream_t s = (cudaStream_t)stream;
+    const marlc_config& c = e->cfg;
+    const int M = e->M, T = c.T, TM = e->TM, Kin = e->Kin, F = e->F;
+    const int start = g_launch_count;
+    if (!accumulate) MARLC_CUDA(cudaMemsetAsync(e->G, 0, sizeof(float) * (size_t)e->param_floats, s));
+
+    float* H = e->buf("H");
+    float* Cb = e->buf("Cb");
+    float* Hc = e->buf("Hc");
+    float* Cc = e->buf("Cc");
+    float* dU = e->buf("dU");
+
+    // ---- heads, batched over T*M rows (their gradients do not depend on the sweep)
+    MARLC_TRY(head_bwd(e, "predict", e->buf("d_preds"), c.nb_class, e->buf("prd_s1"), e->buf("prd_y1"),
+                       H + (size_t)M * c.n_b, c.n_b, c.nl_b, e->buf("dH_heads"), 0, s));
+    MARLC_TRY(policy_logit_grad(e->buf("d_logp"), e->buf("probs"), e->buf<int>("act"), e->buf("d_pol_logits"), TM,
+                                c.n_actions, s));
+    MARLC_TRY(head_bwd(e, "policy", e->buf("d_pol_logits"), c.n_actions, e->buf("pol_s1"), e->buf("pol_y1"),
+                       Hc + (size_t)M * c.n_a, c.n_a, c.nl_a, e->buf("dHc_heads"), 0, s));
+    MARLC_TRY(head_bwd(e, "critic", e->buf("d_values"), 1, e->buf("cri_s1"), e->buf("cri_y1"), Hc + (size_t)M * c.n_a,
+                       c.n_a, c.nl_a, e->buf("dHc_heads"), 1, s));
+
+    // ---- BPTT sweep
+    float* dh = e->buf("dh");
+    float* dhc = e->buf("dhc");
+    float* dc[2] = {e->buf("dc0"), e->buf("dc1")};
+    float* dcc[2] = {e->buf("dcc0"), e->buf("dcc1")};
+    float* dmsg = e->buf("dmsg");
+    float* tmpS = e->buf("tmpS");
+    MARLC_CUDA(cudaMemsetAsync(dh, 0, sizeof(float) * (size_t)M * c.n_b, s));
+    MARLC_CUDA(cudaMemsetAsync(dhc, 0, sizeof(float) * (size_t)M * c.n_a, s));
+    MARLC_CUDA(cudaMemsetAsync(dc[0], 0, sizeof(float) * (size_t)M * c.n_b, s));
+    MARLC_CUDA(cudaMemsetAsync(dcc[0], 0, sizeof(float) * (size_t)M * c.n_a, s));
+    int cur = 0;
+    for (int t = T - 1; t >= 0; --t) {
+        if (t < T - 1) {
+            // message produced at step t was consumed at t+1: encoder backward (models.py:114-116)
+            float* dy2 = e->buf("d_enc_y2") + (size_t)t * M * c.n_m;
+            float* dy1 = e->buf("d_enc_y1") + (size_t)t * M * 2 * c.n_m;
+            MARLC_TRY(block_bwd_norm(e, "encode_msg", 3, dmsg, c.n_m, e->buf("enc_y2") + (size_t)t * M * c.n_m, M,
+                                     c.n_m, dy2, s));
+            MARLC_TRY(gemm_nn(dy2, c.n_m, e->prm("encode_msg.3.weight"), 2 * c.n_m, tmpS, 2 * c.n_m, M, c.n_m,
+                              2 * c.n_m, 0, s));
+            MARLC_TRY(block_bwd_norm(e, "encode_msg", 0, tmpS, 2 * c.n_m,
+                                     e->buf("enc_y1") + (size_t)t * M * 2 * c.n_m, M, 2 * c.n_m, dy1, s));
+            MARLC_TRY(gemm_nn(dy1, 2 * c.n_m, e->prm("encode_msg.0.weight"), c.n_b, dh, c.n_b, M, 2 * c.n_m, c.n_b, 1, s));
+        }
+        float* dgb = e->buf("dgates_b") + (size_t)t * M * 4 * c.n_b;
+        float* dga = e->buf("dgates_a") + (size_t)t * M * 4 * c.n_a;
+        MARLC_TRY(lstm_cell_bwd(dh, e->buf("dH_heads") + (size_t)t * M * c.n_b, dc[cur],
+                                e->buf("gates_b") + (size_t)t * M * 4 * c.n_b, Cb + (size_t)t * M * c.n_b,
+                                Cb + (size_t)(t + 1) * M * c.n_b, dgb, dc[cur ^ 1], M, c.n_b, s));
+        MARLC_TRY(lstm_cell_bwd(dhc, e->buf("dHc_heads") + (size_t)t * M * c.n_a, dcc[cur],
+                                e->buf("gates_a") + (size_t)t * M * 4 * c.n_a, Cc + (size_t)t * M * c.n_a,
+                                Cc + (size_t)(t + 1) * M * c.n_a, dga, dcc[cur ^ 1], M, c.n_a, s));
+        cur ^= 1;
+        // input gradients: du = dg_b Wih_b + dg_a Wih_a ; dh = dg_b Whh_b ; dh^ = dg_a Whh_a
+        float* dUt = dU + (size_t)t * M * Kin;
+        GemmGroup gg;
+        memset(&gg, 0, sizeof(gg));
+        gg.count = 3;
+        {
+            GemmProblem& p = gg.p[0];
+            p.A = dgb; p.sam = 4 * c.n_b; p.sak = 1;
+            p.B = e->prm(std::string(LSTM_B) + "weight_ih"); p.sbk = Kin; p.sbn = 1;
+            p.A2 = dga; p.sam2 = 4 * c.n_a; p.sak2 = 1;
+            p.B2 = e->prm(std::string(LSTM_A) + "weight_ih"); p.sbk2 = Kin; p.sbn2 = 1;
+            p.C = dUt; p.ldc = Kin;
+            p.M = M; p.N = Kin; p.K = 4 * c.n_b; p.K2 = 4 * c.n_a;
+        }
+        {
+            GemmProblem& p = gg.p[1];
+            p.A = dgb; p.sam = 4 * c.n_b; p.sak = 1;
+            p.B = e->prm(std::string(LSTM_B) + "weight_hh"); p.sbk = c.n_b; p.sbn = 1;
+            p.C = dh; p.ldc = c.n_b;
+            p.M = M; p.N = c.n_b; p.K = 4 * c.n_b;
+        }
+        {
+            GemmProblem& p = gg.p[2];
+            p.A = dga; p.sam = 4 * c.n_a; p.sak = 1;
+            p.B = e->prm(std::string(LSTM_A) + "weight_hh"); p.sbk = c.n_a; p.sbn = 1;
+            p.C = dhc; p.ldc = c.n_a;
+            p.M = M; p.N = c.n_a; p.K = 4 * c.n_a;
+        }
+        MARLC_TRY(gemm_group(gg, s));
+        // decoder backward (models.py:97-98); at t == 0 the input message is the constant zero
+        float* ddy2 = e->buf("d_dec_y2") + (size_t)t * M * c.n_m_o;
+        float* ddy1 = e->buf("d_dec_y1") + (size_t)t * M * 2 * c.n_m;
+        MARLC_TRY(block_bwd_norm(e, "decode_msg", 3, dUt + F, Kin, e->buf("dec_y2") + (size_t)t * M * c.n_m_o, M,
+                                 c.n_m_o, ddy2, s));
+        MARLC_TRY(gemm_nn(ddy2, c.n_m_o, e->prm("decode_msg.3.weight"), 2 * c.n_m, tmpS, 2 * c.n_m, M, c.n_m_o,
+                          2 * c.n_m, 0, s));
+        MARLC_TRY(block_bwd_norm(e, "decode_msg", 0, tmpS, 2 * c.n_m, e->buf("dec_y1") + (size_t)t * M * 2 * c.n_m, M,
+                                 2 * c.n_m, ddy1, s));
+        if (t > 0) {
+            MARLC_TRY(gemm_nn(ddy1, 2 * c.n_m, e->prm("decode_msg.0.weight"), c.n_m, e->buf("dcoll"), c.n_m, M,
+                              2 * c.n_m, c.n_m, 0, s));
+            MARLC_TRY(msg_mean(e->buf("dcoll"), dmsg, c.na, c.nb, c.n_m, s));  // symmetric operator = own adjoint
+        }
+    }
+
+    // ---- weight gradients, batched over all T*M rows (reduction dim T*M)
+    for (int k = 0; k < 2; ++k) {
+        const std::string pre = k ? LSTM_A : LSTM_B;
+        const int n = k ? c.n_a : c.n_b;
+        const float* dg = e->buf(k ? "dgates_a" : "dgates_b");
+        MARLC_TRY(gemm_tn(dg, 4 * n, e->buf("U"), Kin, e->grd(pre + "weight_ih"), Kin, TM, 4 * n, Kin, 1, s));
+        MARLC_TRY(gemm_tn(dg, 4 * n, k ? Hc : H, n, e->grd(pre + "weight_hh"), n, TM, 4 * n, n, 1, s));
+        MARLC_TRY(colsum_add(dg, 4 * n, e->grd(pre + "bias_ih"), TM, 4 * n, s));
+        MARLC_TRY(colsum_add(dg, 4 * n, e->grd(pre + "bias_hh"), TM, 4 * n, s));
+    }
+    if (T > 1) {
+        const int R = (T - 1) * M;  // the last message is never consumed
+        MARLC_TRY(gemm_tn(e->buf("d_enc_y2"), c.n_m, e->buf("enc_s1"), 2 * c.n_m, e->grd("encode_msg.3.weight"),
+                          2 * c.n_m, R, c.n_m, 2 * c.n_m, 1, s));
+        MARLC_TRY(gemm_tn(e->buf("d_enc_y1"), 2 * c.n_m, H + (size_t)M * c.n_b, c.n_b, e->grd("encode_msg.0.weight"),
+                          c.n_b, R, 2 * c.n_m, c.n_b, 1, s));
+    }
+    MARLC_TRY(gemm_tn(e->buf("d_dec_y2"), c.n_m_o, e->buf("dec_s1"), 2 * c.n_m, e->grd("decode_msg.3.weight"),
+                      2 * c.n_m, TM, c.n_m_o, 2 * c.n_m, 1, s));
+    MARLC_TRY(gemm_tn(e->buf("d_dec_y1"), 2 * c.n_m, e->buf("coll"), c.n_m, e->grd("decode_msg.0.weight"), c.n_m, TM,
+                      2 * c.n_m, c.n_m, 1, s));
+    // position features (state.py:13-17)
+    MARLC_TRY(block_bwd_norm(e, "map_pos", 0, dU + F + c.n_m_o, Kin, e->buf("pos_y"), TM, c.n_d, e->buf("d_pos_y"), s));
+    MARLC_TRY(gemm_tn(e->buf("d_pos_y"), c.n_d, e->buf("npos"), 2, e->grd("map_pos.0.weight"), 2, TM, c.n_d, 2, 1, s));
+    // feature extractor
+    {
+        const float* ysave[MAX_CNN_LAYERS];
+        CnnBwdBuffers bb;
+        for (int l = 0; l < e->L; ++l) {
+            ysave[l] = e->buf("cnn_y" + std::to_string(l));
+            bb.dY[l] = e->buf("cnn_dY" + std::to_string(l));
+            bb.col[l] = e->buf("cnn_col" + std::to_string(l));
+            bb.gnpart[l] = e->buf("cnn_gnpart" + std::to_string(l));
+        }
+        MARLC_TRY(cnn_bwd(e->cnn, img, e->buf<int>("pos_hist"), c.nb, c.H, c.W, M, TM, ysave, dU, Kin, bb, s));
+        for (int l = 0; l < e->L; ++l) {
+            const CnnDesc& d = e->cnn;
+            const int npos = d.hout[l] * d.hout[l], kk = d.cin[l] * 9, co = d.cout[l];
+            const std::string cw = CNN_PREFIX + std::to_string(3 * l), gn = CNN_PREFIX + std::to_string(3 * l + 1);
+            MARLC_TRY(gemm_tn(bb.dY[l], co, bb.col[l], kk, e->grd(cw + ".weight"), kk, TM * npos, co, kk, 1, s));
+            MARLC_TRY(colsum_add(bb.dY[l], co, e->grd(cw + ".bias"), TM * npos, co, s));
+            MARLC_TRY(colsum_add(bb.gnpart[l], 2 * co, e->grd(gn + ".weight"), TM, co, s));
+            MARLC_TRY(colsum_add(bb.gnpart[l] + co, 2 * co, e->grd(gn + ".bias"), TM, co, s));
+        }
+    }
+    e->last_launches = g_launch_count - start;
+    return 0;
+}
+
+extern "C" int marlc_engine_last_launches(const marlc_engine* e) { return e->last_launches; }
+
+// ---- standalone operators ----------------------------------------------------
+extern "C" int marlc_patch_gather(const float* img, const int64_t* pos, float* obs, int Na, int B, int C, int H, int W,
+                                  int f, void* stream) {
+    MARLC_CHECK(img && pos && obs, "patch_gather: null pointer");
+    return patch_gather_i64(img, pos, obs, Na, B, C, H, W, f, (cudaStream_t)stream);
+}
+extern "C" int marlc_transition(int64_t* pos, const int64_t* act, const int64_t* table, int nA, int M, int f, int H,
+                                int W, float* norm_pos, int* err_flag, void* stream) {
+    MARLC_CHECK(pos && act && table, "transition: null pointer");
+    return transition_i64(pos, act, table, nA, M, f, H, W, norm_pos, err_flag, (cudaStream_t)stream);
+}
+extern "C" int marlc_normalized_positions(const int64_t* pos, float* out, int M, int H, int W, void* stream) {
+    MARLC_CHECK(pos && out, "normalized_positions: null pointer");
+    return normalized_positions_i64(pos, out, M, H, W, (cudaStream_t)stream);
+}
+extern "C" int marlc_linear(const float* X, const float* W, const float* bias, float* Y, int M, int N, int K,
+                            void* stream) {
+    return gemm_nt(X, K, W, K, bias, Y, N, M, N, K, 0, (cudaStream_t)stream);
+}
+extern "C" int marlc_ln_silu(const float* Y, const float* gamma, const float* beta, float* S, int R, int N,
+                             void* stream) {
+    return ln_silu_fwd(Y, N, gamma, beta, S, N, R, N, (cudaStream_t)stream);
+}
+extern "C" int marlc_msg_mean(const float* msg, float* out, int Na, int Nb, int n, void* stream) {
+    return msg_mean(msg, out, Na, Nb, n, (cudaStream_t)stream);
+}
+
+// _Generic2dCnnModule.forward, vision.py:47-49 on N stand-alone windows [N, img_c, f, f]
+extern "C" int marlc_cnn_forward(int layers, const int* cin, const int* cout, const int* groups, int f, int img_c,
+                                 const float* const* w, const float* const* b, const float* const* gn_w,
+                                 const float* const* gn_b, const float* patch, float* out, int N, void* stream) {
+    MARLC_CHECK(layers >= 1 && layers <= MAX_CNN_LAYERS, "cnn_forward: %d layers unsupported", layers);
+    MARLC_CHECK(patch && out, "cnn_forward: null pointer");
+    CnnDesc d;
+    memset(&d, 0, sizeof(d));
+    d.L = layers; d.f = f; d.img_c = img_c;
+    int h = f;
+    for (int l = 0; l < layers; ++l) {
+        d.cin[l] = cin[l]; d.cout[l] = cout[l]; d.groups[l] = groups[l];
+        d.hin[l] = h; h = (h - 1) / 2 + 1; d.hout[l] = h;
+        d.w[l] = w[l]; d.b[l] = b[l]; d.gn_w[l] = gn_w[l]; d.gn_b[l] = gn_b[l];
+    }
+    d.out_size = d.cout[layers - 1] * h * h;
+    return cnn_fwd(d, nullptr, nullptr, patch, 1, f, f, N, nullptr, out, d.out_size, (cudaStream_t)stream);
+}

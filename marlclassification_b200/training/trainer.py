@@ -1,0 +1,116 @@
+"""Actor-critic training loop (reference: training/trainer.py).
+
+Same constructor / ``train_epoch`` / ``eval_epoch`` / ``curr_step`` surface.  One
+iteration is: fused rollout -> fused loss (+ gradients w.r.t. the rollout
+outputs) -> hand-written BPTT into the flat gradient bucket -> (data-parallel:
+one NCCL all-reduce of the bucket) -> Adam.  The five logged scalars come back
+in ONE small device->host copy instead of the reference's 5+ ``.item()`` syncs.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, Optional
+
+import torch as th
+from tqdm import tqdm
+
+from ..core import EpisodeSampler
+from ..metrics import ConfusionMeter, LossMeter
+from ..networks import ModelsWrapper
+from ..parallel import DataParallelContext
+
+MetricLogger = Callable[[int, Dict[str, float]], None]
+
+
+class Trainer:
+    def __init__(
+        self,
+        model: ModelsWrapper,
+        nb_class: int,
+        learning_rate: float,
+        gamma: float,
+        metric_logger: Optional[MetricLogger] = None,
+        log_interval: int = 100,
+        meter_window_size: int = 64,
+        *,
+        dp: Optional[DataParallelContext] = None,
+    ) -> None:
+        self.__model = model
+        model.ensure_flat()
+        self.__optim = th.optim.Adam(model.parameters(), lr=learning_rate)  # trainer.py:33
+        self.__nb_class = nb_class
+        self.__gamma = gamma
+        self.__metric_logger = metric_logger
+        self.__log_interval = log_interval
+        self.__curr_step = 0
+        self.__dp = dp if dp is not None else DataParallelContext()
+        self.__conf_meter = ConfusionMeter(nb_class, window_size=meter_window_size)
+        self.__path_loss_meter = LossMeter(window_size=meter_window_size)
+        self.__error_meter = LossMeter(window_size=meter_window_size)
+        self.__actor_loss_meter = LossMeter(window_size=meter_window_size)
+        self.__critic_loss_meter = LossMeter(window_size=meter_window_size)
+
+    @property
+    def curr_step(self) -> int:
+        return self.__curr_step
+
+    def train_step(self, x: th.Tensor, y: th.Tensor, episode_sampler: EpisodeSampler, **inject) -> th.Tensor:
+        """One optimisation step (trainer.py:66-116).  Returns the device tensor
+        [loss, path, error, actor, critic] without synchronising."""
+        model = self.__model
+        eng = episode_sampler.engine_for(x, gamma=self.__gamma)
+        eng.forward(x, inject.get("pos0"), inject.get("hidden0"), inject.get("actions"))
+        eng.loss_phase_a(y)
+        self.__dp.all_reduce_stats(eng.loss_stats)  # global-batch standardize (functions.py:54-55)
+        eng.loss_phase_b()
+        eng.backward()
+        self.__dp.all_reduce_grads(model.flat_grads)
+        model.attach_grads()
+        self.__optim.step()
+        return eng.loss_out
+
+    def train_epoch(self, dataloader, epoch_index: int, episode_sampler: EpisodeSampler) -> None:
+        self.__model.train()
+        device = self.__model.device
+        tqdm_bar = tqdm(dataloader)
+        for x_train, y_train in tqdm_bar:
+            x_train = x_train.to(device, non_blocking=True)
+            y_train = y_train.to(device, non_blocking=True)
+            loss_out = self.train_step(x_train, y_train, episode_sampler)
+            eng = episode_sampler.engine_for(x_train, gamma=self.__gamma)
+            # meters: one packed D2H read of the five scalars
+            loss_item, path_item, error_item, actor_item, critic_item = loss_out[:5].tolist()
+            self.__conf_meter.add(eng.step_preds[-1].mean(dim=0), y_train)
+            self.__path_loss_meter.add(path_item)
+            self.__error_meter.add(error_item)
+            self.__actor_loss_meter.add(actor_item)
+            self.__critic_loss_meter.add(critic_item)
+            precs, recs = self.__conf_meter.precision(), self.__conf_meter.recall()
+            prec_rec = th.stack((precs.mean(), recs.mean())).tolist()
+            if self.__metric_logger is not None and self.__curr_step % self.__log_interval == 0:
+                self.__metric_logger(
+                    self.__curr_step,
+                    {"error": error_item, "path_loss": path_item, "loss": loss_item,
+                     "train_prec": prec_rec[0], "train_rec": prec_rec[1]},
+                )
+            tqdm_bar.set_description(
+                f"Epoch {epoch_index} - Train, train_prec = {prec_rec[0]:.3f}, train_rec = {prec_rec[1]:.3f}, "
+                f"error = {self.__error_meter.loss():.4f}, path = {self.__path_loss_meter.loss():.4f}, "
+                f"actor = {self.__actor_loss_meter.loss():.4f}, critic = {self.__critic_loss_meter.loss():.4f}"
+            )
+            self.__curr_step += 1
+
+    def eval_epoch(self, dataloader, epoch_index: int, episode_sampler: EpisodeSampler) -> ConfusionMeter:
+        self.__model.eval()
+        device = self.__model.device
+        conf_meter = ConfusionMeter(self.__nb_class, None)
+        with th.no_grad():
+            tqdm_bar = tqdm(dataloader)
+            for x_test, y_test in tqdm_bar:
+                x_test, y_test = x_test.to(device), y_test.to(device)
+                output = episode_sampler.run_episode_get_last_step(x_test)
+                conf_meter.add(output.prediction.mean(dim=0), y_test)  # mean over agents
+                pr = th.stack((conf_meter.precision().mean(), conf_meter.recall().mean())).tolist()
+                tqdm_bar.set_description(
+                    f"Epoch {epoch_index} - Eval, eval_prec = {pr[0]:.4f}, eval_rec = {pr[1]:.4f}"
+                )
+        return conf_meter

@@ -302,7 +302,7 @@ def classification_rewards(step_preds: torch.Tensor, targets: torch.Tensor) -> t
 def discounted_returns(rewards: torch.Tensor, gamma: float) -> torch.Tensor:
     """functions.py:35-51: flip-cumsum-flip of r*gamma^t, divided by gamma^t."""
     T = rewards.shape[0]
-    g = (gamma ** torch.arange(T, dtype=torch.float32)).view(T, *([1] * (rewards.dim() - 1)))
+    g = (gamma ** torch.arange(T, dtype=torch.float32, device=rewards.device)).view(T, *([1] * (rewards.dim() - 1)))
     return (rewards * g).flip(0).cumsum(0).flip(0) / g
 
 

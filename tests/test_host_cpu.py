@@ -1,0 +1,93 @@
+"""CPU-side checks: the C-ABI library loads and exports every declared symbol,
+the flat parameter layout matches the reference's state_dict (names + shapes),
+host-side logic (config, meters, returns helper) behaves like the reference."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+from marlclassification_b200 import _lib
+from marlclassification_b200.config import ModelConfig
+from tests.conftest import GOLDEN_NAMES, ROOT, load_golden
+
+
+def test_library_loads_and_exports_header_symbols():
+    lib = _lib.lib()
+    assert lib.marlc_version() >= 1
+    header = open(os.path.join(ROOT, "include", "marlc.h")).read()
+    declared = set(re.findall(r"\b(marlc_[a-z_0-9]+)\s*\(", header))
+    assert declared, "no declarations parsed from include/marlc.h"
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in marlc.h but not exported"
+    assert declared == set(_lib.exported_symbols())
+
+
+def test_engine_create_rejects_bad_geometry():
+    cfg = _lib.MarlcConfig()
+    handle = C.c_void_p()
+    assert _lib.lib().marlc_engine_create(C.byref(cfg), C.byref(handle)) != 0
+    assert b"geometry" in _lib.lib().marlc_last_error()
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_state_dict_matches_reference(name):
+    fx = load_golden(name)
+    model = ModelConfig(**fx["model_config"]).build_networks()
+    sd = model.state_dict()
+    assert list(sd) == list(fx["state_dict"])  # same keys, same order
+    for k, v in fx["state_dict"].items():
+        assert tuple(sd[k].shape) == tuple(v.shape), k
+    model.load_state_dict(fx["state_dict"])  # strict
+    layout, total = model._layout()
+    assert [n for n, _, _ in layout] == list(sd)
+    for n, off, shape in layout:
+        assert shape == tuple(sd[n].shape) and off % 64 == 0 and off + sd[n].numel() <= total
+
+
+def test_no_cpu_fallback():
+    from marlclassification_b200.core import Environment
+
+    env = Environment([[1, 0], [-1, 0]], 3)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        env.reset(torch.zeros(2, 1, 8, 8), 2)
+    model = ModelConfig(**load_golden("single_agent")["model_config"]).build_networks()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        model.ensure_flat()
+
+
+def test_marl_json_roundtrip(tmp_path):
+    fx = load_golden("mnist_ckpt")
+    cfg = ModelConfig(**fx["model_config"])
+    p = tmp_path / "marl.json"
+    cfg.save_marl_config(str(p))
+    assert ModelConfig.load_marl_config(str(p)) == cfg
+
+
+def test_functions_match_oracle():
+    from marlclassification_b200.training import functions as Fn
+    from oracle import marl_oracle as O
+
+    g = torch.Generator().manual_seed(3)
+    preds = torch.randn(5, 3, 4, 7, generator=g)
+    y = torch.randint(7, (4,), generator=g)
+    assert torch.allclose(Fn.classification_rewards(preds, y), O.classification_rewards(preds, y), atol=1e-6)
+    r = torch.randn(5, 3, 4, generator=g)
+    assert torch.allclose(Fn.discounted_returns(r, 0.9), O.discounted_returns(r, 0.9), atol=1e-5)
+    assert torch.allclose(Fn.standardize(r), O.standardize(r))
+
+
+def test_confusion_meter():
+    from marlclassification_b200.metrics import ConfusionMeter, LossMeter
+
+    cm = ConfusionMeter(3, None)
+    proba = torch.eye(3)
+    cm.add(proba, torch.tensor([0, 1, 1]))
+    assert cm.conf_mat().tolist() == [[1, 0, 0], [0, 1, 1], [0, 0, 0]]
+    assert torch.allclose(cm.precision(), torch.tensor([1.0, 1.0, 0.0]))
+    assert torch.allclose(cm.recall(), torch.tensor([1.0, 0.5, 0.0]))
+    lm = LossMeter(2)
+    for v in (1.0, 2.0, 3.0):
+        lm.add(v)
+    assert lm.loss() == 2.5
