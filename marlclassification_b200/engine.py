@@ -12,7 +12,7 @@ the reference's own loss code (``loss.backward()``) works unchanged.
 """
 from __future__ import annotations
 
-import ctypes as C
+import ctypes as ct
 from typing import Optional, Sequence
 
 import torch as th
@@ -60,7 +60,7 @@ class EpisodeEngine:
         self.cfg = build_config(model, na=na, nb=nb, T=T, C=C, H=H, W=W, actions=actions, gamma=gamma)
         self._L = _lib.lib()
         self._h = C_void_p()
-        _lib.check(self._L.marlc_engine_create(C.byref(self.cfg), C.byref(self._h)))
+        _lib.check(self._L.marlc_engine_create(ct.byref(self.cfg), ct.byref(self._h)))
         nbytes = self._L.marlc_engine_workspace_bytes(self._h)
         with th.cuda.device(self.device):
             self.workspace = th.zeros(nbytes, dtype=th.uint8, device=self.device)
@@ -99,8 +99,8 @@ class EpisodeEngine:
 
     # ---- workspace views ----------------------------------------------------------
     def view(self, name: str, dtype: th.dtype, shape: Sequence[int]) -> th.Tensor:
-        off, nb = C.c_size_t(), C.c_size_t()
-        _lib.check(self._L.marlc_engine_buffer(self._h, name.encode(), C.byref(off), C.byref(nb)))
+        off, nb = ct.c_size_t(), ct.c_size_t()
+        _lib.check(self._L.marlc_engine_buffer(self._h, name.encode(), ct.byref(off), ct.byref(nb)))
         n = 1
         for s in shape:
             n *= s
@@ -116,7 +116,7 @@ class EpisodeEngine:
             raise RuntimeError("model parameters were re-allocated after the engine was built; rebuild the engine")
 
     def seed(self, seed: int) -> None:
-        _lib.check(self._L.marlc_engine_seed(self._h, C.c_uint64(seed), self._stream()))
+        _lib.check(self._L.marlc_engine_seed(self._h, ct.c_uint64(seed), self._stream()))
 
     # ---- the three calls ------------------------------------------------------------
     def forward(self, img: th.Tensor, pos0: Optional[th.Tensor] = None,
@@ -141,7 +141,7 @@ class EpisodeEngine:
             d = self.model.dims
             for h, n in zip(hs, (d["n_b"], d["n_b"], d["n_a"], d["n_a"])):
                 assert tuple(h.shape) == (self.na, self.nb, n), (tuple(h.shape), n)
-            hid = (C.c_void_p * 4)(*[h.data_ptr() for h in hs])
+            hid = (ct.c_void_p * 4)(*[h.data_ptr() for h in hs])
             keep += hs
         act = None
         if actions is not None:
@@ -180,14 +180,14 @@ class EpisodeEngine:
         self.launches["backward"] = self._L.marlc_engine_last_launches(self._h)
 
     def model_step(self, patch, msg, npos, hidden) -> None:
-        hid = (C.c_void_p * 4)(*[h.data_ptr() for h in hidden])
+        hid = (ct.c_void_p * 4)(*[h.data_ptr() for h in hidden])
         self._keep = [patch, msg, npos, *hidden]
         _lib.check(self._L.marlc_model_step(self._h, patch.data_ptr(), msg.data_ptr(), npos.data_ptr(), hid,
                                             self._stream()))
 
 
 def C_void_p():
-    return C.c_void_p()
+    return ct.c_void_p()
 
 
 def get_engine(model, *, na, nb, T, C, H, W, actions, gamma=0.99) -> EpisodeEngine:
@@ -273,8 +273,8 @@ def cnn_forward(module, o_t: th.Tensor) -> th.Tensor:
     L = len(layers)
     seq = [m for m in module.modules() if isinstance(m, (th.nn.Conv2d, th.nn.GroupNorm))]
     convs, norms = seq[0::2], seq[1::2]
-    arr = lambda vals: (C.c_int * L)(*vals)  # noqa: E731
-    parr = lambda ts: (C.c_void_p * L)(*[t.data_ptr() for t in ts])  # noqa: E731
+    arr = lambda vals: (ct.c_int * L)(*vals)  # noqa: E731
+    parr = lambda ts: (ct.c_void_p * L)(*[t.data_ptr() for t in ts])  # noqa: E731
     w = [m.weight.detach().contiguous() for m in convs]
     b = [m.bias.detach().contiguous() for m in convs]
     gw = [m.weight.detach().contiguous() for m in norms]
