@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: one train iteration of the multi-agent episode
+(rollout + actor-critic loss + BPTT + Adam) on synthetic images.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2] [--impl ours|reference]
+
+Prints ONE JSON line (rank 0).  Metric = image-episodes/s (BASELINE.json);
+agent-steps/s = image-episodes/s * Na * T is reported beside it.
+
+* ``value``      inputs resident in HBM (pool of batches larger than L2, cycled),
+                 timed with CUDA events around each step, max over ranks.
+* ``e2e``        same step through the public API (Trainer.train_step) from PINNED
+                 HOST buffers: H2D of the batch + labels and D2H of the loss scalars
+                 inside the timed region, every step.
+* ``roofline``   the dominant kernel, timed alone with CUDA events.
+* ``cpu_baseline`` the CPU oracle port (reference algorithm incl. its mask +
+                 masked_select gather) on this box's host cores, bounded sample.
+* ``--impl reference``: the CPU port alone, all host threads, same metric/config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+README_ACTIONS = [[1, 0], [-1, 0], [0, 1], [0, -1]]
+WORKLOADS = {
+    # README.md:39-43 hyper-parameters
+    "c1": dict(desc="MNIST-shape 28x28, 3 agents, 5 steps, f=6, batch 32", ft="mnist", f=6, n_b=64, n_a=64, n_m=16,
+               n_m_o=24, n_d=8, nl=96, nc=10, na=3, T=5, C=3, H=28, W=28, B=32, actions=README_ACTIONS),
+    "c2": dict(desc="NWPU-RESISC45-shape 256x256 RGB, 16 agents, 16 steps, f=12, nb-class 45, batch 8", ft="resisc45",
+               f=12, n_b=256, n_a=256, n_m=64, n_m_o=96, n_d=16, nl=384, nc=45, na=16, T=16, C=3, H=256, W=256, B=8,
+               actions=README_ACTIONS),
+    "c3": dict(desc="AID-shape 600x600 RGB, 16 agents, 16 steps, f=24, nb-class 30, batch 8", ft="aid", f=24, n_b=256,
+               n_a=256, n_m=64, n_m_o=96, n_d=16, nl=320, nc=30, na=16, T=16, C=3, H=600, W=600, B=8,
+               actions=[[3, 0], [-3, 0], [0, 3], [0, -3]]),
+}
+WORKLOADS["c4"] = dict(WORKLOADS["c2"], desc="RESISC45-shape, global batch 256 sharded over the GPUs", B=256, strong=True)
+for _na in (16, 32, 64, 128, 256):
+    WORKLOADS[f"c5_na{_na}"] = dict(WORKLOADS["c2"], desc=f"agent sweep: {_na} agents, 32 steps, 256x256, batch 8",
+                                    na=_na, T=32)
+
+
+def model_config(w: dict) -> dict:
+    return dict(ft_extr_str=w["ft"], window_size=w["f"], hidden_size_belief=w["n_b"], hidden_size_action=w["n_a"],
+                hidden_size_msg=w["n_m"], hidden_size_msg_output=w["n_m_o"], hidden_size_state=w["n_d"], state_dim=2,
+                actions=w["actions"], nb_class=w["nc"], hidden_size_linear_belief=w["nl"],
+                hidden_size_linear_action=w["nl"])
+
+
+# ------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md "clocks DURING the timed region")
+# ------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int) -> None:
+        self.rows: list[list[str]] = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self) -> None:
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict | None:
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        if not sm:
+            return None
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------
+# CPU port (oracle) timing: cpu_baseline and --impl reference
+# ------------------------------------------------------------------------------------
+def cpu_port_iteration_fn(w: dict, nb: int, threads: int):
+    """Returns a closure running ONE train iteration of the reference algorithm on
+    the CPU (oracle port: rollout with the reference's mask+masked_select gather,
+    loss, autograd backward, Adam)."""
+    from oracle import marl_oracle as O
+
+    torch.set_num_threads(threads)
+    ocfg = O.OracleConfig(ft_extr=w["ft"], f=w["f"], n_b=w["n_b"], n_a=w["n_a"], n_m=w["n_m"], n_m_o=w["n_m_o"],
+                          n_d=w["n_d"], nb_class=w["nc"], nl_b=w["nl"], nl_a=w["nl"], actions=w["actions"])
+    params = {k: v.requires_grad_(True) for k, v in O.init_params(ocfg, seed=0).items()}
+    opt = torch.optim.Adam(list(params.values()), lr=1e-4)
+    g = torch.Generator().manual_seed(1234)
+    img = torch.rand(nb, w["C"], w["H"], w["W"], generator=g)
+    y = torch.randint(w["nc"], (nb,), generator=g)
+    na, T = w["na"], w["T"]
+
+    def one_iteration() -> float:
+        pos0 = torch.stack([torch.randint(w["H"] - w["f"], (na, nb)), torch.randint(w["W"] - w["f"], (na, nb))], -1)
+        hidden0 = [torch.randn(na, nb, n) for n in (ocfg.n_b, ocfg.n_b, ocfg.n_a, ocfg.n_a)]
+        ro = O.rollout(params, ocfg, img, pos0, hidden0, None, T, faithful_gather=True)
+        parts = O.a2c_loss(ro.step_preds, ro.step_log_probas, ro.step_values, y, 0.99)
+        opt.zero_grad()
+        parts.loss.backward()
+        opt.step()
+        return float(parts.loss)
+
+    return one_iteration
+
+
+def time_cpu_port(w: dict, nb: int, budget_s: float, max_iters: int, warmup: int = 1):
+    threads = os.cpu_count() or 1
+    fn = cpu_port_iteration_fn(w, nb, threads)
+    t0 = time.perf_counter()
+    for _ in range(warmup):
+        fn()
+    t_first = (time.perf_counter() - t0) / max(1, warmup)
+    iters = max(1, min(max_iters, int(budget_s / max(t_first, 1e-6))))
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        fn()
+    dt = (time.perf_counter() - t0) / iters
+    return dt, iters, threads
+
+
+# ------------------------------------------------------------------------------------
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--fp32", action="store_true", help="exact-fp32 FFMA GEMMs instead of tcgen05 TF32")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    w = WORKLOADS[args.workload]
+    strong = bool(w.get("strong"))
+    nb = w["B"] // world if strong else w["B"]
+    global_batch = nb * world
+    cfg_out = {"workload": f"{args.workload}: {w['desc']}", "agents": w["na"], "steps_per_episode": w["T"],
+               "window": w["f"], "image": [w["C"], w["H"], w["W"]], "batch_per_gpu": nb, "global_batch": global_batch,
+               "parallelism": f"dp{world}"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        dt, iters, threads = time_cpu_port(w, w["B"], budget_s=150.0, max_iters=args.steps,
+                                           warmup=min(args.warmup, 1))
+        val = w["B"] / dt
+        line = {"impl": "reference", "metric": "image_episodes_per_sec", "value": val, "unit": "image-episodes/s",
+                "agent_steps_per_sec": val * w["na"] * w["T"], "n_gpus": args.gpus, "steps": iters,
+                "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
+                "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": dict(cfg_out, batch_per_gpu=w["B"], global_batch=w["B"], parallelism="cpu"),
+                "cpu_baseline": {"value": val, "unit": "image-episodes/s", "cores": threads, "kind": "port",
+                                 "sample": f"{iters} full train iterations (rollout+loss+backward+Adam) of the workload "
+                                           f"at batch {w['B']}, after 1 warm-up"},
+                "e2e": {"value": val, "unit": "image-episodes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    # ---------------- ours ----------------
+    import torch.distributed as dist
+
+    from marlclassification_b200.config import ModelConfig
+    from marlclassification_b200.core import EpisodeSampler
+    from marlclassification_b200.parallel import DataParallelContext
+    from marlclassification_b200.training import Trainer
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    dp = DataParallelContext()
+
+    torch.manual_seed(0)
+    model, marl, env = ModelConfig(**model_config(w)).build_marl(w["na"])
+    model.use_tc = not args.fp32
+    model.to(dev)
+    dp.broadcast_params(model.flat_params)
+    sampler = EpisodeSampler(marl, env, w["T"], gamma=0.99)
+    trainer = Trainer(model, w["nc"], 1e-4, 0.99, dp=dp, cuda_graph=not args.no_graph)
+
+    # synthetic data: a pool of distinct batches larger than L2 (126 MB), cycled
+    g = torch.Generator().manual_seed(1234 + rank)
+    batch_bytes = nb * w["C"] * w["H"] * w["W"] * 4
+    pool_n = max(4, min(64, int(160e6 // batch_bytes) + 1))
+    host_pool = [torch.rand(nb, w["C"], w["H"], w["W"], generator=g).pin_memory() for _ in range(pool_n)]
+    host_y = [torch.randint(w["nc"], (nb,), generator=g).pin_memory() for _ in range(pool_n)]
+    dev_pool = [t.to(dev) for t in host_pool]
+    dev_y = [t.to(dev) for t in host_y]
+    cfg_out["l2"] = (f"inputs cycle through a pool of {pool_n} distinct batches = {pool_n * batch_bytes / 1e6:.0f} MB"
+                     + (" (> 126 MB L2)" if pool_n * batch_bytes > 126e6 else " (< L2: pool capped at 64 batches)"))
+    cfg_out["cuda_graph"] = not args.no_graph
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run(pool, ys, steps, read_back):
+        """Time `steps` steps with CUDA events on the current stream; returns total ms."""
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        t_wall = time.perf_counter()
+        for i in range(steps):
+            evs[i][0].record()
+            out = trainer.train_step(pool[i % len(pool)], ys[i % len(pool)], sampler)
+            if read_back:
+                scal = out[:5].to("cpu", non_blocking=False)  # D2H of the step's result (implies a sync)
+                assert scal.numel() == 5
+            evs[i][1].record()
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t_wall) * 1e3
+        dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+        return dev_ms, wall
+
+    # warm-up (also captures the CUDA graphs: 2 eager steps, then capture)
+    run(dev_pool, dev_y, args.warmup, False)
+    barrier()
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    dev_ms, wall_ms = run(dev_pool, dev_y, args.steps, False)
+    barrier()
+    # the step stream is saturated only if the host keeps ahead; report the slower of
+    # device-event time and wall time so host-bound runs are not flattered
+    step_ms = max(dev_ms, wall_ms) / args.steps
+    # e2e: pinned host inputs, loss read back, every step
+    run(host_pool, host_y, 3, True)
+    barrier()
+    e2e_dev_ms, e2e_wall_ms = run(host_pool, host_y, args.steps, True)
+    barrier()
+    clk = clocks.stop() if clocks else None
+    e2e_ms = max(e2e_dev_ms, e2e_wall_ms) / args.steps
+
+    t = torch.tensor([step_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    step_ms, e2e_ms = t.tolist()
+
+    eng = sampler.engine_for(dev_pool[0], gamma=0.99)
+    launches = eng.launches["forward"] + eng.launches["loss"] + eng.launches["backward"] + 2
+    if rank == 0:
+        val = global_batch / (step_ms * 1e-3)
+        e2e_val = global_batch / (e2e_ms * 1e-3)
+        line = {"metric": "image_episodes_per_sec", "value": val, "unit": "image-episodes/s",
+                "agent_steps_per_sec": val * w["na"] * w["T"], "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
+                "scaling": "strong" if strong else "weak", "vs_baseline": None,
+                "dtype": "f32" if args.fp32 else "tf32", "data": "synthetic", "config": cfg_out,
+                "e2e": {"value": e2e_val, "unit": "image-episodes/s", "ms_per_step": e2e_ms,
+                        "h2d_bytes_per_step": batch_bytes + nb * 8, "d2h_bytes_per_step": 20},
+                "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches, "clocks": clk}
+        try:
+            from bench_roofline import roofline_for
+
+            line["roofline"] = roofline_for(model, w, nb, dev)
+        except Exception as exc:  # keep the headline even if the micro-benchmark breaks
+            line["roofline"] = {"error": repr(exc)}
+        if world == 1 and not args.no_cpu_baseline:
+            dt, iters, threads = time_cpu_port(w, w["B"], budget_s=args.cpu_budget, max_iters=20)
+            line["cpu_baseline"] = {"value": w["B"] / dt, "unit": "image-episodes/s", "cores": threads, "kind": "port",
+                                    "sample": f"{iters} full train iterations of the same workload (batch {w['B']}) "
+                                              f"by the CPU oracle port, after 1 warm-up"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -50,6 +50,15 @@ int marlc_ln_silu(const float* Y, const float* gamma, const float* beta, float* 
 /* aggregate_messages, message.py:5-17. msg/out f32[Na,Nb,n]. */
 int marlc_msg_mean(const float* msg, float* out, int Na, int Nb, int n, void* stream);
 
+/* tcgen05 TF32 GEMM (TMA-fed, TMEM accumulators): C[M,N] (+)= A B^T (+ A2 B2^T) (+ bias).
+ * K-major operand: [M|N rows][K contiguous]; MN-major (a_mn/b_mn != 0): [K rows][M|N
+ * contiguous].  Pointers 16-byte aligned, leading dimensions multiples of 4.  This is
+ * the kernel behind nn.Linear / nn.LSTMCell forward (recurrent.py:30) and their
+ * input / weight gradients. */
+int marlc_tc_gemm(const float* A, int64_t lda, int a_mn, const float* B, int64_t ldb, int b_mn, const float* A2,
+                  int64_t lda2, const float* B2, int64_t ldb2, int K2, const float* bias, float* C, int64_t ldc,
+                  int M, int N, int K, int accumulate, int allow_split, void* stream);
+
 /* _Generic2dCnnModule.forward, vision.py:47-49: k x [conv3x3 s2 p1 -> GroupNorm ->
  * SiLU] -> flatten on N stand-alone windows patch f32[N,img_c,f,f] (the first
  * cin[0] channels are read) -> out f32[N, cout[k-1]*h_k^2].  w/b/gn_w/gn_b are
@@ -117,6 +126,12 @@ int marlc_loss_phase_b(marlc_engine* e, void* stream);
  * buffers; written by phase B or by the caller) into the flat grads buffer
  * (zeroed first unless accumulate != 0). img must be the forward's batch. */
 int marlc_episode_backward(marlc_engine* e, const float* img, int accumulate, void* stream);
+
+/* optim.step(), trainer.py:33,116: torch.optim.Adam semantics (no weight decay,
+ * no amsgrad) over the flat bucket; g is multiplied by grad_scale first (1/world
+ * under data parallelism).  `step` is a device int64 counter, incremented here. */
+int marlc_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                    float beta1, float beta2, float eps, float grad_scale, int64_t* step, void* stream);
 
 /* Number of kernels the last forward/backward call launched (for bench accounting). */
 int marlc_engine_last_launches(const marlc_engine* e);

@@ -40,6 +40,8 @@ _SIGS = {
     "marlc_linear": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "marlc_ln_silu": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _P]),
     "marlc_msg_mean": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "marlc_tc_gemm": (C.c_int, [_P, C.c_int64, C.c_int, _P, C.c_int64, C.c_int, _P, C.c_int64, _P, C.c_int64, C.c_int, _P,
+                                _P, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "marlc_cnn_forward": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.c_int,
                                     C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), _P, _P, C.c_int, _P]),
     "marlc_engine_create": (C.c_int, [C.POINTER(MarlcConfig), C.POINTER(_P)]),
@@ -57,6 +59,8 @@ _SIGS = {
     "marlc_loss_phase_a": (C.c_int, [_P, _P, _P]),
     "marlc_loss_phase_b": (C.c_int, [_P, _P]),
     "marlc_episode_backward": (C.c_int, [_P, _P, C.c_int, _P]),
+    "marlc_adam_step": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                  _P, _P]),
     "marlc_engine_last_launches": (C.c_int, [_P]),
 }
 

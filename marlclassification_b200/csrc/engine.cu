@@ -11,6 +11,7 @@
 
 #include "../../include/marlc.h"
 #include "kernels.cuh"
+#include "tc.cuh"
 
 namespace marlc {
 
@@ -291,11 +292,51 @@ extern "C" int marlc_engine_seed(marlc_engine* e, uint64_t seed, void* stream) {
     return 0;
 }
 
+
+// ---- GEMM dispatch: tcgen05 TF32 when enabled and TMA-addressable, else exact fp32 FFMA ----------
+static bool tc_worth(int m_out, int n_out, int k_red) { return n_out >= 16 && k_red >= 32 && m_out >= 1; }
+
+// Y[M,N] = X[M,K] W[N,K]^T + bias
+static int G_nt(const marlc_engine* e, const float* X, long ldx, const float* W, long ldw, const float* bias, float* Y,
+                long ldy, int M, int N, int K, int accumulate, cudaStream_t s) {
+    if (e->cfg.use_tc && tc_worth(M, N, K)) {
+        TcGemmArgs a;
+        a.A = tc_op(X, ldx); a.B = tc_op(W, ldw); a.K = K;
+        a.C = Y; a.ldc = ldy; a.M = M; a.N = N; a.bias = bias; a.accumulate = accumulate;
+        if (tc_operand_ok(a.A) && tc_operand_ok(a.B)) return tc_gemm(a, s);
+    }
+    return gemm_nt(X, ldx, W, ldw, bias, Y, ldy, M, N, K, accumulate, s);
+}
+// dX[M,K] (+)= dY[M,N] W[N,K]   (reduction over N; W is the MN-major B operand)
+static int G_nn(const marlc_engine* e, const float* dY, long lddy, const float* W, long ldw, float* dX, long lddx, int M,
+                int N, int K, int accumulate, cudaStream_t s) {
+    if (e->cfg.use_tc && tc_worth(M, K, N)) {
+        TcGemmArgs a;
+        a.A = tc_op(dY, lddy); a.B = tc_op(W, ldw, true); a.K = N;
+        a.C = dX; a.ldc = lddx; a.M = M; a.N = K; a.accumulate = accumulate;
+        a.allow_split = accumulate ? 0 : 1;
+        if (tc_operand_ok(a.A) && tc_operand_ok(a.B)) return tc_gemm(a, s);
+    }
+    return gemm_nn(dY, lddy, W, ldw, dX, lddx, M, N, K, accumulate, s);
+}
+// dW[N,K] += dY[R,N]^T X[R,K]   (reduction over rows R; both operands MN-major)
+static int G_tn(const marlc_engine* e, const float* dY, long lddy, const float* X, long ldx, float* dW, long lddw, int R,
+                int N, int K, cudaStream_t s) {
+    if (e->cfg.use_tc && tc_worth(N, K, R) && K >= 16) {
+        TcGemmArgs a;
+        a.A = tc_op(dY, lddy, true); a.B = tc_op(X, ldx, true); a.K = R;
+        a.C = dW; a.ldc = lddw; a.M = N; a.N = K; a.accumulate = 1;
+        a.allow_split = 1;
+        if (tc_operand_ok(a.A) && tc_operand_ok(a.B)) return tc_gemm(a, s);
+    }
+    return gemm_tn(dY, lddy, X, ldx, dW, lddw, R, N, K, 1, s);
+}
+
 // Linear -> LN -> SiLU block forward on R rows (message.py:26-33 etc.)
 static int block_fwd(marlc_engine* e, const std::string& name, int i, const float* X, long ldx, int R, int n_in,
                      int n_out, float* y_pre, float* S, long lds, cudaStream_t s) {
     const std::string a = name + "." + std::to_string(i), b = name + "." + std::to_string(i + 1);
-    MARLC_TRY(gemm_nt(X, ldx, e->prm(a + ".weight"), n_in, e->prm(a + ".bias"), y_pre, n_out, R, n_out, n_in, 0, s));
+    MARLC_TRY(G_nt(e, X, ldx, e->prm(a + ".weight"), n_in, e->prm(a + ".bias"), y_pre, n_out, R, n_out, n_in, 0, s));
     MARLC_TRY(ln_silu_fwd(y_pre, n_out, e->prm(b + ".weight"), e->prm(b + ".bias"), S, lds, R, n_out, s));
     return 0;
 }
@@ -333,24 +374,48 @@ static int step_networks(marlc_engine* e, int t, const float* img, const int* po
     // both LSTM cells share u_t                                   (models.py:107-123)
     float* gb = e->buf("gates_b") + (size_t)t * M * 4 * c.n_b;
     float* ga = e->buf("gates_a") + (size_t)t * M * 4 * c.n_a;
-    GemmGroup gg;
-    memset(&gg, 0, sizeof(gg));
-    gg.count = 2;
-    for (int k = 0; k < 2; ++k) {
-        const std::string pre = k ? LSTM_A : LSTM_B;
-        const int n = k ? c.n_a : c.n_b;
-        GemmProblem& p = gg.p[k];
-        p.A = Ut; p.sam = Kin; p.sak = 1;
-        p.B = e->prm(pre + "weight_ih"); p.sbk = 1; p.sbn = Kin;
-        p.A2 = k ? hc_in : h_in; p.sam2 = n; p.sak2 = 1;
-        p.B2 = e->prm(pre + "weight_hh"); p.sbk2 = 1; p.sbn2 = n;
-        p.bias = e->prm(pre + "bias_ih"); p.bias2 = e->prm(pre + "bias_hh");
-        p.C = k ? ga : gb; p.ldc = 4 * n;
-        p.M = M; p.N = 4 * n; p.K = Kin; p.K2 = n;
+    bool fused = false;
+    if (c.use_tc && c.n_a == c.n_b) {
+        TcLstmArgs la[2];
+        for (int k = 0; k < 2; ++k) {
+            const std::string pre = k ? LSTM_A : LSTM_B;
+            const int n = k ? c.n_a : c.n_b;
+            TcLstmArgs& a = la[k];
+            a.U = tc_op(Ut, Kin);
+            a.Hprev = tc_op(k ? hc_in : h_in, n);
+            a.Wih = e->prm(pre + "weight_ih"); a.Whh = e->prm(pre + "weight_hh");
+            a.bih = e->prm(pre + "bias_ih"); a.bhh = e->prm(pre + "bias_hh");
+            a.c_prev = k ? cc_in : c_in;
+            a.c_new = (k ? Cc : Cb) + (size_t)(t + 1) * M * n;
+            a.h_new = (k ? Hc : H) + (size_t)(t + 1) * M * n;
+            a.gates = k ? ga : gb;
+            a.M = M; a.Kin = Kin; a.n = n;
+        }
+        if (tc_lstm_supported(la[0]) && tc_lstm_supported(la[1])) {
+            MARLC_TRY(tc_lstm_pair(la[0], la[1], s));
+            fused = true;
+        }
     }
-    MARLC_TRY(gemm_group(gg, s));
-    MARLC_TRY(lstm_cell_fwd(gb, c_in, Cb + (size_t)(t + 1) * M * c.n_b, H + (size_t)(t + 1) * M * c.n_b, M, c.n_b, s));
-    MARLC_TRY(lstm_cell_fwd(ga, cc_in, Cc + (size_t)(t + 1) * M * c.n_a, Hc + (size_t)(t + 1) * M * c.n_a, M, c.n_a, s));
+    if (!fused) {
+        GemmGroup gg;
+        memset(&gg, 0, sizeof(gg));
+        gg.count = 2;
+        for (int k = 0; k < 2; ++k) {
+            const std::string pre = k ? LSTM_A : LSTM_B;
+            const int n = k ? c.n_a : c.n_b;
+            GemmProblem& p = gg.p[k];
+            p.A = Ut; p.sam = Kin; p.sak = 1;
+            p.B = e->prm(pre + "weight_ih"); p.sbk = 1; p.sbn = Kin;
+            p.A2 = k ? hc_in : h_in; p.sam2 = n; p.sak2 = 1;
+            p.B2 = e->prm(pre + "weight_hh"); p.sbk2 = 1; p.sbn2 = n;
+            p.bias = e->prm(pre + "bias_ih"); p.bias2 = e->prm(pre + "bias_hh");
+            p.C = k ? ga : gb; p.ldc = 4 * n;
+            p.M = M; p.N = 4 * n; p.K = Kin; p.K2 = n;
+        }
+        MARLC_TRY(gemm_group(gg, s));
+        MARLC_TRY(lstm_cell_fwd(gb, c_in, Cb + (size_t)(t + 1) * M * c.n_b, H + (size_t)(t + 1) * M * c.n_b, M, c.n_b, s));
+        MARLC_TRY(lstm_cell_fwd(ga, cc_in, Cc + (size_t)(t + 1) * M * c.n_a, Hc + (size_t)(t + 1) * M * c.n_a, M, c.n_a, s));
+    }
     // message for the next step                                   (models.py:114-116)
     float* enc_s1 = e->buf("enc_s1") + (size_t)t * M * 2 * c.n_m;
     MARLC_TRY(block_fwd(e, "encode_msg", 0, H + (size_t)(t + 1) * M * c.n_b, c.n_b, M, c.n_b, 2 * c.n_m,
@@ -397,8 +462,8 @@ static int value_pred_heads(marlc_engine* e, int R, cudaStream_t s) {
                       e->buf("step_values"), 1, R, 1, c.nl_a, 0, s));
     MARLC_TRY(block_fwd(e, "predict", 0, e->buf("H") + (size_t)M * c.n_b, c.n_b, R, c.n_b, c.nl_b, e->buf("prd_y1"),
                         e->buf("prd_s1"), c.nl_b, s));
-    MARLC_TRY(gemm_nt(e->buf("prd_s1"), c.nl_b, e->prm("predict.3.weight"), c.nl_b, e->prm("predict.3.bias"),
-                      e->buf("step_preds"), c.nb_class, R, c.nb_class, c.nl_b, 0, s));
+    MARLC_TRY(G_nt(e, e->buf("prd_s1"), c.nl_b, e->prm("predict.3.weight"), c.nl_b, e->prm("predict.3.bias"),
+                   e->buf("step_preds"), c.nb_class, R, c.nb_class, c.nl_b, 0, s));
     return 0;
 }
 
@@ -517,11 +582,11 @@ static int head_bwd(marlc_engine* e, const std::string& name, const float* dOut,
     float* S = e->buf("scratchS");
     float* Y = e->buf("scratchY");
     MARLC_TRY(colsum_add(dOut, N, e->grd(name + ".3.bias"), TM, N, s));
-    MARLC_TRY(gemm_tn(dOut, N, s1, nl, e->grd(name + ".3.weight"), nl, TM, N, nl, 1, s));
-    MARLC_TRY(gemm_nn(dOut, N, e->prm(name + ".3.weight"), nl, S, nl, TM, N, nl, 0, s));
+    MARLC_TRY(G_tn(e, dOut, N, s1, nl, e->grd(name + ".3.weight"), nl, TM, N, nl, s));
+    MARLC_TRY(G_nn(e, dOut, N, e->prm(name + ".3.weight"), nl, S, nl, TM, N, nl, 0, s));
     MARLC_TRY(block_bwd_norm(e, name, 0, S, nl, y1, TM, nl, Y, s));
-    MARLC_TRY(gemm_tn(Y, nl, state, n_state, e->grd(name + ".0.weight"), n_state, TM, nl, n_state, 1, s));
-    MARLC_TRY(gemm_nn(Y, nl, e->prm(name + ".0.weight"), n_state, dState, n_state, TM, nl, n_state, accumulate_state, s));
+    MARLC_TRY(G_tn(e, Y, nl, state, n_state, e->grd(name + ".0.weight"), n_state, TM, nl, n_state, s));
+    MARLC_TRY(G_nn(e, Y, nl, e->prm(name + ".0.weight"), n_state, dState, n_state, TM, nl, n_state, accumulate_state, s));
     return 0;
 }
 
@@ -569,11 +634,11 @@ extern "C" int marlc_episode_backward(marlc_engine* e, const float* img, int acc
             float* dy1 = e->buf("d_enc_y1") + (size_t)t * M * 2 * c.n_m;
             MARLC_TRY(block_bwd_norm(e, "encode_msg", 3, dmsg, c.n_m, e->buf("enc_y2") + (size_t)t * M * c.n_m, M,
                                      c.n_m, dy2, s));
-            MARLC_TRY(gemm_nn(dy2, c.n_m, e->prm("encode_msg.3.weight"), 2 * c.n_m, tmpS, 2 * c.n_m, M, c.n_m,
+            MARLC_TRY(G_nn(e, dy2, c.n_m, e->prm("encode_msg.3.weight"), 2 * c.n_m, tmpS, 2 * c.n_m, M, c.n_m,
                               2 * c.n_m, 0, s));
             MARLC_TRY(block_bwd_norm(e, "encode_msg", 0, tmpS, 2 * c.n_m,
                                      e->buf("enc_y1") + (size_t)t * M * 2 * c.n_m, M, 2 * c.n_m, dy1, s));
-            MARLC_TRY(gemm_nn(dy1, 2 * c.n_m, e->prm("encode_msg.0.weight"), c.n_b, dh, c.n_b, M, 2 * c.n_m, c.n_b, 1, s));
+            MARLC_TRY(G_nn(e, dy1, 2 * c.n_m, e->prm("encode_msg.0.weight"), c.n_b, dh, c.n_b, M, 2 * c.n_m, c.n_b, 1, s));
         }
         float* dgb = e->buf("dgates_b") + (size_t)t * M * 4 * c.n_b;
         float* dga = e->buf("dgates_a") + (size_t)t * M * 4 * c.n_a;
@@ -586,6 +651,27 @@ extern "C" int marlc_episode_backward(marlc_engine* e, const float* img, int acc
         cur ^= 1;
         // input gradients: du = dg_b Wih_b + dg_a Wih_a ; dh = dg_b Whh_b ; dh^ = dg_a Whh_a
         float* dUt = dU + (size_t)t * M * Kin;
+        bool tc_dx = false;
+        if (c.use_tc) {
+            TcGemmArgs a;
+            a.A = tc_op(dgb, 4 * c.n_b); a.B = tc_op(e->prm(std::string(LSTM_B) + "weight_ih"), Kin, true); a.K = 4 * c.n_b;
+            a.A2 = tc_op(dga, 4 * c.n_a); a.B2 = tc_op(e->prm(std::string(LSTM_A) + "weight_ih"), Kin, true); a.K2 = 4 * c.n_a;
+            a.C = dUt; a.ldc = Kin; a.M = M; a.N = Kin; a.allow_split = 1;
+            TcGemmArgs b;
+            b.A = tc_op(dgb, 4 * c.n_b); b.B = tc_op(e->prm(std::string(LSTM_B) + "weight_hh"), c.n_b, true); b.K = 4 * c.n_b;
+            b.C = dh; b.ldc = c.n_b; b.M = M; b.N = c.n_b; b.allow_split = 1;
+            TcGemmArgs d;
+            d.A = tc_op(dga, 4 * c.n_a); d.B = tc_op(e->prm(std::string(LSTM_A) + "weight_hh"), c.n_a, true); d.K = 4 * c.n_a;
+            d.C = dhc; d.ldc = c.n_a; d.M = M; d.N = c.n_a; d.allow_split = 1;
+            if (tc_operand_ok(a.A) && tc_operand_ok(a.B) && tc_operand_ok(a.A2) && tc_operand_ok(a.B2) &&
+                tc_operand_ok(b.B) && tc_operand_ok(d.B) && c.n_a >= 16 && c.n_b >= 16) {
+                MARLC_TRY(tc_gemm(a, s));
+                MARLC_TRY(tc_gemm(b, s));
+                MARLC_TRY(tc_gemm(d, s));
+                tc_dx = true;
+            }
+        }
+        if (!tc_dx) {
         GemmGroup gg;
         memset(&gg, 0, sizeof(gg));
         gg.count = 3;
@@ -613,17 +699,18 @@ extern "C" int marlc_episode_backward(marlc_engine* e, const float* img, int acc
             p.M = M; p.N = c.n_a; p.K = 4 * c.n_a;
         }
         MARLC_TRY(gemm_group(gg, s));
+        }
         // decoder backward (models.py:97-98); at t == 0 the input message is the constant zero
         float* ddy2 = e->buf("d_dec_y2") + (size_t)t * M * c.n_m_o;
         float* ddy1 = e->buf("d_dec_y1") + (size_t)t * M * 2 * c.n_m;
         MARLC_TRY(block_bwd_norm(e, "decode_msg", 3, dUt + F, Kin, e->buf("dec_y2") + (size_t)t * M * c.n_m_o, M,
                                  c.n_m_o, ddy2, s));
-        MARLC_TRY(gemm_nn(ddy2, c.n_m_o, e->prm("decode_msg.3.weight"), 2 * c.n_m, tmpS, 2 * c.n_m, M, c.n_m_o,
+        MARLC_TRY(G_nn(e, ddy2, c.n_m_o, e->prm("decode_msg.3.weight"), 2 * c.n_m, tmpS, 2 * c.n_m, M, c.n_m_o,
                           2 * c.n_m, 0, s));
         MARLC_TRY(block_bwd_norm(e, "decode_msg", 0, tmpS, 2 * c.n_m, e->buf("dec_y1") + (size_t)t * M * 2 * c.n_m, M,
                                  2 * c.n_m, ddy1, s));
         if (t > 0) {
-            MARLC_TRY(gemm_nn(ddy1, 2 * c.n_m, e->prm("decode_msg.0.weight"), c.n_m, e->buf("dcoll"), c.n_m, M,
+            MARLC_TRY(G_nn(e, ddy1, 2 * c.n_m, e->prm("decode_msg.0.weight"), c.n_m, e->buf("dcoll"), c.n_m, M,
                               2 * c.n_m, c.n_m, 0, s));
             MARLC_TRY(msg_mean(e->buf("dcoll"), dmsg, c.na, c.nb, c.n_m, s));  // symmetric operator = own adjoint
         }
@@ -634,25 +721,25 @@ extern "C" int marlc_episode_backward(marlc_engine* e, const float* img, int acc
         const std::string pre = k ? LSTM_A : LSTM_B;
         const int n = k ? c.n_a : c.n_b;
         const float* dg = e->buf(k ? "dgates_a" : "dgates_b");
-        MARLC_TRY(gemm_tn(dg, 4 * n, e->buf("U"), Kin, e->grd(pre + "weight_ih"), Kin, TM, 4 * n, Kin, 1, s));
-        MARLC_TRY(gemm_tn(dg, 4 * n, k ? Hc : H, n, e->grd(pre + "weight_hh"), n, TM, 4 * n, n, 1, s));
+        MARLC_TRY(G_tn(e, dg, 4 * n, e->buf("U"), Kin, e->grd(pre + "weight_ih"), Kin, TM, 4 * n, Kin, s));
+        MARLC_TRY(G_tn(e, dg, 4 * n, k ? Hc : H, n, e->grd(pre + "weight_hh"), n, TM, 4 * n, n, s));
         MARLC_TRY(colsum_add(dg, 4 * n, e->grd(pre + "bias_ih"), TM, 4 * n, s));
         MARLC_TRY(colsum_add(dg, 4 * n, e->grd(pre + "bias_hh"), TM, 4 * n, s));
     }
     if (T > 1) {
         const int R = (T - 1) * M;  // the last message is never consumed
-        MARLC_TRY(gemm_tn(e->buf("d_enc_y2"), c.n_m, e->buf("enc_s1"), 2 * c.n_m, e->grd("encode_msg.3.weight"),
-                          2 * c.n_m, R, c.n_m, 2 * c.n_m, 1, s));
-        MARLC_TRY(gemm_tn(e->buf("d_enc_y1"), 2 * c.n_m, H + (size_t)M * c.n_b, c.n_b, e->grd("encode_msg.0.weight"),
-                          c.n_b, R, 2 * c.n_m, c.n_b, 1, s));
+        MARLC_TRY(G_tn(e, e->buf("d_enc_y2"), c.n_m, e->buf("enc_s1"), 2 * c.n_m, e->grd("encode_msg.3.weight"),
+                          2 * c.n_m, R, c.n_m, 2 * c.n_m, s));
+        MARLC_TRY(G_tn(e, e->buf("d_enc_y1"), 2 * c.n_m, H + (size_t)M * c.n_b, c.n_b, e->grd("encode_msg.0.weight"),
+                          c.n_b, R, 2 * c.n_m, c.n_b, s));
     }
-    MARLC_TRY(gemm_tn(e->buf("d_dec_y2"), c.n_m_o, e->buf("dec_s1"), 2 * c.n_m, e->grd("decode_msg.3.weight"),
-                      2 * c.n_m, TM, c.n_m_o, 2 * c.n_m, 1, s));
-    MARLC_TRY(gemm_tn(e->buf("d_dec_y1"), 2 * c.n_m, e->buf("coll"), c.n_m, e->grd("decode_msg.0.weight"), c.n_m, TM,
-                      2 * c.n_m, c.n_m, 1, s));
+    MARLC_TRY(G_tn(e, e->buf("d_dec_y2"), c.n_m_o, e->buf("dec_s1"), 2 * c.n_m, e->grd("decode_msg.3.weight"),
+                      2 * c.n_m, TM, c.n_m_o, 2 * c.n_m, s));
+    MARLC_TRY(G_tn(e, e->buf("d_dec_y1"), 2 * c.n_m, e->buf("coll"), c.n_m, e->grd("decode_msg.0.weight"), c.n_m, TM,
+                      2 * c.n_m, c.n_m, s));
     // position features (state.py:13-17)
     MARLC_TRY(block_bwd_norm(e, "map_pos", 0, dU + F + c.n_m_o, Kin, e->buf("pos_y"), TM, c.n_d, e->buf("d_pos_y"), s));
-    MARLC_TRY(gemm_tn(e->buf("d_pos_y"), c.n_d, e->buf("npos"), 2, e->grd("map_pos.0.weight"), 2, TM, c.n_d, 2, 1, s));
+    MARLC_TRY(G_tn(e, e->buf("d_pos_y"), c.n_d, e->buf("npos"), 2, e->grd("map_pos.0.weight"), 2, TM, c.n_d, 2, s));
     // feature extractor
     {
         const float* ysave[MAX_CNN_LAYERS];
@@ -668,7 +755,7 @@ extern "C" int marlc_episode_backward(marlc_engine* e, const float* img, int acc
             const CnnDesc& d = e->cnn;
             const int npos = d.hout[l] * d.hout[l], kk = d.cin[l] * 9, co = d.cout[l];
             const std::string cw = CNN_PREFIX + std::to_string(3 * l), gn = CNN_PREFIX + std::to_string(3 * l + 1);
-            MARLC_TRY(gemm_tn(bb.dY[l], co, bb.col[l], kk, e->grd(cw + ".weight"), kk, TM * npos, co, kk, 1, s));
+            MARLC_TRY(G_tn(e, bb.dY[l], co, bb.col[l], kk, e->grd(cw + ".weight"), kk, TM * npos, co, kk, s));
             MARLC_TRY(colsum_add(bb.dY[l], co, e->grd(cw + ".bias"), TM * npos, co, s));
             MARLC_TRY(colsum_add(bb.gnpart[l], 2 * co, e->grd(gn + ".weight"), TM, co, s));
             MARLC_TRY(colsum_add(bb.gnpart[l] + co, 2 * co, e->grd(gn + ".bias"), TM, co, s));
@@ -724,4 +811,16 @@ extern "C" int marlc_cnn_forward(int layers, const int* cin, const int* cout, co
     }
     d.out_size = d.cout[layers - 1] * h * h;
     return cnn_fwd(d, nullptr, nullptr, patch, 1, f, f, N, nullptr, out, d.out_size, (cudaStream_t)stream);
+}
+
+// Tensor-core GEMM, exposed for unit tests: C[M,N] (+)= A.B^T (+ A2.B2^T) (+ bias).
+// a_mn / b_mn select MN-major operands ([K rows][M|N contiguous]) instead of K-major.
+extern "C" int marlc_tc_gemm(const float* A, int64_t lda, int a_mn, const float* B, int64_t ldb, int b_mn,
+                             const float* A2, int64_t lda2, const float* B2, int64_t ldb2, int K2, const float* bias,
+                             float* C, int64_t ldc, int M, int N, int K, int accumulate, int allow_split, void* stream) {
+    TcGemmArgs a;
+    a.A = tc_op(A, lda, a_mn != 0); a.B = tc_op(B, ldb, b_mn != 0); a.K = K;
+    if (K2 > 0) { a.A2 = tc_op(A2, lda2, a_mn != 0); a.B2 = tc_op(B2, ldb2, b_mn != 0); a.K2 = K2; }
+    a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.bias = bias; a.accumulate = accumulate; a.allow_split = allow_split;
+    return tc_gemm(a, (cudaStream_t)stream);
 }

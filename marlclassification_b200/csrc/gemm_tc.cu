@@ -1,0 +1,491 @@
+// Tensor-core GEMMs for sm_100a: TMA (cp.async.bulk.tensor) -> 128B-swizzled
+// shared memory -> tcgen05.mma kind::tf32 (fp32 operands read directly, fp32
+// accumulators in TMEM) -> tcgen05.ld epilogue.  Hand-written PTX; no CUTLASS.
+//
+//   D[M,N] (+)= sum_k A(m,k) B(n,k)  [+ second operand pair]  (+ bias)
+//
+// Operand majors (both supported for A and B, so no transposed copies exist):
+//   K-major : memory [rows = M or N][K contiguous]      (nn.Linear forward: X, W)
+//   MN-major: memory [K rows][M or N contiguous]        (dX = dY.W: B = W;  dW = dY^T.X: both)
+//
+// CTA = 192 threads: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc),
+// warps 2..5 = epilogue (one TMEM lane quarter each).  Tile 128 x BN x 32, STAGES-deep
+// mbarrier ring.  Epilogues: plain store / accumulate / split-K atomic add, and the
+// fused LSTM cell (gates i,f,g,o of one hidden unit live in the same CTA tile).
+#include <cuda.h>
+
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace marlc {
+
+constexpr int BM = 128;
+constexpr int BK = 32;  // floats = 128 bytes = one swizzle row
+constexpr int UMMA_K = 8;
+constexpr int TC_THREADS = 192;
+
+// ---------------------------------------------------------------------------------
+// host: tensor maps
+// ---------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// 3-D map over [slabs][rows][inner] fp32, box = [1][box_rows][32], 128B swizzle, zero OOB fill
+static int make_map(CUtensorMap* m, const float* ptr, long inner, long rows, long slabs, long ld, long slab_stride,
+                    int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    MARLC_CHECK(enc, "cuTensorMapEncodeTiled not available");
+    cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)slabs};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)(slabs > 1 ? slab_stride : rows * ld) * 4};
+    cuuint32_t box[3] = {32, (cuuint32_t)box_rows, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)ptr, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MARLC_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d): ptr=%p inner=%ld rows=%ld ld=%ld box_rows=%d",
+                (int)r, (const void*)ptr, inner, rows, ld, box_rows);
+    return 0;
+}
+
+bool tc_operand_ok(const TcOperand& o) {
+    return o.ptr && (((uintptr_t)o.ptr & 15) == 0) && (o.ld % 4 == 0) && (o.slab_stride % 4 == 0);
+}
+
+// ---------------------------------------------------------------------------------
+// device: PTX wrappers
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+#define TMEM_LD8(addr, r)                                                                             \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"            \
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), \
+                   "=r"(r[7])                                                                         \
+                 : "r"(addr))
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// smem matrix descriptor, 128B swizzle (cute::UMMA::SmemDescriptor bit layout)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// ---------------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------------
+enum { EPI_STORE = 0, EPI_LSTM = 1 };
+
+struct TcKernelParams {
+    CUtensorMap a1, b1, a2, b2;  // second pair unused when nk2 == 0
+    int nk1, nk2;                // K blocks of each pair
+    int slab_a1, slab_b1, slab_a2, slab_b2;
+    int M, N;
+    // EPI_STORE
+    float* C;
+    long ldc;
+    const float* bias;
+    const float* bias2;
+    int accumulate, splits;
+    // EPI_LSTM (N = 4*n; tile = HU hidden units x 4 gates)
+    const float* c_prev;
+    float* c_new;
+    float* h_new;
+    float* gates;
+    int n_hidden;
+};
+struct TcKernelParams2 {  // two independent problems in one launch (blockIdx.z)
+    TcKernelParams p[2];
+};
+
+template <int BN, int STAGES>
+struct TcSmem {
+    static constexpr int A_BYTES = BM * BK * 4;
+    static constexpr int B_BYTES = BN * BK * 4;
+    static constexpr int BYTES = STAGES * (A_BYTES + B_BYTES) + 1024;
+};
+
+template <int BN, bool A_MN, bool B_MN, int EPI, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_constant__ TcKernelParams2 pp) {
+    using S = TcSmem<BN, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + STAGES * S::A_BYTES;
+    __shared__ __align__(8) uint64_t full_bar[STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[STAGES];
+    __shared__ __align__(8) uint64_t tmem_full_bar;
+    __shared__ uint32_t tmem_base_smem;
+
+    const bool two = (EPI == EPI_LSTM);
+    const TcKernelParams& p = pp.p[two ? blockIdx.z : 0];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * BM;
+    const int n_tile = blockIdx.x;
+    // K-block range of this CTA (split-K over the concatenated list of both pairs)
+    const int nkb = p.nk1 + p.nk2;
+    int kb_begin = 0, kb_end = nkb;
+    if (EPI == EPI_STORE && p.splits > 1) {
+        const int per = (nkb + p.splits - 1) / p.splits;
+        kb_begin = blockIdx.z * per;
+        kb_end = min(nkb, kb_begin + per);
+    }
+    const int my_kb = max(0, kb_end - kb_begin);
+    constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
+                     "r"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 0) {
+        // ============================ TMA producer ============================
+        if (lane == 0) {
+            for (int i = 0; i < my_kb; ++i) {
+                const int s = i % STAGES, ph = (i / STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                mbar_expect_tx(&full_bar[s], S::A_BYTES + S::B_BYTES);
+                const int kb = kb_begin + i;
+                const bool second = kb >= p.nk1;
+                const int k0 = (second ? kb - p.nk1 : kb) * BK;
+                const CUtensorMap* ma = second ? &p.a2 : &p.a1;
+                const CUtensorMap* mb = second ? &p.b2 : &p.b1;
+                const int za = second ? p.slab_a2 : p.slab_a1, zb = second ? p.slab_b2 : p.slab_b1;
+                uint8_t* a_dst = sA + s * S::A_BYTES;
+                uint8_t* b_dst = sB + s * S::B_BYTES;
+                if (!A_MN) tma_load_3d(a_dst, ma, &full_bar[s], k0, m0, za);
+                else
+                    for (int j = 0; j < BM / 32; ++j) tma_load_3d(a_dst + j * 4096, ma, &full_bar[s], m0 + 32 * j, k0, za);
+                if (EPI == EPI_LSTM) {
+                    // gather the 4 gate row-blocks of HU hidden units: rows g*n + j0 .. +HU
+                    constexpr int HU = BN / 4;
+                    for (int g = 0; g < 4; ++g)
+                        tma_load_3d(b_dst + g * HU * 128, mb, &full_bar[s], k0, g * p.n_hidden + n_tile * HU, zb);
+                } else if (!B_MN) {
+                    tma_load_3d(b_dst, mb, &full_bar[s], k0, n_tile * BN, zb);
+                } else {
+                    for (int j = 0; j < BN / 32; ++j)
+                        tma_load_3d(b_dst + j * 4096, mb, &full_bar[s], n_tile * BN + 32 * j, k0, zb);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ============================ MMA issuer ============================
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) |
+                                   ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            for (int i = 0; i < my_kb; ++i) {
+                const int s = i % STAGES, ph = (i / STAGES) & 1;
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(sA + s * S::A_BYTES), b_addr = smem_u32(sB + s * S::B_BYTES);
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    // K-major: advance 32 B inside the swizzled 128 B row; SBO = 1024 (8 rows x 128 B)
+                    // MN-major: one 8-k-row group (1024 B) per MMA; LBO = 4096 between 32-float MN groups
+                    const uint64_t ad = A_MN ? make_desc(a_addr + k * 1024, 4096, 1024) : make_desc(a_addr + k * 32, 16, 1024);
+                    const uint64_t bd = B_MN ? make_desc(b_addr + k * 1024, 4096, 1024) : make_desc(b_addr + k * 32, 16, 1024);
+                    umma_tf32(tmem_base, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs retire
+            }
+            umma_commit(&tmem_full_bar);
+        }
+    } else {
+        // ============================ epilogue (warps 2..5) ============================
+        const int q = warp & 3;  // TMEM lane quarter this warp may touch
+        const int m = m0 + 32 * q + lane;
+        mbar_wait(&tmem_full_bar, 0);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + ((uint32_t)(32 * q) << 16);
+        if (EPI == EPI_STORE) {
+            const int nbase = n_tile * BN;
+            const bool vec = ((p.ldc & 3) == 0) && (((uintptr_t)p.C & 15) == 0);
+            const bool first_split = (p.splits <= 1) || (blockIdx.z == 0);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 8) {
+                uint32_t r[8];
+                if (my_kb > 0) { TMEM_LD8(trow + c0, r); tmem_ld_wait(); }
+                else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) r[j] = 0u;
+                }
+                if (m < p.M) {
+                    float v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int n = nbase + c0 + j;
+                        v[j] = __uint_as_float(r[j]);
+                        if (first_split && n < p.N) {
+                            if (p.bias) v[j] += p.bias[n];
+                            if (p.bias2) v[j] += p.bias2[n];
+                        }
+                    }
+                    float* crow = p.C + (long)m * p.ldc + nbase + c0;
+                    if (p.splits > 1) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (nbase + c0 + j < p.N) atomicAdd(crow + j, v[j]);
+                    } else if (vec && nbase + c0 + 8 <= p.N) {
+                        float4 lo = make_float4(v[0], v[1], v[2], v[3]), hi = make_float4(v[4], v[5], v[6], v[7]);
+                        if (p.accumulate) {
+                            const float4 o0 = *reinterpret_cast<float4*>(crow), o1 = *reinterpret_cast<float4*>(crow + 4);
+                            lo.x += o0.x; lo.y += o0.y; lo.z += o0.z; lo.w += o0.w;
+                            hi.x += o1.x; hi.y += o1.y; hi.z += o1.z; hi.w += o1.w;
+                        }
+                        *reinterpret_cast<float4*>(crow) = lo;
+                        *reinterpret_cast<float4*>(crow + 4) = hi;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (nbase + c0 + j < p.N) crow[j] = p.accumulate ? crow[j] + v[j] : v[j];
+                    }
+                }
+            }
+        } else {
+            // fused LSTM cell (recurrent.py:30): columns [g*HU + j] hold gate g of hidden unit j0 + j
+            constexpr int HU = BN / 4;
+            const int n = p.n_hidden, j0 = n_tile * HU;
+#pragma unroll 1
+            for (int jb = 0; jb < HU; jb += 8) {
+                uint32_t ri[8], rf[8], rg[8], ro[8];
+                TMEM_LD8(trow + 0 * HU + jb, ri);
+                TMEM_LD8(trow + 1 * HU + jb, rf);
+                TMEM_LD8(trow + 2 * HU + jb, rg);
+                TMEM_LD8(trow + 3 * HU + jb, ro);
+                tmem_ld_wait();
+                if (m < p.M) {
+                    const long off = (long)m * n + j0 + jb;
+                    const float4 cp0 = *reinterpret_cast<const float4*>(p.c_prev + off);
+                    const float4 cp1 = *reinterpret_cast<const float4*>(p.c_prev + off + 4);
+                    const float cp[8] = {cp0.x, cp0.y, cp0.z, cp0.w, cp1.x, cp1.y, cp1.z, cp1.w};
+                    float gi[8], gf[8], gc[8], go[8], cn[8], hn[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int col = j0 + jb + j;
+                        gi[j] = sigmoidf_(__uint_as_float(ri[j]) + p.bias[col] + p.bias2[col]);
+                        gf[j] = sigmoidf_(__uint_as_float(rf[j]) + p.bias[n + col] + p.bias2[n + col]);
+                        gc[j] = tanhf(__uint_as_float(rg[j]) + p.bias[2 * n + col] + p.bias2[2 * n + col]);
+                        go[j] = sigmoidf_(__uint_as_float(ro[j]) + p.bias[3 * n + col] + p.bias2[3 * n + col]);
+                        cn[j] = gf[j] * cp[j] + gi[j] * gc[j];
+                        hn[j] = go[j] * tanhf(cn[j]);
+                    }
+                    float* g_row = p.gates + (long)m * 4 * n + j0 + jb;
+                    auto st8 = [](float* dst, const float* v) {
+                        *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+                        *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                    };
+                    st8(g_row, gi); st8(g_row + n, gf); st8(g_row + 2 * n, gc); st8(g_row + 3 * n, go);
+                    st8(p.c_new + off, cn);
+                    st8(p.h_new + off, hn);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------------
+static int operand_map(CUtensorMap* m, const TcOperand& o, int mn_extent, int k_extent, int box_rows_kmajor) {
+    // K-major: [mn_extent rows][k_extent inner];  MN-major: [k_extent rows][mn_extent inner]
+    if (!o.mn_major) return make_map(m, o.ptr, k_extent, mn_extent, o.slabs, o.ld, o.slab_stride, box_rows_kmajor);
+    return make_map(m, o.ptr, mn_extent, k_extent, o.slabs, o.ld, o.slab_stride, 32);
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_store(const TcKernelParams2& kp, int gx, int gy, int gz, cudaStream_t s) {
+    constexpr int STAGES = BN >= 256 ? 3 : 4;
+    using S = TcSmem<BN, STAGES>;
+    auto kern = tc_gemm_kernel<BN, A_MN, B_MN, EPI_STORE, STAGES>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        MARLC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES));
+        attr_done = true;
+    }
+    kern<<<dim3(gx, gy, gz), TC_THREADS, S::BYTES, s>>>(kp);
+    MARLC_LAUNCH_CHECK();
+    return 0;
+}
+
+int tc_gemm(const TcGemmArgs& a, cudaStream_t s) {
+    MARLC_CHECK(tc_operand_ok(a.A) && tc_operand_ok(a.B), "tc_gemm: operand not TMA-addressable");
+    MARLC_CHECK(a.K > 0 && a.M > 0 && a.N > 0, "tc_gemm: empty problem");
+    const bool pair2 = a.K2 > 0;
+    if (pair2) {
+        MARLC_CHECK(tc_operand_ok(a.A2) && tc_operand_ok(a.B2), "tc_gemm: second operand pair not TMA-addressable");
+        MARLC_CHECK(a.A2.mn_major == a.A.mn_major && a.B2.mn_major == a.B.mn_major, "tc_gemm: operand pairs must share majors");
+    }
+    // tile width: keep enough CTAs in flight for small problems
+    const int mt = (a.M + BM - 1) / BM;
+    int BN = 128;
+    if (a.N <= 32) BN = 32;
+    else if (a.N <= 64 || mt * ((a.N + 127) / 128) < MARLC_SMS / 2) BN = 64;
+    TcKernelParams2 kp;
+    memset(&kp, 0, sizeof(kp));
+    TcKernelParams& p = kp.p[0];
+    MARLC_TRY(operand_map(&p.a1, a.A, a.M, a.K, BM));
+    MARLC_TRY(operand_map(&p.b1, a.B, a.N, a.K, BN));
+    p.nk1 = (a.K + BK - 1) / BK;
+    p.slab_a1 = a.A.slab; p.slab_b1 = a.B.slab;
+    if (pair2) {
+        MARLC_TRY(operand_map(&p.a2, a.A2, a.M, a.K2, BM));
+        MARLC_TRY(operand_map(&p.b2, a.B2, a.N, a.K2, BN));
+        p.nk2 = (a.K2 + BK - 1) / BK;
+        p.slab_a2 = a.A2.slab; p.slab_b2 = a.B2.slab;
+    }
+    p.M = a.M; p.N = a.N; p.C = a.C; p.ldc = a.ldc; p.bias = a.bias; p.bias2 = a.bias2;
+    p.accumulate = a.accumulate;
+    const int nt = (a.N + BN - 1) / BN, nkb = p.nk1 + p.nk2;
+    int splits = 1;
+    if (a.allow_split && mt * nt < MARLC_SMS) {
+        splits = min(max(1, nkb / 4), max(1, (2 * MARLC_SMS) / (mt * nt)));
+        // every split must own at least one K block
+        while (splits > 1 && ((nkb + splits - 1) / splits) * (splits - 1) >= nkb) --splits;
+    }
+    p.splits = splits;
+    if (splits > 1 && !a.accumulate) {
+        if (a.ldc == a.N) MARLC_CUDA(cudaMemsetAsync(a.C, 0, sizeof(float) * (size_t)a.M * a.N, s));
+        else MARLC_CUDA(cudaMemset2DAsync(a.C, sizeof(float) * a.ldc, 0, sizeof(float) * a.N, a.M, s));
+    }
+#define DISPATCH(BNv)                                                                     \
+    if (a.A.mn_major) {                                                                   \
+        if (a.B.mn_major) return launch_store<BNv, true, true>(kp, nt, mt, splits, s);    \
+        return launch_store<BNv, true, false>(kp, nt, mt, splits, s);                     \
+    } else {                                                                              \
+        if (a.B.mn_major) return launch_store<BNv, false, true>(kp, nt, mt, splits, s);   \
+        return launch_store<BNv, false, false>(kp, nt, mt, splits, s);                    \
+    }
+    if (BN == 32) { DISPATCH(32) }
+    if (BN == 64) { DISPATCH(64) }
+    DISPATCH(128)
+#undef DISPATCH
+}
+
+template <int BN>
+static int launch_lstm(const TcKernelParams2& kp, int gx, int gy, cudaStream_t s) {
+    constexpr int STAGES = 4;
+    using S = TcSmem<BN, STAGES>;
+    auto kern = tc_gemm_kernel<BN, false, false, EPI_LSTM, STAGES>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        MARLC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES));
+        attr_done = true;
+    }
+    kern<<<dim3(gx, gy, 2), TC_THREADS, S::BYTES, s>>>(kp);
+    MARLC_LAUNCH_CHECK();
+    return 0;
+}
+
+bool tc_lstm_supported(const TcLstmArgs& a) {
+    return tc_operand_ok(a.U) && tc_operand_ok(a.Hprev) && (((uintptr_t)a.Wih | (uintptr_t)a.Whh) & 15) == 0 &&
+           a.Kin % 4 == 0 && a.n % 8 == 0 && a.n >= 8 && (((uintptr_t)a.c_prev | (uintptr_t)a.c_new | (uintptr_t)a.h_new |
+           (uintptr_t)a.gates) & 15) == 0;
+}
+
+int tc_lstm_pair(const TcLstmArgs& c0, const TcLstmArgs& c1, cudaStream_t s) {
+    MARLC_CHECK(tc_lstm_supported(c0) && tc_lstm_supported(c1), "tc_lstm_pair: unsupported shapes / alignment");
+    MARLC_CHECK(c0.M == c1.M, "tc_lstm_pair: row counts differ");
+    // hidden units per CTA: small tiles when M is small (more CTAs), 32 when rows are plentiful
+    const int mt = (c0.M + BM - 1) / BM;
+    int HU = mt >= 8 ? 32 : (mt >= 2 ? 16 : 8);
+    while (HU > 8 && (c0.n % HU != 0 || c1.n % HU != 0)) HU >>= 1;
+    MARLC_CHECK(c0.n % HU == 0 && c1.n % HU == 0, "tc_lstm_pair: hidden size not a multiple of %d", HU);
+    TcKernelParams2 kp;
+    memset(&kp, 0, sizeof(kp));
+    const TcLstmArgs* cs[2] = {&c0, &c1};
+    int gx = 0;
+    for (int k = 0; k < 2; ++k) {
+        const TcLstmArgs& c = *cs[k];
+        TcKernelParams& p = kp.p[k];
+        MARLC_TRY(make_map(&p.a1, c.U.ptr, c.Kin, c.M, c.U.slabs, c.U.ld, c.U.slab_stride, BM));
+        MARLC_TRY(make_map(&p.b1, c.Wih, c.Kin, 4 * c.n, 1, c.Kin, 0, HU));
+        MARLC_TRY(make_map(&p.a2, c.Hprev.ptr, c.n, c.M, c.Hprev.slabs, c.Hprev.ld, c.Hprev.slab_stride, BM));
+        MARLC_TRY(make_map(&p.b2, c.Whh, c.n, 4 * c.n, 1, c.n, 0, HU));
+        p.nk1 = (c.Kin + BK - 1) / BK;
+        p.nk2 = (c.n + BK - 1) / BK;
+        p.slab_a1 = c.U.slab; p.slab_a2 = c.Hprev.slab;
+        p.M = c.M; p.N = 4 * c.n;
+        p.bias = c.bih; p.bias2 = c.bhh;
+        p.c_prev = c.c_prev; p.c_new = c.c_new; p.h_new = c.h_new; p.gates = c.gates;
+        p.n_hidden = c.n;
+        p.splits = 1;
+        gx = max(gx, c.n / HU);
+    }
+    MARLC_CHECK(c0.n == c1.n, "tc_lstm_pair: the two cells must have the same hidden size (got %d, %d)", c0.n, c1.n);
+    if (HU == 8) return launch_lstm<32>(kp, gx, mt, s);
+    if (HU == 16) return launch_lstm<64>(kp, gx, mt, s);
+    return launch_lstm<128>(kp, gx, mt, s);
+}
+
+}  // namespace marlc

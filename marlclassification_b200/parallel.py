@@ -47,6 +47,11 @@ class DataParallelContext:
             dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM, group=self.group)
             flat_grads.mul_(1.0 / self.world_size)
 
+    def all_reduce_grads_sum(self, flat_grads: th.Tensor) -> None:
+        """Sum only; the 1/world scale is folded into the fused Adam (grad_scale)."""
+        if self.enabled:
+            dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM, group=self.group)
+
     def broadcast_params(self, flat_params: th.Tensor, src: int = 0) -> None:
         if self.enabled:
             dist.broadcast(flat_params, src=src, group=self.group)

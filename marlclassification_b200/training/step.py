@@ -1,0 +1,102 @@
+"""One optimisation step for a fixed episode geometry, replayed as CUDA graphs.
+
+The step is   rollout -> loss phase A -> [all-reduce 3 doubles] -> loss phase B
+-> BPTT -> [all-reduce flat grads] -> fused Adam.   Everything between the
+collectives is one captured graph (the engine never allocates or synchronises),
+so a 16-step episode costs a handful of host calls instead of ~10^4 launches.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch as th
+
+from ..engine import EpisodeEngine
+from ..parallel import DataParallelContext
+from .optim import FlatAdam
+
+
+class TrainStep:
+    def __init__(self, engine: EpisodeEngine, optim: FlatAdam, dp: Optional[DataParallelContext] = None,
+                 use_graph: bool = True) -> None:
+        self.engine, self.optim = engine, optim
+        self.dp = dp if dp is not None else DataParallelContext()
+        self.use_graph = use_graph
+        dev = engine.device
+        self.static_img = th.zeros(engine.nb, engine.C, engine.H, engine.W, dtype=th.float32, device=dev)
+        self.static_y = th.zeros(engine.nb, dtype=th.int64, device=dev)
+        self._graphs: Optional[list] = None
+        self._warm = 0
+
+    # ---- the segments between collectives -----------------------------------------
+    def _seg_forward(self) -> None:
+        self.engine.forward(self.static_img)
+        self.engine.loss_phase_a(self.static_y)
+
+    def _seg_backward(self) -> None:
+        self.engine.loss_phase_b()
+        self.engine.backward(self.static_img)
+
+    def _seg_update(self) -> None:
+        self.optim.step(1.0 / self.dp.world_size)
+
+    def _segments(self):
+        if self.dp.enabled:
+            return [self._seg_forward, self._seg_backward, self._seg_update]
+        return [lambda: (self._seg_forward(), self._seg_backward(), self._seg_update())]
+
+    def _capture(self) -> None:
+        graphs = []
+        for seg in self._segments():
+            g = th.cuda.CUDAGraph()
+            with th.cuda.graph(g):
+                seg()
+            graphs.append(g)
+        self._graphs = graphs
+
+    @property
+    def launches_per_step(self) -> int:
+        l = self.engine.launches
+        return l["forward"] + l["loss"] + l["backward"] + 2  # + Adam (2 kernels)
+
+    def run_static(self) -> th.Tensor:
+        """Run one step on whatever is in static_img / static_y."""
+        eng, dp = self.engine, self.dp
+        if self.use_graph and self._graphs is None and self._warm >= 2:
+            self._capture()
+        if self._graphs is not None:
+            segs = [g.replay for g in self._graphs]
+        else:
+            segs = self._segments()
+            self._warm += 1
+        if dp.enabled:
+            segs[0]()
+            dp.all_reduce_stats(eng.loss_stats)
+            segs[1]()
+            dp.all_reduce_grads_sum(eng.model.flat_grads)
+            segs[2]()
+        else:
+            segs[0]()
+        return eng.loss_out
+
+    def __call__(self, img: th.Tensor, y: th.Tensor, **inject) -> th.Tensor:
+        """img / y may live on the host (pinned -> async H2D) or on the device."""
+        if inject.get("pos0") is not None or inject.get("hidden0") is not None or inject.get("actions") is not None:
+            return self._run_injected(img, y, inject)
+        self.static_img.copy_(img, non_blocking=True)
+        self.static_y.copy_(y, non_blocking=True)
+        return self.run_static()
+
+    def _run_injected(self, img, y, inject) -> th.Tensor:
+        """Parity path: explicit draws, eager (pointers differ per call)."""
+        eng, dp = self.engine, self.dp
+        self.static_img.copy_(img, non_blocking=True)
+        self.static_y.copy_(y, non_blocking=True)
+        eng.forward(self.static_img, inject.get("pos0"), inject.get("hidden0"), inject.get("actions"))
+        eng.loss_phase_a(self.static_y)
+        dp.all_reduce_stats(eng.loss_stats)
+        eng.loss_phase_b()
+        eng.backward(self.static_img)
+        dp.all_reduce_grads_sum(eng.model.flat_grads)
+        self._seg_update()
+        return eng.loss_out

@@ -17,6 +17,8 @@ from ..core import EpisodeSampler
 from ..metrics import ConfusionMeter, LossMeter
 from ..networks import ModelsWrapper
 from ..parallel import DataParallelContext
+from .optim import FlatAdam
+from .step import TrainStep
 
 MetricLogger = Callable[[int, Dict[str, float]], None]
 
@@ -33,10 +35,13 @@ class Trainer:
         meter_window_size: int = 64,
         *,
         dp: Optional[DataParallelContext] = None,
+        cuda_graph: bool = True,
     ) -> None:
         self.__model = model
         model.ensure_flat()
-        self.__optim = th.optim.Adam(model.parameters(), lr=learning_rate)  # trainer.py:33
+        self.__optim = FlatAdam(model, lr=learning_rate)  # th.optim.Adam semantics, trainer.py:33
+        self.__cuda_graph = cuda_graph
+        self.__steps: dict = {}
         self.__nb_class = nb_class
         self.__gamma = gamma
         self.__metric_logger = metric_logger
@@ -54,28 +59,23 @@ class Trainer:
         return self.__curr_step
 
     def train_step(self, x: th.Tensor, y: th.Tensor, episode_sampler: EpisodeSampler, **inject) -> th.Tensor:
-        """One optimisation step (trainer.py:66-116).  Returns the device tensor
-        [loss, path, error, actor, critic] without synchronising."""
-        model = self.__model
+        """One optimisation step (trainer.py:66-116): rollout, loss, backward, Adam.
+        Returns the device tensor [loss, path, error, actor, critic] without
+        synchronising.  ``x`` / ``y`` may be host (pinned) or device tensors."""
         eng = episode_sampler.engine_for(x, gamma=self.__gamma)
-        eng.forward(x, inject.get("pos0"), inject.get("hidden0"), inject.get("actions"))
-        eng.loss_phase_a(y)
-        self.__dp.all_reduce_stats(eng.loss_stats)  # global-batch standardize (functions.py:54-55)
-        eng.loss_phase_b()
-        eng.backward()
-        self.__dp.all_reduce_grads(model.flat_grads)
-        model.attach_grads()
-        self.__optim.step()
-        return eng.loss_out
+        step = self.__steps.get(id(eng))
+        if step is None:
+            step = TrainStep(eng, self.__optim, self.__dp, use_graph=self.__cuda_graph)
+            self.__steps[id(eng)] = step
+        return step(x, y, **inject)
 
     def train_epoch(self, dataloader, epoch_index: int, episode_sampler: EpisodeSampler) -> None:
         self.__model.train()
         device = self.__model.device
         tqdm_bar = tqdm(dataloader)
         for x_train, y_train in tqdm_bar:
-            x_train = x_train.to(device, non_blocking=True)
-            y_train = y_train.to(device, non_blocking=True)
             loss_out = self.train_step(x_train, y_train, episode_sampler)
+            y_train = y_train.to(device, non_blocking=True)
             eng = episode_sampler.engine_for(x_train, gamma=self.__gamma)
             # meters: one packed D2H read of the five scalars
             loss_item, path_item, error_item, actor_item, critic_item = loss_out[:5].tolist()

@@ -447,3 +447,48 @@ def test_trainer_step_reduces_loss():
         out = trainer.train_step(img, y, sampler, **inject)
         errs.append(out[2].item())
     assert math.isfinite(errs[-1]) and errs[-1] < errs[0]
+
+
+def test_flat_adam_matches_torch_adam():
+    from marlclassification_b200.training.optim import FlatAdam
+
+    fx = load_golden("conftest_odd")
+    cfg, model, _, _ = build(fx)
+    model.load_state_dict(fx["state_dict"])
+    model.to(DEV)
+    ref_params = [p.detach().clone().requires_grad_(True) for p in model.parameters()]
+    ref_opt = torch.optim.Adam(ref_params, lr=1e-3)
+    opt = FlatAdam(model, lr=1e-3)
+    g = torch.Generator(device=DEV).manual_seed(0)
+    for _ in range(5):
+        model.flat_grads.copy_(torch.randn(model.flat_grads.shape, generator=g, device=DEV))
+        model.attach_grads()
+        for rp, p in zip(ref_params, model.parameters()):
+            rp.grad = p.grad.detach().clone()
+        ref_opt.step()
+        opt.step()
+    for rp, p in zip(ref_params, model.parameters()):
+        assert torch.allclose(rp, p, rtol=1e-5, atol=1e-6)
+
+
+def test_graphed_step_matches_eager():
+    """CUDA-graph replay of the train step == eager launches (same device RNG stream)."""
+    from marlclassification_b200.core import EpisodeSampler
+    from marlclassification_b200.training import Trainer
+
+    fx = load_golden("resisc_small")
+    img, y = fx["img"].to(DEV), fx["targets"].to(DEV)
+    finals = []
+    for graph in (False, True):
+        cfg, model, marl, env = build(fx)
+        model.load_state_dict(fx["state_dict"])
+        model.to(DEV)
+        sampler = EpisodeSampler(marl, env, fx["T"], gamma=fx["gamma"])
+        sampler.engine_for(img, gamma=fx["gamma"]).seed(123)
+        trainer = Trainer(model, fx["model_config"]["nb_class"], 1e-4, fx["gamma"], cuda_graph=graph)
+        for _ in range(6):
+            out = trainer.train_step(img, y, sampler)
+        torch.cuda.synchronize()
+        finals.append((model.flat_params.clone(), out.clone()))
+    assert rel_l2(finals[1][0].cpu(), finals[0][0].cpu()) < 1e-4
+    assert abs(finals[1][1][0].item() - finals[0][1][0].item()) <= 1e-3 * abs(finals[0][1][0].item())

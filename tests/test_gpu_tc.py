@@ -1,0 +1,159 @@
+"""tcgen05 / TMA TF32 GEMM kernel (csrc/gemm_tc.cu) against torch fp64, every
+operand-major combination, ragged edges, split-K, dual operand pairs; and the
+TF32 engine mode (fused LSTM-cell epilogue, tensor-core dX / dW) against the
+fixtures recorded from the reference.
+
+Stated bounds for the TF32 mode (inputs truncated to 10 mantissa bits, fp32
+accumulate): forward outputs rel-L2 <= 5e-3, per-parameter gradients <= 2e-2.
+Inputs that are exactly representable in TF32 must reproduce fp32 to 1e-5.
+"""
+import pytest
+import torch
+
+from tests.conftest import GOLDEN_NAMES, load_golden, rel_l2
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TF32_FWD_TOL = 5e-3
+TF32_GRAD_TOL = 2e-2
+
+
+def tf32_round(x):
+    """Keep 10 mantissa bits (exactly representable TF32 values)."""
+    return (x.view(torch.int32) & ~0x1FFF).view(torch.float32)
+
+
+def run_tc(A, B, a_mn, b_mn, M, N, K, bias=None, A2=None, B2=None, K2=0, C0=None, accumulate=0, allow_split=0):
+    from marlclassification_b200 import _lib
+
+    C = torch.zeros(M, N, device=DEV) if C0 is None else C0.clone()
+    _lib.check(_lib.lib().marlc_tc_gemm(
+        A.data_ptr(), A.stride(0), a_mn, B.data_ptr(), B.stride(0), b_mn,
+        None if A2 is None else A2.data_ptr(), 0 if A2 is None else A2.stride(0),
+        None if B2 is None else B2.data_ptr(), 0 if B2 is None else B2.stride(0), K2,
+        None if bias is None else bias.data_ptr(), C.data_ptr(), C.stride(0), M, N, K, accumulate, allow_split,
+        _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    return C
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 64, 32), (200, 96, 160), (128, 1024, 368), (64, 32, 2048),
+                                   (300, 40, 72), (2048, 384, 256)])
+def test_tc_gemm_exact_on_tf32_inputs(a_mn, b_mn, M, N, K):
+    g = torch.Generator(device=DEV).manual_seed(M + N + K + 2 * a_mn + b_mn)
+    # logical A [M,K], B [N,K]
+    A = tf32_round(torch.randn(M, K, device=DEV, generator=g))
+    B = tf32_round(torch.randn(N, K, device=DEV, generator=g))
+    Am = A.t().contiguous() if a_mn else A  # MN-major storage: [K rows][M contiguous]
+    Bm = B.t().contiguous() if b_mn else B
+    if (Am.stride(0) % 4) or (Bm.stride(0) % 4):
+        pytest.skip("leading dimension not a multiple of 4 floats (TMA stride rule)")
+    bias = torch.randn(N, device=DEV, generator=g)
+    C = run_tc(Am, Bm, a_mn, b_mn, M, N, K, bias=bias)
+    ref = A.double() @ B.double().t() + bias.double()
+    assert rel_l2(C.cpu(), ref.cpu()) < 1e-5
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 1)])
+def test_tc_gemm_tf32_error_bound(a_mn, b_mn):
+    M, N, K = 256, 192, 512
+    g = torch.Generator(device=DEV).manual_seed(7)
+    A, B = torch.randn(M, K, device=DEV, generator=g), torch.randn(N, K, device=DEV, generator=g)
+    Am = A.t().contiguous() if a_mn else A
+    Bm = B.t().contiguous() if b_mn else B
+    C = run_tc(Am, Bm, a_mn, b_mn, M, N, K)
+    err = rel_l2(C.cpu(), (A.double() @ B.double().t()).cpu())
+    print(f"tf32 rel-L2 error, K={K}: {err:.2e}")
+    assert err < 2e-3
+
+
+def test_tc_gemm_split_k_dual_pair_accumulate():
+    M, N, K, K2 = 128, 368, 1024, 1024
+    g = torch.Generator(device=DEV).manual_seed(11)
+    A = tf32_round(torch.randn(M, K, device=DEV, generator=g))
+    A2 = tf32_round(torch.randn(M, K2, device=DEV, generator=g))
+    W = tf32_round(torch.randn(K, N, device=DEV, generator=g))    # MN-major B: [K rows][N contiguous]
+    W2 = tf32_round(torch.randn(K2, N, device=DEV, generator=g))
+    ref = A.double() @ W.double() + A2.double() @ W2.double()
+    C = run_tc(A, W, 0, 1, M, N, K, A2=A2, B2=W2, K2=K2, allow_split=1)
+    assert rel_l2(C.cpu(), ref.cpu()) < 1e-5
+    C0 = torch.randn(M, N, device=DEV, generator=g)
+    C = run_tc(A, W, 0, 1, M, N, K, A2=A2, B2=W2, K2=K2, C0=C0, accumulate=1, allow_split=1)
+    assert rel_l2(C.cpu(), (ref + C0.double()).cpu()) < 1e-5
+    C = run_tc(A, W, 0, 1, M, N, K, C0=C0, accumulate=1, allow_split=0)
+    assert rel_l2(C.cpu(), (A.double() @ W.double() + C0.double()).cpu()) < 1e-5
+
+
+def test_tc_gemm_strided_views():
+    """Operands / outputs that are column slices of wider buffers (u_t slices)."""
+    M, N, K = 128, 96, 128
+    g = torch.Generator(device=DEV).manual_seed(3)
+    Abig = tf32_round(torch.randn(M, 368, device=DEV, generator=g))
+    B = tf32_round(torch.randn(N, K, device=DEV, generator=g))
+    Cbig = torch.zeros(M, 368, device=DEV)
+    A = Abig[:, 64:64 + K]
+    Cv = Cbig[:, 256:256 + N]
+    from marlclassification_b200 import _lib
+
+    _lib.check(_lib.lib().marlc_tc_gemm(A.data_ptr(), 368, 0, B.data_ptr(), K, 0, None, 0, None, 0, 0, None,
+                                        Cv.data_ptr(), 368, M, N, K, 0, 0, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    assert rel_l2(Cv.cpu(), (A.double() @ B.double().t()).cpu()) < 1e-5
+    assert Cbig[:, :256].abs().max().item() == 0 and Cbig[:, 256 + N:].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("name", ["mnist_ckpt", "resisc_small", "aid_small"])
+def test_tf32_engine_vs_reference(name):
+    from tests.test_gpu_parity import run_fixture
+
+    fx = load_golden(name)
+    model, marl, env, sampler, inject = run_fixture(fx, use_tc=True)
+    img = fx["img"].to(DEV)
+    eng = sampler.engine_for(img)
+    eng.forward(img, **inject)
+    assert torch.equal(eng.step_pos.cpu(), fx["step_pos"])  # positions stay bit-exact in every mode
+    e = [rel_l2(eng.step_preds.cpu(), fx["step_preds"]), rel_l2(eng.step_log_probas.cpu(), fx["step_log_probas"]),
+         rel_l2(eng.step_values.cpu(), fx["step_values"])]
+    loss_out = eng.loss(fx["targets"].to(DEV)).cpu()
+    eng.backward()
+    model.attach_grads()
+    worst = max(rel_l2(p.grad.cpu(), fx["grads"][k]) for k, p in model.named_parameters() if fx["grads"][k].norm() > 0)
+    print(f"{name} tf32: preds/logp/values rel-L2 = {e[0]:.1e}/{e[1]:.1e}/{e[2]:.1e}, worst grad = {worst:.1e}")
+    assert max(e) < TF32_FWD_TOL
+    assert abs(loss_out[0].item() - fx["logged"]["loss"]) <= TF32_FWD_TOL * abs(fx["logged"]["loss"])
+    assert worst < TF32_GRAD_TOL
+
+
+def test_tf32_full_c2_vs_fp32_mode():
+    """RESISC45 shape (README nets): the TF32 mode against our own exact-fp32 mode."""
+    from marlclassification_b200.config import ModelConfig
+    from marlclassification_b200.core import EpisodeSampler
+    from tests.test_gpu_parity import FULL
+
+    spec = FULL["c2_resisc45"]
+    na, nb, T = spec["na"], spec["nb"], spec["T"]
+    torch.manual_seed(0)
+    model, marl, env = ModelConfig(**spec["mc"]).build_marl(na)
+    model.to(DEV)
+    g = torch.Generator().manual_seed(5)
+    img = torch.rand(nb, 3, 256, 256, generator=g).to(DEV)
+    y = torch.randint(45, (nb,), generator=g).to(DEV)
+    pos0 = torch.stack([torch.randint(244, (na, nb), generator=g), torch.randint(244, (na, nb), generator=g)], -1).to(DEV)
+    hidden0 = [torch.randn(na, nb, 256, generator=g).to(DEV) for _ in range(4)]
+    actions = torch.randint(4, (T, na, nb), generator=g).to(DEV)
+    res = {}
+    for use_tc in (False, True):
+        model.use_tc = use_tc
+        sampler = EpisodeSampler(marl, env, T, gamma=0.99)
+        eng = sampler.engine_for(img)
+        eng.forward(img, pos0, hidden0, actions)
+        loss = eng.loss(y).clone()
+        eng.backward()
+        res[use_tc] = (eng.step_preds.clone(), eng.step_values.clone(), loss, model.flat_grads.clone(),
+                       eng.step_pos.clone())
+    assert torch.equal(res[True][4], res[False][4])
+    ep, ev = rel_l2(res[True][0].cpu(), res[False][0].cpu()), rel_l2(res[True][1].cpu(), res[False][1].cpu())
+    eg = rel_l2(res[True][3].cpu(), res[False][3].cpu())
+    print(f"c2 tf32 vs fp32: preds {ep:.1e}, values {ev:.1e}, flat grads {eg:.1e}")
+    assert ep < TF32_FWD_TOL and ev < TF32_FWD_TOL and eg < TF32_GRAD_TOL
