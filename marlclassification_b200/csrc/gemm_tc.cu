@@ -43,8 +43,10 @@ static EncodeTiledFn get_encode() {
 }
 
 // 3-D map over [slabs][rows][inner] fp32, box = [1][box_rows][32], 128B swizzle, zero OOB fill
+// mn_major operands use the 32B-atom variant of the 128B swizzle: the only shared-memory
+// layout tcgen05 accepts for MN-major TF32 (UMMA layout type SWIZZLE_128B_BASE32B)
 static int make_map(CUtensorMap* m, const float* ptr, long inner, long rows, long slabs, long ld, long slab_stride,
-                    int box_rows) {
+                    int box_rows, bool mn_major = false) {
     EncodeTiledFn enc = get_encode();
     MARLC_CHECK(enc, "cuTensorMapEncodeTiled not available");
     cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)slabs};
@@ -52,7 +54,9 @@ static int make_map(CUtensorMap* m, const float* ptr, long inner, long rows, lon
     cuuint32_t box[3] = {32, (cuuint32_t)box_rows, 1};
     cuuint32_t es[3] = {1, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)ptr, dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     MARLC_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d): ptr=%p inner=%ld rows=%ld ld=%ld box_rows=%d",
                 (int)r, (const void*)ptr, inner, rows, ld, box_rows);
@@ -119,10 +123,11 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
                  : "r"(addr))
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// smem matrix descriptor, 128B swizzle (cute::UMMA::SmemDescriptor bit layout)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// smem matrix descriptor (cute::UMMA::SmemDescriptor bit layout).
+// layout_type: 2 = SWIZZLE_128B (K-major tiles), 1 = SWIZZLE_128B_BASE32B (MN-major TF32 tiles)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
-           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | ((uint64_t)layout_type << 61);
 }
 
 // ---------------------------------------------------------------------------------
@@ -245,10 +250,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
                 const uint32_t a_addr = smem_u32(sA + s * S::A_BYTES), b_addr = smem_u32(sB + s * S::B_BYTES);
 #pragma unroll
                 for (int k = 0; k < BK / UMMA_K; ++k) {
-                    // K-major: advance 32 B inside the swizzled 128 B row; SBO = 1024 (8 rows x 128 B)
-                    // MN-major: one 8-k-row group (1024 B) per MMA; LBO = 4096 between 32-float MN groups
-                    const uint64_t ad = A_MN ? make_desc(a_addr + k * 1024, 4096, 1024) : make_desc(a_addr + k * 32, 16, 1024);
-                    const uint64_t bd = B_MN ? make_desc(b_addr + k * 1024, 4096, 1024) : make_desc(b_addr + k * 32, 16, 1024);
+                    // K-major : advance 32 B inside the swizzled 128 B row; SBO = 1024 (8 rows x 128 B)
+                    // MN-major: 8 k-rows (1024 B) per MMA = two 4-row swizzle atoms, SBO = 512 between
+                    //           them; LBO = 4096 between the 32-float MN groups (one TMA box each)
+                    const uint64_t ad = A_MN ? make_desc(a_addr + k * 1024, 4096, 512, 1) : make_desc(a_addr + k * 32, 16, 1024, 2);
+                    const uint64_t bd = B_MN ? make_desc(b_addr + k * 1024, 4096, 512, 1) : make_desc(b_addr + k * 32, 16, 1024, 2);
                     umma_tf32(tmem_base, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
                 }
                 umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs retire
@@ -360,7 +366,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
 static int operand_map(CUtensorMap* m, const TcOperand& o, int mn_extent, int k_extent, int box_rows_kmajor) {
     // K-major: [mn_extent rows][k_extent inner];  MN-major: [k_extent rows][mn_extent inner]
     if (!o.mn_major) return make_map(m, o.ptr, k_extent, mn_extent, o.slabs, o.ld, o.slab_stride, box_rows_kmajor);
-    return make_map(m, o.ptr, mn_extent, k_extent, o.slabs, o.ld, o.slab_stride, 32);
+    return make_map(m, o.ptr, mn_extent, k_extent, o.slabs, o.ld, o.slab_stride, 32, true);
 }
 
 template <int BN, bool A_MN, bool B_MN>
