@@ -81,6 +81,7 @@ typedef struct marlc_config {
     int n_b, n_a, n_m, n_m_o, n_d, nl_b, nl_a, nb_class;
     float gamma;     /* trainer.py:35 */
     int use_tc;      /* 1: tcgen05 TF32 GEMMs where shapes allow, 0: exact fp32 FFMA everywhere */
+    int use_chains;  /* 1: fused per-step chain kernels (4 launches fwd / 3 bwd per step), 0: one kernel per op */
 } marlc_config;
 
 typedef struct marlc_engine marlc_engine;

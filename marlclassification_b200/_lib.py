@@ -26,7 +26,7 @@ class MarlcConfig(C.Structure):
         ("cnn_groups", C.c_int * MAX_CNN_LAYERS),
         ("n_b", C.c_int), ("n_a", C.c_int), ("n_m", C.c_int), ("n_m_o", C.c_int), ("n_d", C.c_int),
         ("nl_b", C.c_int), ("nl_a", C.c_int), ("nb_class", C.c_int),
-        ("gamma", C.c_float), ("use_tc", C.c_int),
+        ("gamma", C.c_float), ("use_tc", C.c_int), ("use_chains", C.c_int),
     ]
 
 

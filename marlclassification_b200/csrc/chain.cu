@@ -1,0 +1,524 @@
+// Fused per-step chain kernels -- see chain.cuh.  All arithmetic fp32 (FFMA); the
+// GEMM-heavy parts of a step (LSTM gates, policy/encoder block-0, dX) stay on the
+// tensor cores (gemm_tc.cu); these kernels glue the small row-local pieces together
+// so a rollout step is 4 launches forward and 3 backward instead of 17 + 13.
+#include <initializer_list>
+
+#include "chain.cuh"
+
+namespace marlc {
+
+constexpr int RB = 4;          // rows per CTA in the row-block roles
+constexpr int CT = 256;        // threads per CTA
+constexpr int WT_K = 16;       // k-extent of the staged weight tile
+constexpr int WT_P = WT_K + 1; // pitch (conflict-free column reads)
+constexpr float LN_EPS_C = 1e-5f;
+
+// ---------------------------------------------------------------------------------
+// row-block building blocks (every thread of the CTA must call them)
+// ---------------------------------------------------------------------------------
+
+// ys[r][n] = sum_k xT[k][r] * W[n][k] + bias[n]     (nn.Linear on RB rows)
+__device__ void rb_linear(const float* xT, const float* __restrict__ W, const float* __restrict__ bias, float* ys,
+                          int ldy, int N, int K, float* wt) {
+    const int tid = threadIdx.x;
+    const bool vec = ((K & 3) == 0) && (((uintptr_t)W & 15) == 0);
+    for (int n0 = 0; n0 < N; n0 += CT) {
+        float acc[RB];
+#pragma unroll
+        for (int r = 0; r < RB; ++r) acc[r] = 0.f;
+        const int n = n0 + tid;
+        for (int k0 = 0; k0 < K; k0 += WT_K) {
+            if (vec) {
+#pragma unroll
+                for (int i = 0; i < (CT * WT_K / 4) / CT; ++i) {
+                    const int idx = tid + i * CT, row = idx >> 2, c4 = idx & 3, k = k0 + 4 * c4;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (n0 + row < N && k < K) v = __ldg(reinterpret_cast<const float4*>(W + (long)(n0 + row) * K + k));
+                    float* d = wt + row * WT_P + 4 * c4;
+                    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+                }
+            } else {
+                for (int idx = tid; idx < CT * WT_K; idx += CT) {
+                    const int row = idx / WT_K, kk = idx % WT_K;
+                    wt[row * WT_P + kk] = (n0 + row < N && k0 + kk < K) ? __ldg(W + (long)(n0 + row) * K + k0 + kk) : 0.f;
+                }
+            }
+            __syncthreads();
+            if (n < N) {
+                const int kmax = min(WT_K, K - k0);
+                const float* wrow = wt + tid * WT_P;
+                for (int kk = 0; kk < kmax; ++kk) {
+                    const float w = wrow[kk];
+                    const float4 x = *reinterpret_cast<const float4*>(xT + (k0 + kk) * RB);
+                    acc[0] = fmaf(w, x.x, acc[0]); acc[1] = fmaf(w, x.y, acc[1]);
+                    acc[2] = fmaf(w, x.z, acc[2]); acc[3] = fmaf(w, x.w, acc[3]);
+                }
+            }
+            __syncthreads();
+        }
+        if (n < N) {
+            const float b = bias ? bias[n] : 0.f;
+#pragma unroll
+            for (int r = 0; r < RB; ++r) ys[r * ldy + n] = acc[r] + b;
+        }
+    }
+    __syncthreads();
+}
+
+// dx[r][k] = sum_n dyT[n][r] * W[n][k]   (input gradient; W rows are read coalesced)
+// out: smem [RB][ldo] (+ optional add), nothing global
+__device__ void rb_dx(const float* dyT, const float* __restrict__ W, float* out, int ldo, int N, int K) {
+    for (int k = threadIdx.x; k < K; k += CT) {
+        float acc[RB];
+#pragma unroll
+        for (int r = 0; r < RB; ++r) acc[r] = 0.f;
+        for (int n = 0; n < N; ++n) {
+            const float w = __ldg(W + (long)n * K + k);
+            const float4 d = *reinterpret_cast<const float4*>(dyT + n * RB);
+            acc[0] = fmaf(w, d.x, acc[0]); acc[1] = fmaf(w, d.y, acc[1]);
+            acc[2] = fmaf(w, d.z, acc[2]); acc[3] = fmaf(w, d.w, acc[3]);
+        }
+#pragma unroll
+        for (int r = 0; r < RB; ++r) out[r * ldo + k] = acc[r];
+    }
+    __syncthreads();
+}
+
+// LayerNorm + SiLU on RB rows held in smem ys[r][n]; warp r handles row r.
+//   pre_g : optional global copy of the pre-norm values (saved for backward)
+//   s_g   : optional global output          sT: optional smem output, transposed [n][RB]
+__device__ void rb_ln_silu(const float* ys, int ldy, int N, const float* __restrict__ gamma,
+                           const float* __restrict__ beta, int rows_valid, long row0, float* pre_g, long ld_pre,
+                           float* s_g, long ld_s, float* sT) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp < RB) {
+        const int r = warp;
+        if (r < rows_valid) {
+            const float* y = ys + r * ldy;
+            const float inv = 1.0f / (float)N;
+            float s = 0.f;
+            for (int n = lane; n < N; n += 32) s += y[n];
+            const float mean = warp_sum(s) * inv;
+            float v = 0.f;
+            for (int n = lane; n < N; n += 32) { const float d = y[n] - mean; v += d * d; }
+            const float rstd = 1.0f / sqrtf(warp_sum(v) * inv + LN_EPS_C);
+            for (int n = lane; n < N; n += 32) {
+                const float yv = y[n];
+                if (pre_g) pre_g[(row0 + r) * ld_pre + n] = yv;
+                const float o = siluf_((yv - mean) * rstd * gamma[n] + beta[n]);
+                if (s_g) s_g[(row0 + r) * ld_s + n] = o;
+                if (sT) sT[n * RB + r] = o;
+            }
+        } else if (sT) {
+            for (int n = lane; n < N; n += 32) sT[n * RB + r] = 0.f;
+        }
+    }
+    __syncthreads();
+}
+
+// Backward of LayerNorm + SiLU on RB rows.
+//   ds   [RB][ld] smem: incoming gradient w.r.t. the block output (DESTROYED: becomes dz)
+//   ypre [RB][ld] smem: saved pre-norm values                      (DESTROYED: becomes xhat)
+//   dy   [RB][ld] smem out; dyT [N][RB] smem out (optional); dy_g global out (optional)
+//   dgamma / dbeta / dbias: global accumulators (atomicAdd of the RB-row partial sums)
+__device__ void rb_ln_silu_bwd(float* ds, float* ypre, int ld, int N, const float* __restrict__ gamma,
+                               const float* __restrict__ beta, int rows_valid, long row0, float* dy, float* dyT,
+                               float* dy_g, long ld_dyg, float* dgamma, float* dbeta, float* dbias) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp < RB) {
+        const int r = warp;
+        float* y = ypre + r * ld;
+        float* g = ds + r * ld;
+        if (r < rows_valid) {
+            const float inv = 1.0f / (float)N;
+            float s = 0.f;
+            for (int n = lane; n < N; n += 32) s += y[n];
+            const float mean = warp_sum(s) * inv;
+            float v = 0.f;
+            for (int n = lane; n < N; n += 32) { const float d = y[n] - mean; v += d * d; }
+            const float rstd = 1.0f / sqrtf(warp_sum(v) * inv + LN_EPS_C);
+            float c1 = 0.f, c2 = 0.f;
+            for (int n = lane; n < N; n += 32) {
+                const float xh = (y[n] - mean) * rstd;
+                const float dz = g[n] * silu_grad_(xh * gamma[n] + beta[n]);
+                const float dxh = dz * gamma[n];
+                c1 += dxh;
+                c2 += dxh * xh;
+                y[n] = xh;
+                g[n] = dz;
+            }
+            c1 = warp_sum(c1) * inv;
+            c2 = warp_sum(c2) * inv;
+            for (int n = lane; n < N; n += 32) {
+                const float o = rstd * (g[n] * gamma[n] - c1 - y[n] * c2);
+                dy[r * ld + n] = o;
+                if (dyT) dyT[n * RB + r] = o;
+                if (dy_g) dy_g[(row0 + r) * ld_dyg + n] = o;
+            }
+        } else {
+            for (int n = lane; n < N; n += 32) {
+                y[n] = 0.f; g[n] = 0.f; dy[r * ld + n] = 0.f;
+                if (dyT) dyT[n * RB + r] = 0.f;
+            }
+        }
+    }
+    __syncthreads();
+    for (int n = threadIdx.x; n < N; n += CT) {
+        float a = 0.f, b = 0.f, c = 0.f;
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+            a += ds[r * ld + n] * ypre[r * ld + n];
+            b += ds[r * ld + n];
+            c += dy[r * ld + n];
+        }
+        if (dgamma) atomicAdd(dgamma + n, a);
+        if (dbeta) atomicAdd(dbeta + n, b);
+        if (dbias) atomicAdd(dbias + n, c);
+    }
+    __syncthreads();
+}
+
+// (sum over the other agents of the same image) / (Na - 1): message.py:5-17 and its adjoint
+__device__ __forceinline__ float other_agents_mean(const float* __restrict__ x, int m, int j, int Na, int Nb, int n) {
+    if (Na <= 1) return 0.f;
+    const int b = m % Nb;
+    const float* base = x + (long)b * n + j;
+    const long stride = (long)Nb * n;
+    float s = 0.f;
+    for (int a = 0; a < Na; ++a) s += base[a * stride];
+    return (s - x[(long)m * n + j]) / (float)(Na - 1);
+}
+
+struct ChainSmem {
+    float *bufA, *bufB, *bufC, *bufT, *wt;
+    __device__ ChainSmem(float* sm, int maxw) {
+        bufA = sm; bufB = bufA + RB * maxw; bufC = bufB + RB * maxw; bufT = bufC + RB * maxw; wt = bufT + RB * maxw;
+    }
+};
+static size_t chain_smem_bytes(int maxw) { return sizeof(float) * ((size_t)4 * RB * maxw + (size_t)CT * WT_P); }
+static int maxw_of(std::initializer_list<int> v) {
+    int m = 4;
+    for (int x : v) m = max(m, x);
+    return (m + 3) & ~3;
+}
+
+// ---------------------------------------------------------------------------------
+// forward "pre": CNN role (blocks [0,M)) | decoder + position-feature role
+// ---------------------------------------------------------------------------------
+struct StepPreKernelArgs { StepPreArgs a; int maxw; };
+
+__global__ void __launch_bounds__(CT) step_pre_kernel(const StepPreKernelArgs ka) {
+    extern __shared__ __align__(16) float sm[];
+    const StepPreArgs& a = ka.a;
+    if ((int)blockIdx.x < a.M) {
+        cnn_fwd_block(a.cnn, blockIdx.x, sm);
+        return;
+    }
+    const int row0 = ((int)blockIdx.x - a.M) * RB;
+    const int rows_valid = min(RB, a.M - row0);
+    const int n_m = a.d0.n_in, n1 = a.d0.n_out, n2 = a.d3.n_out;
+    ChainSmem S(sm, ka.maxw);
+    // collected message (mean of the other agents)                      message.py:5-17
+    for (int e = threadIdx.x; e < RB * n_m; e += CT) {
+        const int r = e / n_m, j = e % n_m;
+        float v = 0.f;
+        if (r < rows_valid) {
+            v = other_agents_mean(a.msg_in, row0 + r, j, a.Na, a.Nb, n_m);
+            a.coll[(long)(row0 + r) * n_m + j] = v;
+        }
+        S.bufT[j * RB + r] = v;
+    }
+    __syncthreads();
+    // decoder block 0 and block 3                                        message.py:36-49
+    rb_linear(S.bufT, a.d0.W, a.d0.b, S.bufA, ka.maxw, n1, n_m, S.wt);
+    rb_ln_silu(S.bufA, ka.maxw, n1, a.d0.g, a.d0.be, rows_valid, row0, a.dec_y1, n1, a.dec_s1, n1, S.bufT);
+    rb_linear(S.bufT, a.d3.W, a.d3.b, S.bufA, ka.maxw, n2, n1, S.wt);
+    rb_ln_silu(S.bufA, ka.maxw, n2, a.d3.g, a.d3.be, rows_valid, row0, a.dec_y2, n2, a.U + a.F, a.ldu, nullptr);
+    // position features                                                  state.py:7-17
+    {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nd = a.pos.n_out;
+        if (warp < rows_valid) {
+            const long m = row0 + warp;
+            const float p0 = a.npos[2 * m], p1 = a.npos[2 * m + 1];
+            const float inv = 1.0f / (float)nd;
+            float s = 0.f;
+            for (int j = lane; j < nd; j += 32) {
+                const float y = fmaf(p1, a.pos.W[2 * j + 1], p0 * a.pos.W[2 * j]) + a.pos.b[j];
+                a.pos_y[m * nd + j] = y;
+                S.bufB[warp * ka.maxw + j] = y;
+                s += y;
+            }
+            const float mean = warp_sum(s) * inv;
+            float v = 0.f;
+            for (int j = lane; j < nd; j += 32) { const float d = S.bufB[warp * ka.maxw + j] - mean; v += d * d; }
+            const float rstd = 1.0f / sqrtf(warp_sum(v) * inv + LN_EPS_C);
+            float* o = a.U + m * a.ldu + a.F + n2;
+            for (int j = lane; j < nd; j += 32)
+                o[j] = siluf_((S.bufB[warp * ka.maxw + j] - mean) * rstd * a.pos.g[j] + a.pos.be[j]);
+        }
+    }
+}
+
+int step_pre(const StepPreArgs& a, cudaStream_t s) {
+    if (a.M <= 0) return 0;
+    StepPreKernelArgs ka;
+    ka.a = a;
+    ka.maxw = maxw_of({a.d0.n_in, a.d0.n_out, a.d3.n_out, a.pos.n_out});
+    const size_t smem = max(chain_smem_bytes(ka.maxw), sizeof(float) * 2 * (size_t)a.cnn.bufsz);
+    MARLC_CHECK(smem <= 200 * 1024, "step_pre: shared memory %zu B too large", smem);
+    static size_t attr = 0;
+    if (smem > 48 * 1024 && smem > attr) {
+        MARLC_CUDA(cudaFuncSetAttribute(step_pre_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = smem;
+    }
+    const int grid = a.M + (a.M + RB - 1) / RB;
+    step_pre_kernel<<<grid, CT, smem, s>>>(ka);
+    MARLC_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// forward "post": policy tail + sampling + transition (warp per row) | encoder tail (row blocks)
+// ---------------------------------------------------------------------------------
+constexpr int MAX_ACT = 16;
+
+__device__ void policy_tail_row(const StepPostArgs& a, const int m, float* srow /* smem [nl] */) {
+    const PolicyActArgs& p = a.act;
+    const int lane = threadIdx.x & 31, nl = p.nl;
+    const float* y = a.pol_y1 + (long)m * nl;
+    const float inv = 1.0f / (float)nl;
+    float s = 0.f;
+    for (int k = lane; k < nl; k += 32) s += y[k];
+    const float mean = warp_sum(s) * inv;
+    float v = 0.f;
+    for (int k = lane; k < nl; k += 32) { const float d = y[k] - mean; v += d * d; }
+    const float rstd = 1.0f / sqrtf(warp_sum(v) * inv + LN_EPS_C);
+    float* s1 = const_cast<float*>(p.s1) + (long)m * nl;
+    for (int k = lane; k < nl; k += 32) {
+        const float o = siluf_((y[k] - mean) * rstd * a.pol_g[k] + a.pol_be[k]);
+        s1[k] = o;      // saved for the batched weight gradient of policy.3
+        srow[k] = o;
+    }
+    __syncwarp();
+    float logit[MAX_ACT];
+#pragma unroll 1
+    for (int j = 0; j < p.nA; ++j) {
+        const float* w = p.W3 + (long)j * nl;
+        float d = 0.f;
+        for (int k = lane; k < nl; k += 32) d = fmaf(srow[k], w[k], d);
+        logit[j] = warp_sum(d) + p.b3[j];
+    }
+    float mx = -INFINITY;
+    for (int j = 0; j < p.nA; ++j) mx = fmaxf(mx, logit[j]);
+    float den = 0.f;
+    for (int j = 0; j < p.nA; ++j) { logit[j] = expf(logit[j] - mx); den += logit[j]; }
+    const float invd = 1.0f / den;
+    int act;
+    if (p.act_in) act = (int)p.act_in[m];
+    else {
+        const uint64_t episode = p.rng_state[1];
+        const Philox ph(p.rng_state[0]);
+        const uint4 r = ph((uint64_t)p.t * (uint64_t)p.M + (uint64_t)m, (episode << 8) | 7);
+        const float u = u01(r.x);
+        float cdf = 0.f;
+        act = p.nA - 1;
+        for (int j = 0; j < p.nA; ++j) {
+            cdf += logit[j] * invd;
+            if (u < cdf) { act = j; break; }
+        }
+    }
+    if (lane == 0) {
+        float pa = 0.f;
+        for (int j = 0; j < p.nA; ++j) {
+            const float pr = logit[j] * invd;
+            p.probs[(long)m * p.nA + j] = pr;
+            if (j == act) pa = pr;
+        }
+        p.logp[m] = logf(pa);
+        p.act_out[m] = act;
+        int py = p.pos_in[2 * m], px = p.pos_in[2 * m + 1];
+        if (act >= 0 && act < p.nA) {
+            const int ny = py + p.moves[2 * act], nx = px + p.moves[2 * act + 1];
+            if ((ny >= 0) & (ny + p.f < p.H) & (nx >= 0) & (nx + p.f < p.W)) { py = ny; px = nx; }
+        }
+        p.pos_out[2 * m] = py; p.pos_out[2 * m + 1] = px;
+        p.step_pos[2 * (long)m] = py; p.step_pos[2 * (long)m + 1] = px;
+        p.npos_out[2 * m] = (float)py / (float)p.H;
+        p.npos_out[2 * m + 1] = (float)px / (float)p.W;
+    }
+}
+
+struct StepPostKernelArgs { StepPostArgs a; int maxw; int pol_blocks; };
+
+__global__ void __launch_bounds__(CT) step_post_kernel(const StepPostKernelArgs ka) {
+    extern __shared__ __align__(16) float sm[];
+    const StepPostArgs& a = ka.a;
+    if ((int)blockIdx.x < ka.pol_blocks) {
+        const int warp = threadIdx.x >> 5;
+        const int m = blockIdx.x * (CT / 32) + warp;
+        if (m < a.M) policy_tail_row(a, m, sm + warp * a.act.nl);
+        return;
+    }
+    const int row0 = ((int)blockIdx.x - ka.pol_blocks) * RB;
+    const int rows_valid = min(RB, a.M - row0);
+    const int n1 = a.e3.n_in, n2 = a.e3.n_out;
+    ChainSmem S(sm, ka.maxw);
+    for (int e = threadIdx.x; e < RB * n1; e += CT) {
+        const int r = e / n1, k = e % n1;
+        S.bufA[r * ka.maxw + k] = r < rows_valid ? a.enc_y1[(long)(row0 + r) * n1 + k] : 0.f;
+    }
+    __syncthreads();
+    rb_ln_silu(S.bufA, ka.maxw, n1, a.enc_g, a.enc_be, rows_valid, row0, nullptr, 0, a.enc_s1, n1, S.bufT);
+    rb_linear(S.bufT, a.e3.W, a.e3.b, S.bufA, ka.maxw, n2, n1, S.wt);
+    rb_ln_silu(S.bufA, ka.maxw, n2, a.e3.g, a.e3.be, rows_valid, row0, a.enc_y2, n2, a.msg_out, n2, nullptr);
+}
+
+int step_post(const StepPostArgs& a, cudaStream_t s) {
+    if (a.M <= 0) return 0;
+    MARLC_CHECK(a.act.nA <= MAX_ACT, "step_post: nb_action=%d > %d", a.act.nA, MAX_ACT);
+    StepPostKernelArgs ka;
+    ka.a = a;
+    ka.maxw = maxw_of({a.e3.n_in, a.e3.n_out});
+    ka.pol_blocks = (a.M + CT / 32 - 1) / (CT / 32);
+    const size_t smem = max(chain_smem_bytes(ka.maxw), sizeof(float) * (size_t)(CT / 32) * a.act.nl);
+    MARLC_CHECK(smem <= 200 * 1024, "step_post: shared memory %zu B too large", smem);
+    static size_t attr = 0;
+    if (smem > 48 * 1024 && smem > attr) {
+        MARLC_CUDA(cudaFuncSetAttribute(step_post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = smem;
+    }
+    const int grid = ka.pol_blocks + (a.M + RB - 1) / RB;
+    step_post_kernel<<<grid, CT, smem, s>>>(ka);
+    MARLC_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// backward "pre" (step t): adjoint message mean -> encoder backward -> dh += ... -> both LSTM cells
+// ---------------------------------------------------------------------------------
+struct BwdPreKernelArgs { BwdPreArgs a; int maxw; };
+
+__global__ void __launch_bounds__(CT) bwd_pre_kernel(const BwdPreKernelArgs ka) {
+    extern __shared__ __align__(16) float sm[];
+    const BwdPreArgs& a = ka.a;
+    const int row0 = blockIdx.x * RB, rows_valid = min(RB, a.M - row0), mw = ka.maxw;
+    ChainSmem S(sm, mw);
+    const int n_m = a.n_m, n1 = a.e0.n_out, nb = a.n[0];
+    float* dhx = S.bufC;  // [RB][mw] encoder contribution to dh (belief cell only)
+    if (a.dcoll) {
+        // gradient of the message produced at step t = adjoint mean of dcoll(t+1); encoder block 3 backward
+        for (int e = threadIdx.x; e < RB * n_m; e += CT) {
+            const int r = e / n_m, j = e % n_m;
+            const bool ok = r < rows_valid;
+            S.bufA[r * mw + j] = ok ? other_agents_mean(a.dcoll, row0 + r, j, a.Na, a.Nb, n_m) : 0.f;
+            S.bufB[r * mw + j] = ok ? a.enc_y2[(long)(row0 + r) * n_m + j] : 0.f;
+        }
+        __syncthreads();
+        rb_ln_silu_bwd(S.bufA, S.bufB, mw, n_m, a.e3.g, a.e3.be, rows_valid, row0, dhx, S.bufT, a.d_enc_y2, n_m,
+                       a.e3.dg, a.e3.dbe, a.e3.db);
+        rb_dx(S.bufT, a.e3.W, S.bufA, mw, n_m, n1);  // ds1 [RB][2n_m]
+        for (int e = threadIdx.x; e < RB * n1; e += CT) {
+            const int r = e / n1, k = e % n1;
+            S.bufB[r * mw + k] = r < rows_valid ? a.enc_y1[(long)(row0 + r) * n1 + k] : 0.f;
+        }
+        __syncthreads();
+        rb_ln_silu_bwd(S.bufA, S.bufB, mw, n1, a.e0.g, a.e0.be, rows_valid, row0, dhx, S.bufT, a.d_enc_y1, n1,
+                       a.e0.dg, a.e0.dbe, a.e0.db);
+        rb_dx(S.bufT, a.e0.W, dhx, mw, n1, nb);      // dh contribution [RB][n_b]
+    }
+    // point-wise LSTM backward, both cells (recurrent.py:30)
+    for (int k = 0; k < 2; ++k) {
+        const int n = a.n[k];
+        for (int e = threadIdx.x; e < rows_valid * n; e += CT) {
+            const int r = e / n, j = e % n;
+            const long m = row0 + r, idx = m * n + j;
+            const float* g = a.gates[k] + m * 4 * n;
+            const float gi = g[j], gf = g[n + j], gg = g[2 * n + j], go = g[3 * n + j];
+            float dh = a.dh_heads[k][idx];
+            if (a.dh_carry[k]) dh += a.dh_carry[k][idx];
+            if (k == 0 && a.dcoll) dh += dhx[r * mw + j];
+            const float tc = tanhf(a.c_new[k][idx]);
+            const float dc = (a.dc_next[k] ? a.dc_next[k][idx] : 0.f) + dh * go * (1.f - tc * tc);
+            float* dg = a.dgates[k] + m * 4 * n;
+            dg[j] = dc * gg * gi * (1.f - gi);
+            dg[n + j] = dc * a.c_prev[k][idx] * gf * (1.f - gf);
+            dg[2 * n + j] = dc * gi * (1.f - gg * gg);
+            dg[3 * n + j] = dh * tc * go * (1.f - go);
+            a.dc_prev[k][idx] = dc * gf;
+        }
+    }
+}
+
+int bwd_pre(const BwdPreArgs& a, cudaStream_t s) {
+    if (a.M <= 0) return 0;
+    BwdPreKernelArgs ka;
+    ka.a = a;
+    ka.maxw = maxw_of({a.n_m, a.e0.n_out, a.n[0]});
+    const size_t smem = chain_smem_bytes(ka.maxw);
+    MARLC_CHECK(smem <= 200 * 1024, "bwd_pre: shared memory %zu B too large", smem);
+    static size_t attr = 0;
+    if (smem > 48 * 1024 && smem > attr) {
+        MARLC_CUDA(cudaFuncSetAttribute(bwd_pre_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = smem;
+    }
+    bwd_pre_kernel<<<(a.M + RB - 1) / RB, CT, smem, s>>>(ka);
+    MARLC_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// backward "post" (step t): decoder backward from du_t -> dcoll
+// ---------------------------------------------------------------------------------
+struct BwdPostKernelArgs { BwdPostArgs a; int maxw; };
+
+__global__ void __launch_bounds__(CT) bwd_post_kernel(const BwdPostKernelArgs ka) {
+    extern __shared__ __align__(16) float sm[];
+    const BwdPostArgs& a = ka.a;
+    const int row0 = blockIdx.x * RB, rows_valid = min(RB, a.M - row0), mw = ka.maxw;
+    ChainSmem S(sm, mw);
+    const int n_m = a.n_m, n1 = a.d0.n_out, n2 = a.n_m_o;
+    for (int e = threadIdx.x; e < RB * n2; e += CT) {
+        const int r = e / n2, j = e % n2;
+        const bool ok = r < rows_valid;
+        S.bufA[r * mw + j] = ok ? a.dU[(long)(row0 + r) * a.ldu + a.F + j] : 0.f;
+        S.bufB[r * mw + j] = ok ? a.dec_y2[(long)(row0 + r) * n2 + j] : 0.f;
+    }
+    __syncthreads();
+    rb_ln_silu_bwd(S.bufA, S.bufB, mw, n2, a.d3.g, a.d3.be, rows_valid, row0, S.bufC, S.bufT, a.d_dec_y2, n2, a.d3.dg,
+                   a.d3.dbe, a.d3.db);
+    rb_dx(S.bufT, a.d3.W, S.bufA, mw, n2, n1);
+    for (int e = threadIdx.x; e < RB * n1; e += CT) {
+        const int r = e / n1, k = e % n1;
+        S.bufB[r * mw + k] = r < rows_valid ? a.dec_y1[(long)(row0 + r) * n1 + k] : 0.f;
+    }
+    __syncthreads();
+    rb_ln_silu_bwd(S.bufA, S.bufB, mw, n1, a.d0.g, a.d0.be, rows_valid, row0, S.bufC, S.bufT, a.d_dec_y1, n1, a.d0.dg,
+                   a.d0.dbe, a.d0.db);
+    if (a.dcoll) {
+        rb_dx(S.bufT, a.d0.W, S.bufA, mw, n1, n_m);
+        for (int e = threadIdx.x; e < rows_valid * n_m; e += CT) {
+            const int r = e / n_m, j = e % n_m;
+            a.dcoll[(long)(row0 + r) * n_m + j] = S.bufA[r * mw + j];
+        }
+    }
+}
+
+int bwd_post(const BwdPostArgs& a, cudaStream_t s) {
+    if (a.M <= 0) return 0;
+    BwdPostKernelArgs ka;
+    ka.a = a;
+    ka.maxw = maxw_of({a.n_m, a.d0.n_out, a.n_m_o});
+    const size_t smem = chain_smem_bytes(ka.maxw);
+    MARLC_CHECK(smem <= 200 * 1024, "bwd_post: shared memory %zu B too large", smem);
+    static size_t attr = 0;
+    if (smem > 48 * 1024 && smem > attr) {
+        MARLC_CUDA(cudaFuncSetAttribute(bwd_post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = smem;
+    }
+    bwd_post_kernel<<<(a.M + RB - 1) / RB, CT, smem, s>>>(ka);
+    MARLC_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace marlc

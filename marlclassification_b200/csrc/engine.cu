@@ -11,6 +11,7 @@
 
 #include "../../include/marlc.h"
 #include "kernels.cuh"
+#include "chain.cuh"
 #include "tc.cuh"
 
 namespace marlc {
@@ -113,6 +114,7 @@ extern "C" int marlc_engine_create(const marlc_config* c, marlc_engine** out) {
     MARLC_CHECK(c->cnn_cin[0] <= c->C, "CNN wants %d input channels, image has %d", c->cnn_cin[0], c->C);
     marlc_engine* e = new marlc_engine();
     e->cfg = *c;
+    if (c->na * c->nb < 1) e->cfg.use_chains = 0;
     e->M = c->na * c->nb;
     e->TM = e->M * c->T;
     e->L = c->cnn_layers;
@@ -332,6 +334,18 @@ static int G_tn(const marlc_engine* e, const float* dY, long lddy, const float* 
     return gemm_tn(dY, lddy, X, ldx, dW, lddw, R, N, K, 1, s);
 }
 
+
+static ChainLin chain_lin(const marlc_engine* e, const std::string& name, int i, int n_in, int n_out, bool norm) {
+    const std::string a = name + "." + std::to_string(i), b = name + "." + std::to_string(i + 1);
+    ChainLin c;
+    c.W = e->prm(a + ".weight"); c.b = e->prm(a + ".bias");
+    c.g = norm ? e->prm(b + ".weight") : nullptr; c.be = norm ? e->prm(b + ".bias") : nullptr;
+    c.dW = e->G ? e->grd(a + ".weight") : nullptr; c.db = e->G ? e->grd(a + ".bias") : nullptr;
+    c.dg = (norm && e->G) ? e->grd(b + ".weight") : nullptr; c.dbe = (norm && e->G) ? e->grd(b + ".bias") : nullptr;
+    c.n_in = n_in; c.n_out = n_out;
+    return c;
+}
+
 // Linear -> LN -> SiLU block forward on R rows (message.py:26-33 etc.)
 static int block_fwd(marlc_engine* e, const std::string& name, int i, const float* X, long ldx, int R, int n_in,
                      int n_out, float* y_pre, float* S, long lds, cudaStream_t s) {
@@ -355,22 +369,43 @@ static int step_networks(marlc_engine* e, int t, const float* img, const int* po
     float* Cb = e->buf("Cb");
     float* Hc = e->buf("Hc");
     float* Cc = e->buf("Cc");
-    // b_t: gather + CNN straight into u_t[:, 0:F]                (models.py:92-94)
-    float* ysave[MAX_CNN_LAYERS];
-    for (int l = 0; l < e->L; ++l) ysave[l] = e->buf("cnn_y" + std::to_string(l)) + (size_t)t * M * e->cnn_sz[l];
-    MARLC_TRY(cnn_fwd(e->cnn, img, pos, patch, c.nb, c.H, c.W, M, ysave, Ut, Kin, s));
-    // d_bar_t: message mean + decoder into u_t[:, F:F+n_m_o]     (models.py:97-98)
-    float* coll = e->buf("coll") + (size_t)t * M * c.n_m;
-    MARLC_TRY(msg_mean(msg_in, coll, c.na, c.nb, c.n_m, s));
-    float* dec_s1 = e->buf("dec_s1") + (size_t)t * M * 2 * c.n_m;
-    MARLC_TRY(block_fwd(e, "decode_msg", 0, coll, c.n_m, M, c.n_m, 2 * c.n_m,
-                        e->buf("dec_y1") + (size_t)t * M * 2 * c.n_m, dec_s1, 2 * c.n_m, s));
-    MARLC_TRY(block_fwd(e, "decode_msg", 3, dec_s1, 2 * c.n_m, M, 2 * c.n_m, c.n_m_o,
-                        e->buf("dec_y2") + (size_t)t * M * c.n_m_o, Ut + F, Kin, s));
-    // lambda_t into u_t[:, F+n_m_o:]                             (models.py:101)
-    MARLC_TRY(pos_features_fwd(npos_in, e->prm("map_pos.0.weight"), e->prm("map_pos.0.bias"),
-                               e->prm("map_pos.1.weight"), e->prm("map_pos.1.bias"),
-                               e->buf("pos_y") + (size_t)t * M * c.n_d, Ut + F + c.n_m_o, Kin, M, c.n_d, s));
+    if (c.use_chains) {
+        // fused "pre" launch: CNN | message mean + decoder + position features  (models.py:92-101)
+        StepPreArgs pa;
+        memset(&pa, 0, sizeof(pa));
+        pa.cnn.d = e->cnn; pa.cnn.img = img; pa.cnn.pos = pos; pa.cnn.patch = patch; pa.cnn.out = Ut; pa.cnn.ldo = Kin;
+        pa.cnn.B = c.nb; pa.cnn.H = c.H; pa.cnn.W = c.W; pa.cnn.M = M; pa.cnn.bufsz = cnn_max_act(e->cnn);
+        for (int l = 0; l < e->L; ++l) pa.cnn.y_save[l] = e->buf("cnn_y" + std::to_string(l)) + (size_t)t * M * e->cnn_sz[l];
+        pa.msg_in = msg_in;
+        pa.coll = e->buf("coll") + (size_t)t * M * c.n_m;
+        pa.d0 = chain_lin(e, "decode_msg", 0, c.n_m, 2 * c.n_m, true);
+        pa.d3 = chain_lin(e, "decode_msg", 3, 2 * c.n_m, c.n_m_o, true);
+        pa.dec_y1 = e->buf("dec_y1") + (size_t)t * M * 2 * c.n_m;
+        pa.dec_s1 = e->buf("dec_s1") + (size_t)t * M * 2 * c.n_m;
+        pa.dec_y2 = e->buf("dec_y2") + (size_t)t * M * c.n_m_o;
+        pa.npos = npos_in;
+        pa.pos = chain_lin(e, "map_pos", 0, 2, c.n_d, true);
+        pa.pos_y = e->buf("pos_y") + (size_t)t * M * c.n_d;
+        pa.U = Ut; pa.ldu = Kin; pa.F = F; pa.Na = c.na; pa.Nb = c.nb; pa.M = M;
+        MARLC_TRY(step_pre(pa, s));
+    } else {
+        // b_t: gather + CNN straight into u_t[:, 0:F]                (models.py:92-94)
+        float* ysave[MAX_CNN_LAYERS];
+        for (int l = 0; l < e->L; ++l) ysave[l] = e->buf("cnn_y" + std::to_string(l)) + (size_t)t * M * e->cnn_sz[l];
+        MARLC_TRY(cnn_fwd(e->cnn, img, pos, patch, c.nb, c.H, c.W, M, ysave, Ut, Kin, s));
+        // d_bar_t: message mean + decoder into u_t[:, F:F+n_m_o]     (models.py:97-98)
+        float* coll = e->buf("coll") + (size_t)t * M * c.n_m;
+        MARLC_TRY(msg_mean(msg_in, coll, c.na, c.nb, c.n_m, s));
+        float* dec_s1 = e->buf("dec_s1") + (size_t)t * M * 2 * c.n_m;
+        MARLC_TRY(block_fwd(e, "decode_msg", 0, coll, c.n_m, M, c.n_m, 2 * c.n_m,
+                            e->buf("dec_y1") + (size_t)t * M * 2 * c.n_m, dec_s1, 2 * c.n_m, s));
+        MARLC_TRY(block_fwd(e, "decode_msg", 3, dec_s1, 2 * c.n_m, M, 2 * c.n_m, c.n_m_o,
+                            e->buf("dec_y2") + (size_t)t * M * c.n_m_o, Ut + F, Kin, s));
+        // lambda_t into u_t[:, F+n_m_o:]                             (models.py:101)
+        MARLC_TRY(pos_features_fwd(npos_in, e->prm("map_pos.0.weight"), e->prm("map_pos.0.bias"),
+                                   e->prm("map_pos.1.weight"), e->prm("map_pos.1.bias"),
+                                   e->buf("pos_y") + (size_t)t * M * c.n_d, Ut + F + c.n_m_o, Kin, M, c.n_d, s));
+    }
     // both LSTM cells share u_t                                   (models.py:107-123)
     float* gb = e->buf("gates_b") + (size_t)t * M * 4 * c.n_b;
     float* ga = e->buf("gates_a") + (size_t)t * M * 4 * c.n_a;
@@ -416,6 +451,15 @@ static int step_networks(marlc_engine* e, int t, const float* img, const int* po
         MARLC_TRY(lstm_cell_fwd(gb, c_in, Cb + (size_t)(t + 1) * M * c.n_b, H + (size_t)(t + 1) * M * c.n_b, M, c.n_b, s));
         MARLC_TRY(lstm_cell_fwd(ga, cc_in, Cc + (size_t)(t + 1) * M * c.n_a, Hc + (size_t)(t + 1) * M * c.n_a, M, c.n_a, s));
     }
+    if (c.use_chains) {
+        // block-0 GEMMs of the encoder and the policy (tensor cores), tails fused in step_act()
+        MARLC_TRY(G_nt(e, H + (size_t)(t + 1) * M * c.n_b, c.n_b, e->prm("encode_msg.0.weight"), c.n_b,
+                       e->prm("encode_msg.0.bias"), e->buf("enc_y1") + (size_t)t * M * 2 * c.n_m, 2 * c.n_m, M,
+                       2 * c.n_m, c.n_b, 0, s));
+        MARLC_TRY(G_nt(e, Hc + (size_t)(t + 1) * M * c.n_a, c.n_a, e->prm("policy.0.weight"), c.n_a,
+                       e->prm("policy.0.bias"), e->buf("pol_y1") + (size_t)t * M * c.nl_a, c.nl_a, M, c.nl_a, c.n_a, 0, s));
+        return 0;
+    }
     // message for the next step                                   (models.py:114-116)
     float* enc_s1 = e->buf("enc_s1") + (size_t)t * M * 2 * c.n_m;
     MARLC_TRY(block_fwd(e, "encode_msg", 0, H + (size_t)(t + 1) * M * c.n_b, c.n_b, M, c.n_b, 2 * c.n_m,
@@ -449,6 +493,22 @@ static int step_act(marlc_engine* e, int t, const int64_t* act_in, cudaStream_t 
     pa.npos_out = e->buf("npos") + (size_t)(t + 1) * M * 2;
     for (int j = 0; j < c.n_actions; ++j) { pa.moves[2 * j] = c.actions[j][0]; pa.moves[2 * j + 1] = c.actions[j][1]; }
     pa.M = M; pa.nl = c.nl_a; pa.nA = c.n_actions; pa.t = t; pa.f = c.f; pa.H = c.H; pa.W = c.W;
+    if (c.use_chains) {
+        // fused "post" launch: policy LN/SiLU + logits + softmax + sample + transition | encoder tail
+        StepPostArgs sp;
+        memset(&sp, 0, sizeof(sp));
+        sp.act = pa;
+        sp.pol_y1 = e->buf("pol_y1") + (size_t)t * M * c.nl_a;
+        sp.pol_g = e->prm("policy.1.weight"); sp.pol_be = e->prm("policy.1.bias");
+        sp.enc_y1 = e->buf("enc_y1") + (size_t)t * M * 2 * c.n_m;
+        sp.enc_g = e->prm("encode_msg.1.weight"); sp.enc_be = e->prm("encode_msg.1.bias");
+        sp.enc_s1 = e->buf("enc_s1") + (size_t)t * M * 2 * c.n_m;
+        sp.e3 = chain_lin(e, "encode_msg", 3, 2 * c.n_m, c.n_m, true);
+        sp.enc_y2 = e->buf("enc_y2") + (size_t)t * M * c.n_m;
+        sp.msg_out = e->buf("msg") + (size_t)(t + 1) * M * c.n_m;
+        sp.M = M;
+        return step_post(sp, s);
+    }
     return policy_act(pa, s);
 }
 
@@ -627,6 +687,105 @@ extern "C" int marlc_episode_backward(marlc_engine* e, const float* img, int acc
     MARLC_CUDA(cudaMemsetAsync(dc[0], 0, sizeof(float) * (size_t)M * c.n_b, s));
     MARLC_CUDA(cudaMemsetAsync(dcc[0], 0, sizeof(float) * (size_t)M * c.n_a, s));
     int cur = 0;
+    if (c.use_chains) {
+        float* dcoll = e->buf("dcoll");
+        for (int t = T - 1; t >= 0; --t) {
+            float* dgb = e->buf("dgates_b") + (size_t)t * M * 4 * c.n_b;
+            float* dga = e->buf("dgates_a") + (size_t)t * M * 4 * c.n_a;
+            // fused: adjoint mean + encoder backward + dh accumulation + both LSTM cells' point-wise backward
+            BwdPreArgs bp;
+            memset(&bp, 0, sizeof(bp));
+            bp.dcoll = (t < T - 1) ? dcoll : nullptr;  // the last message is never consumed
+            bp.e0 = chain_lin(e, "encode_msg", 0, c.n_b, 2 * c.n_m, true);
+            bp.e3 = chain_lin(e, "encode_msg", 3, 2 * c.n_m, c.n_m, true);
+            bp.enc_y1 = e->buf("enc_y1") + (size_t)t * M * 2 * c.n_m;
+            bp.enc_y2 = e->buf("enc_y2") + (size_t)t * M * c.n_m;
+            bp.d_enc_y1 = e->buf("d_enc_y1") + (size_t)t * M * 2 * c.n_m;
+            bp.d_enc_y2 = e->buf("d_enc_y2") + (size_t)t * M * c.n_m;
+            bp.dh_carry[0] = (t < T - 1) ? dh : nullptr;
+            bp.dh_carry[1] = (t < T - 1) ? dhc : nullptr;
+            bp.dh_heads[0] = e->buf("dH_heads") + (size_t)t * M * c.n_b;
+            bp.dh_heads[1] = e->buf("dHc_heads") + (size_t)t * M * c.n_a;
+            bp.dc_next[0] = (t < T - 1) ? dc[cur] : nullptr;
+            bp.dc_next[1] = (t < T - 1) ? dcc[cur] : nullptr;
+            bp.gates[0] = e->buf("gates_b") + (size_t)t * M * 4 * c.n_b;
+            bp.gates[1] = e->buf("gates_a") + (size_t)t * M * 4 * c.n_a;
+            bp.c_prev[0] = Cb + (size_t)t * M * c.n_b;
+            bp.c_prev[1] = Cc + (size_t)t * M * c.n_a;
+            bp.c_new[0] = Cb + (size_t)(t + 1) * M * c.n_b;
+            bp.c_new[1] = Cc + (size_t)(t + 1) * M * c.n_a;
+            bp.dgates[0] = dgb; bp.dgates[1] = dga;
+            bp.dc_prev[0] = dc[cur ^ 1]; bp.dc_prev[1] = dcc[cur ^ 1];
+            bp.n[0] = c.n_b; bp.n[1] = c.n_a;
+            bp.Na = c.na; bp.Nb = c.nb; bp.M = M; bp.n_m = c.n_m;
+            MARLC_TRY(bwd_pre(bp, s));
+            cur ^= 1;
+            // input gradients: du = dg_b Wih_b + dg_a Wih_a ; dh = dg_b Whh_b ; dh^ = dg_a Whh_a
+            float* dUt = dU + (size_t)t * M * Kin;
+            bool tc_dx = false;
+            if (c.use_tc) {
+                TcGemmArgs a;
+                a.A = tc_op(dgb, 4 * c.n_b); a.B = tc_op(e->prm(std::string(LSTM_B) + "weight_ih"), Kin, true); a.K = 4 * c.n_b;
+                a.A2 = tc_op(dga, 4 * c.n_a); a.B2 = tc_op(e->prm(std::string(LSTM_A) + "weight_ih"), Kin, true); a.K2 = 4 * c.n_a;
+                a.C = dUt; a.ldc = Kin; a.M = M; a.N = Kin; a.allow_split = 1;
+                TcGemmArgs b;
+                b.A = tc_op(dgb, 4 * c.n_b); b.B = tc_op(e->prm(std::string(LSTM_B) + "weight_hh"), c.n_b, true); b.K = 4 * c.n_b;
+                b.C = dh; b.ldc = c.n_b; b.M = M; b.N = c.n_b; b.allow_split = 1;
+                TcGemmArgs d;
+                d.A = tc_op(dga, 4 * c.n_a); d.B = tc_op(e->prm(std::string(LSTM_A) + "weight_hh"), c.n_a, true); d.K = 4 * c.n_a;
+                d.C = dhc; d.ldc = c.n_a; d.M = M; d.N = c.n_a; d.allow_split = 1;
+                if (tc_operand_ok(a.A) && tc_operand_ok(a.B) && tc_operand_ok(a.A2) && tc_operand_ok(a.B2) &&
+                    tc_operand_ok(b.B) && tc_operand_ok(d.B) && c.n_a >= 16 && c.n_b >= 16) {
+                    MARLC_TRY(tc_gemm(a, s));
+                    MARLC_TRY(tc_gemm(b, s));
+                    MARLC_TRY(tc_gemm(d, s));
+                    tc_dx = true;
+                }
+            }
+            if (!tc_dx) {
+            GemmGroup gg;
+            memset(&gg, 0, sizeof(gg));
+            gg.count = 3;
+            {
+                GemmProblem& p = gg.p[0];
+                p.A = dgb; p.sam = 4 * c.n_b; p.sak = 1;
+                p.B = e->prm(std::string(LSTM_B) + "weight_ih"); p.sbk = Kin; p.sbn = 1;
+                p.A2 = dga; p.sam2 = 4 * c.n_a; p.sak2 = 1;
+                p.B2 = e->prm(std::string(LSTM_A) + "weight_ih"); p.sbk2 = Kin; p.sbn2 = 1;
+                p.C = dUt; p.ldc = Kin;
+                p.M = M; p.N = Kin; p.K = 4 * c.n_b; p.K2 = 4 * c.n_a;
+            }
+            {
+                GemmProblem& p = gg.p[1];
+                p.A = dgb; p.sam = 4 * c.n_b; p.sak = 1;
+                p.B = e->prm(std::string(LSTM_B) + "weight_hh"); p.sbk = c.n_b; p.sbn = 1;
+                p.C = dh; p.ldc = c.n_b;
+                p.M = M; p.N = c.n_b; p.K = 4 * c.n_b;
+            }
+            {
+                GemmProblem& p = gg.p[2];
+                p.A = dga; p.sam = 4 * c.n_a; p.sak = 1;
+                p.B = e->prm(std::string(LSTM_A) + "weight_hh"); p.sbk = c.n_a; p.sbn = 1;
+                p.C = dhc; p.ldc = c.n_a;
+                p.M = M; p.N = c.n_a; p.K = 4 * c.n_a;
+            }
+            MARLC_TRY(gemm_group(gg, s));
+            }
+            // fused decoder backward (models.py:97-98) -> dcoll for step t-1
+            BwdPostArgs bq;
+            memset(&bq, 0, sizeof(bq));
+            bq.dU = dUt; bq.ldu = Kin; bq.F = F;
+            bq.d0 = chain_lin(e, "decode_msg", 0, c.n_m, 2 * c.n_m, true);
+            bq.d3 = chain_lin(e, "decode_msg", 3, 2 * c.n_m, c.n_m_o, true);
+            bq.dec_y1 = e->buf("dec_y1") + (size_t)t * M * 2 * c.n_m;
+            bq.dec_y2 = e->buf("dec_y2") + (size_t)t * M * c.n_m_o;
+            bq.d_dec_y1 = e->buf("d_dec_y1") + (size_t)t * M * 2 * c.n_m;
+            bq.d_dec_y2 = e->buf("d_dec_y2") + (size_t)t * M * c.n_m_o;
+            bq.dcoll = t > 0 ? dcoll : nullptr;
+            bq.M = M; bq.n_m = c.n_m; bq.n_m_o = c.n_m_o;
+            MARLC_TRY(bwd_post(bq, s));
+        }
+    } else
     for (int t = T - 1; t >= 0; --t) {
         if (t < T - 1) {
             // message produced at step t was consumed at t+1: encoder backward (models.py:114-116)

@@ -42,6 +42,7 @@ def build_config(model, *, na: int, nb: int, T: int, C: int, H: int, W: int, act
     cfg.nl_b, cfg.nl_a, cfg.nb_class = d["nl_b"], d["nl_a"], d["nb_class"]
     cfg.gamma = float(gamma)
     cfg.use_tc = 1 if getattr(model, "use_tc", True) else 0
+    cfg.use_chains = 1 if getattr(model, "use_chains", True) else 0
     return cfg
 
 
@@ -193,7 +194,8 @@ def C_void_p():
 def get_engine(model, *, na, nb, T, C, H, W, actions, gamma=0.99) -> EpisodeEngine:
     """Engines are cached on the model per geometry (workspaces are reused across iterations)."""
     model.ensure_flat()
-    key = (na, nb, T, C, H, W, tuple(tuple(a) for a in actions), float(gamma), bool(getattr(model, "use_tc", True)))
+    key = (na, nb, T, C, H, W, tuple(tuple(a) for a in actions), float(gamma), bool(getattr(model, "use_tc", True)),
+           bool(getattr(model, "use_chains", True)))
     eng = model._engines.get(key)
     if eng is None:
         eng = EpisodeEngine(model, na=na, nb=nb, T=T, C=C, H=H, W=W, actions=actions, gamma=gamma)

@@ -87,6 +87,7 @@ class ModelsWrapper(nn.Module):
         self._flat_grads: th.Tensor | None = None
         self._engines: dict = {}
         self.use_tc = True  # tcgen05 TF32 GEMMs where shapes allow; False = exact fp32 everywhere
+        self.use_chains = True  # fused per-step chain kernels; False = one kernel per op (debug / comparison)
 
     # ---- reference surface ------------------------------------------------------
     @property

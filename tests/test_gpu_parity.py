@@ -492,3 +492,24 @@ def test_graphed_step_matches_eager():
         finals.append((model.flat_params.clone(), out.clone()))
     assert rel_l2(finals[1][0].cpu(), finals[0][0].cpu()) < 1e-4
     assert abs(finals[1][1][0].item() - finals[0][1][0].item()) <= 1e-3 * abs(finals[0][1][0].item())
+
+
+@pytest.mark.parametrize("name", ["conftest_odd", "aid_small"])
+def test_chains_match_unfused(name):
+    """The fused per-step chain kernels against the one-kernel-per-op path (both exact fp32)."""
+    fx = load_golden(name)
+    img, y = fx["img"].to(DEV), fx["targets"].to(DEV)
+    res = []
+    for chains in (False, True):
+        model, marl, env, sampler, inject = run_fixture(fx)
+        model.use_chains = chains
+        eng = sampler.engine_for(img)
+        eng.forward(img, **inject)
+        loss = eng.loss(y).clone()
+        eng.backward()
+        res.append((eng.step_preds.clone(), eng.step_values.clone(), eng.step_log_probas.clone(), loss,
+                    model.flat_grads.clone(), eng.launches.copy()))
+    print("launches unfused/fused:", res[0][5], res[1][5])
+    for a, b in zip(res[0][:5], res[1][:5]):
+        assert rel_l2(b.cpu(), a.cpu()) < 1e-5
+    assert res[1][5]["forward"] < res[0][5]["forward"] and res[1][5]["backward"] < res[0][5]["backward"]
