@@ -85,6 +85,48 @@ __device__ void rb_dx(const float* dyT, const float* __restrict__ W, float* out,
     __syncthreads();
 }
 
+
+// ---- shared-memory resident weights -------------------------------------------------
+// The whole weight matrix of a small layer is copied once into shared memory (coalesced
+// 128-bit global loads, all independent) so the inner loops never wait on L2.
+__device__ __forceinline__ void stage_w(float* dst, const float* __restrict__ W, int N, int K, int P) {
+    stage_rows(dst, W, N, K, P);
+}
+__host__ __device__ inline int odd_pitch(int K) { return K | 1; }
+
+// rb_linear with W resident in smem (row pitch P odd => conflict-free column walk)
+__device__ void rb_linear_s(const float* xT, const float* Ws, int P, const float* __restrict__ bias, float* ys, int ldy,
+                            int N, int K) {
+    for (int n = threadIdx.x; n < N; n += CT) {
+        const float* w = Ws + n * P;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+        for (int k = 0; k < K; ++k) {
+            const float wv = w[k];
+            const float4 x = *reinterpret_cast<const float4*>(xT + k * RB);
+            a0 = fmaf(wv, x.x, a0); a1 = fmaf(wv, x.y, a1); a2 = fmaf(wv, x.z, a2); a3 = fmaf(wv, x.w, a3);
+        }
+        const float b = bias ? bias[n] : 0.f;
+        ys[n] = a0 + b; ys[ldy + n] = a1 + b; ys[2 * ldy + n] = a2 + b; ys[3 * ldy + n] = a3 + b;
+    }
+    __syncthreads();
+}
+
+// rb_dx with W resident in smem
+__device__ void rb_dx_s(const float* dyT, const float* Ws, int P, float* out, int ldo, int N, int K) {
+    for (int k = threadIdx.x; k < K; k += CT) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+        for (int n = 0; n < N; ++n) {
+            const float wv = Ws[n * P + k];
+            const float4 d = *reinterpret_cast<const float4*>(dyT + n * RB);
+            a0 = fmaf(wv, d.x, a0); a1 = fmaf(wv, d.y, a1); a2 = fmaf(wv, d.z, a2); a3 = fmaf(wv, d.w, a3);
+        }
+        out[k] = a0; out[ldo + k] = a1; out[2 * ldo + k] = a2; out[3 * ldo + k] = a3;
+    }
+    __syncthreads();
+}
+
 // LayerNorm + SiLU on RB rows held in smem ys[r][n]; warp r handles row r.
 //   pre_g : optional global copy of the pre-norm values (saved for backward)
 //   s_g   : optional global output          sT: optional smem output, transposed [n][RB]
@@ -191,12 +233,19 @@ __device__ __forceinline__ float other_agents_mean(const float* __restrict__ x, 
 }
 
 struct ChainSmem {
-    float *bufA, *bufB, *bufC, *bufT, *wt;
+    float *bufA, *bufB, *bufC, *bufT, *wt, *wres;
     __device__ ChainSmem(float* sm, int maxw) {
         bufA = sm; bufB = bufA + RB * maxw; bufC = bufB + RB * maxw; bufT = bufC + RB * maxw; wt = bufT + RB * maxw;
+        wres = wt + CT * WT_P;
     }
 };
 static size_t chain_smem_bytes(int maxw) { return sizeof(float) * ((size_t)4 * RB * maxw + (size_t)CT * WT_P); }
+constexpr size_t CHAIN_SMEM_LIMIT = 200 * 1024;
+// floats of staged weights for two matrices, or 0 if they do not fit next to the row buffers
+static int staged_floats(int maxw, int n1, int p1, int n2, int p2) {
+    const size_t w = (size_t)n1 * p1 + (size_t)n2 * p2;
+    return (chain_smem_bytes(maxw) + sizeof(float) * w <= CHAIN_SMEM_LIMIT) ? (int)w : 0;
+}
 static int maxw_of(std::initializer_list<int> v) {
     int m = 4;
     for (int x : v) m = max(m, x);
@@ -206,7 +255,7 @@ static int maxw_of(std::initializer_list<int> v) {
 // ---------------------------------------------------------------------------------
 // forward "pre": CNN role (blocks [0,M)) | decoder + position-feature role
 // ---------------------------------------------------------------------------------
-struct StepPreKernelArgs { StepPreArgs a; int maxw; };
+struct StepPreKernelArgs { StepPreArgs a; int maxw; int staged; };
 
 __global__ void __launch_bounds__(CT) step_pre_kernel(const StepPreKernelArgs ka) {
     extern __shared__ __align__(16) float sm[];
@@ -219,6 +268,10 @@ __global__ void __launch_bounds__(CT) step_pre_kernel(const StepPreKernelArgs ka
     const int rows_valid = min(RB, a.M - row0);
     const int n_m = a.d0.n_in, n1 = a.d0.n_out, n2 = a.d3.n_out;
     ChainSmem S(sm, ka.maxw);
+    const int P0 = odd_pitch(n_m), P3 = odd_pitch(n1);
+    float* W0s = S.wres;
+    float* W3s = W0s + n1 * P0;
+    if (ka.staged) { stage_w(W0s, a.d0.W, n1, n_m, P0); stage_w(W3s, a.d3.W, n2, n1, P3); }
     // collected message (mean of the other agents)                      message.py:5-17
     for (int e = threadIdx.x; e < RB * n_m; e += CT) {
         const int r = e / n_m, j = e % n_m;
@@ -231,9 +284,11 @@ __global__ void __launch_bounds__(CT) step_pre_kernel(const StepPreKernelArgs ka
     }
     __syncthreads();
     // decoder block 0 and block 3                                        message.py:36-49
-    rb_linear(S.bufT, a.d0.W, a.d0.b, S.bufA, ka.maxw, n1, n_m, S.wt);
+    if (ka.staged) rb_linear_s(S.bufT, W0s, P0, a.d0.b, S.bufA, ka.maxw, n1, n_m);
+    else rb_linear(S.bufT, a.d0.W, a.d0.b, S.bufA, ka.maxw, n1, n_m, S.wt);
     rb_ln_silu(S.bufA, ka.maxw, n1, a.d0.g, a.d0.be, rows_valid, row0, a.dec_y1, n1, a.dec_s1, n1, S.bufT);
-    rb_linear(S.bufT, a.d3.W, a.d3.b, S.bufA, ka.maxw, n2, n1, S.wt);
+    if (ka.staged) rb_linear_s(S.bufT, W3s, P3, a.d3.b, S.bufA, ka.maxw, n2, n1);
+    else rb_linear(S.bufT, a.d3.W, a.d3.b, S.bufA, ka.maxw, n2, n1, S.wt);
     rb_ln_silu(S.bufA, ka.maxw, n2, a.d3.g, a.d3.be, rows_valid, row0, a.dec_y2, n2, a.U + a.F, a.ldu, nullptr);
     // position features                                                  state.py:7-17
     {
@@ -265,7 +320,9 @@ int step_pre(const StepPreArgs& a, cudaStream_t s) {
     StepPreKernelArgs ka;
     ka.a = a;
     ka.maxw = maxw_of({a.d0.n_in, a.d0.n_out, a.d3.n_out, a.pos.n_out});
-    const size_t smem = max(chain_smem_bytes(ka.maxw), sizeof(float) * 2 * (size_t)a.cnn.bufsz);
+    const int wfl = staged_floats(ka.maxw, a.d0.n_out, odd_pitch(a.d0.n_in), a.d3.n_out, odd_pitch(a.d3.n_in));
+    ka.staged = wfl > 0;
+    const size_t smem = max(chain_smem_bytes(ka.maxw) + sizeof(float) * (size_t)wfl, cnn_fwd_smem_bytes(a.cnn));
     MARLC_CHECK(smem <= 200 * 1024, "step_pre: shared memory %zu B too large", smem);
     static size_t attr = 0;
     if (smem > 48 * 1024 && smem > attr) {
@@ -349,7 +406,7 @@ __device__ void policy_tail_row(const StepPostArgs& a, const int m, float* srow 
     }
 }
 
-struct StepPostKernelArgs { StepPostArgs a; int maxw; int pol_blocks; };
+struct StepPostKernelArgs { StepPostArgs a; int maxw; int pol_blocks; int staged; };
 
 __global__ void __launch_bounds__(CT) step_post_kernel(const StepPostKernelArgs ka) {
     extern __shared__ __align__(16) float sm[];
@@ -364,13 +421,16 @@ __global__ void __launch_bounds__(CT) step_post_kernel(const StepPostKernelArgs 
     const int rows_valid = min(RB, a.M - row0);
     const int n1 = a.e3.n_in, n2 = a.e3.n_out;
     ChainSmem S(sm, ka.maxw);
+    const int P3 = odd_pitch(n1);
+    if (ka.staged) stage_w(S.wres, a.e3.W, n2, n1, P3);
     for (int e = threadIdx.x; e < RB * n1; e += CT) {
         const int r = e / n1, k = e % n1;
         S.bufA[r * ka.maxw + k] = r < rows_valid ? a.enc_y1[(long)(row0 + r) * n1 + k] : 0.f;
     }
     __syncthreads();
     rb_ln_silu(S.bufA, ka.maxw, n1, a.enc_g, a.enc_be, rows_valid, row0, nullptr, 0, a.enc_s1, n1, S.bufT);
-    rb_linear(S.bufT, a.e3.W, a.e3.b, S.bufA, ka.maxw, n2, n1, S.wt);
+    if (ka.staged) rb_linear_s(S.bufT, S.wres, P3, a.e3.b, S.bufA, ka.maxw, n2, n1);
+    else rb_linear(S.bufT, a.e3.W, a.e3.b, S.bufA, ka.maxw, n2, n1, S.wt);
     rb_ln_silu(S.bufA, ka.maxw, n2, a.e3.g, a.e3.be, rows_valid, row0, a.enc_y2, n2, a.msg_out, n2, nullptr);
 }
 
@@ -381,7 +441,9 @@ int step_post(const StepPostArgs& a, cudaStream_t s) {
     ka.a = a;
     ka.maxw = maxw_of({a.e3.n_in, a.e3.n_out});
     ka.pol_blocks = (a.M + CT / 32 - 1) / (CT / 32);
-    const size_t smem = max(chain_smem_bytes(ka.maxw), sizeof(float) * (size_t)(CT / 32) * a.act.nl);
+    const int wfl = staged_floats(ka.maxw, a.e3.n_out, odd_pitch(a.e3.n_in), 0, 0);
+    ka.staged = wfl > 0;
+    const size_t smem = max(chain_smem_bytes(ka.maxw) + sizeof(float) * (size_t)wfl, sizeof(float) * (size_t)(CT / 32) * a.act.nl);
     MARLC_CHECK(smem <= 200 * 1024, "step_post: shared memory %zu B too large", smem);
     static size_t attr = 0;
     if (smem > 48 * 1024 && smem > attr) {
@@ -397,7 +459,7 @@ int step_post(const StepPostArgs& a, cudaStream_t s) {
 // ---------------------------------------------------------------------------------
 // backward "pre" (step t): adjoint message mean -> encoder backward -> dh += ... -> both LSTM cells
 // ---------------------------------------------------------------------------------
-struct BwdPreKernelArgs { BwdPreArgs a; int maxw; };
+struct BwdPreKernelArgs { BwdPreArgs a; int maxw; int staged; };
 
 __global__ void __launch_bounds__(CT) bwd_pre_kernel(const BwdPreKernelArgs ka) {
     extern __shared__ __align__(16) float sm[];
@@ -406,7 +468,10 @@ __global__ void __launch_bounds__(CT) bwd_pre_kernel(const BwdPreKernelArgs ka) 
     ChainSmem S(sm, mw);
     const int n_m = a.n_m, n1 = a.e0.n_out, nb = a.n[0];
     float* dhx = S.bufC;  // [RB][mw] encoder contribution to dh (belief cell only)
+    float* W3s = S.wres;             // encode_msg.3 weight [n_m][n1]
+    float* W0s = W3s + n_m * n1;     // encode_msg.0 weight [n1][nb]
     if (a.dcoll) {
+        if (ka.staged) { stage_w(W3s, a.e3.W, n_m, n1, n1); stage_w(W0s, a.e0.W, n1, nb, nb); }
         // gradient of the message produced at step t = adjoint mean of dcoll(t+1); encoder block 3 backward
         for (int e = threadIdx.x; e < RB * n_m; e += CT) {
             const int r = e / n_m, j = e % n_m;
@@ -417,7 +482,8 @@ __global__ void __launch_bounds__(CT) bwd_pre_kernel(const BwdPreKernelArgs ka) 
         __syncthreads();
         rb_ln_silu_bwd(S.bufA, S.bufB, mw, n_m, a.e3.g, a.e3.be, rows_valid, row0, dhx, S.bufT, a.d_enc_y2, n_m,
                        a.e3.dg, a.e3.dbe, a.e3.db);
-        rb_dx(S.bufT, a.e3.W, S.bufA, mw, n_m, n1);  // ds1 [RB][2n_m]
+        if (ka.staged) rb_dx_s(S.bufT, W3s, n1, S.bufA, mw, n_m, n1);  // ds1 [RB][2n_m]
+        else rb_dx(S.bufT, a.e3.W, S.bufA, mw, n_m, n1);
         for (int e = threadIdx.x; e < RB * n1; e += CT) {
             const int r = e / n1, k = e % n1;
             S.bufB[r * mw + k] = r < rows_valid ? a.enc_y1[(long)(row0 + r) * n1 + k] : 0.f;
@@ -425,7 +491,8 @@ __global__ void __launch_bounds__(CT) bwd_pre_kernel(const BwdPreKernelArgs ka) 
         __syncthreads();
         rb_ln_silu_bwd(S.bufA, S.bufB, mw, n1, a.e0.g, a.e0.be, rows_valid, row0, dhx, S.bufT, a.d_enc_y1, n1,
                        a.e0.dg, a.e0.dbe, a.e0.db);
-        rb_dx(S.bufT, a.e0.W, dhx, mw, n1, nb);      // dh contribution [RB][n_b]
+        if (ka.staged) rb_dx_s(S.bufT, W0s, nb, dhx, mw, n1, nb);      // dh contribution [RB][n_b]
+        else rb_dx(S.bufT, a.e0.W, dhx, mw, n1, nb);
     }
     // point-wise LSTM backward, both cells (recurrent.py:30)
     for (int k = 0; k < 2; ++k) {
@@ -455,7 +522,9 @@ int bwd_pre(const BwdPreArgs& a, cudaStream_t s) {
     BwdPreKernelArgs ka;
     ka.a = a;
     ka.maxw = maxw_of({a.n_m, a.e0.n_out, a.n[0]});
-    const size_t smem = chain_smem_bytes(ka.maxw);
+    const int wfl = staged_floats(ka.maxw, a.n_m, a.e0.n_out, a.e0.n_out, a.n[0]);
+    ka.staged = wfl > 0;
+    const size_t smem = chain_smem_bytes(ka.maxw) + sizeof(float) * (size_t)wfl;
     MARLC_CHECK(smem <= 200 * 1024, "bwd_pre: shared memory %zu B too large", smem);
     static size_t attr = 0;
     if (smem > 48 * 1024 && smem > attr) {
@@ -470,7 +539,7 @@ int bwd_pre(const BwdPreArgs& a, cudaStream_t s) {
 // ---------------------------------------------------------------------------------
 // backward "post" (step t): decoder backward from du_t -> dcoll
 // ---------------------------------------------------------------------------------
-struct BwdPostKernelArgs { BwdPostArgs a; int maxw; };
+struct BwdPostKernelArgs { BwdPostArgs a; int maxw; int staged; };
 
 __global__ void __launch_bounds__(CT) bwd_post_kernel(const BwdPostKernelArgs ka) {
     extern __shared__ __align__(16) float sm[];
@@ -478,6 +547,9 @@ __global__ void __launch_bounds__(CT) bwd_post_kernel(const BwdPostKernelArgs ka
     const int row0 = blockIdx.x * RB, rows_valid = min(RB, a.M - row0), mw = ka.maxw;
     ChainSmem S(sm, mw);
     const int n_m = a.n_m, n1 = a.d0.n_out, n2 = a.n_m_o;
+    float* W3s = S.wres;           // decode_msg.3 weight [n2][n1]
+    float* W0s = W3s + n2 * n1;    // decode_msg.0 weight [n1][n_m]
+    if (ka.staged) { stage_w(W3s, a.d3.W, n2, n1, n1); if (a.dcoll) stage_w(W0s, a.d0.W, n1, n_m, n_m); }
     for (int e = threadIdx.x; e < RB * n2; e += CT) {
         const int r = e / n2, j = e % n2;
         const bool ok = r < rows_valid;
@@ -487,7 +559,8 @@ __global__ void __launch_bounds__(CT) bwd_post_kernel(const BwdPostKernelArgs ka
     __syncthreads();
     rb_ln_silu_bwd(S.bufA, S.bufB, mw, n2, a.d3.g, a.d3.be, rows_valid, row0, S.bufC, S.bufT, a.d_dec_y2, n2, a.d3.dg,
                    a.d3.dbe, a.d3.db);
-    rb_dx(S.bufT, a.d3.W, S.bufA, mw, n2, n1);
+    if (ka.staged) rb_dx_s(S.bufT, W3s, n1, S.bufA, mw, n2, n1);
+    else rb_dx(S.bufT, a.d3.W, S.bufA, mw, n2, n1);
     for (int e = threadIdx.x; e < RB * n1; e += CT) {
         const int r = e / n1, k = e % n1;
         S.bufB[r * mw + k] = r < rows_valid ? a.dec_y1[(long)(row0 + r) * n1 + k] : 0.f;
@@ -496,7 +569,8 @@ __global__ void __launch_bounds__(CT) bwd_post_kernel(const BwdPostKernelArgs ka
     rb_ln_silu_bwd(S.bufA, S.bufB, mw, n1, a.d0.g, a.d0.be, rows_valid, row0, S.bufC, S.bufT, a.d_dec_y1, n1, a.d0.dg,
                    a.d0.dbe, a.d0.db);
     if (a.dcoll) {
-        rb_dx(S.bufT, a.d0.W, S.bufA, mw, n1, n_m);
+        if (ka.staged) rb_dx_s(S.bufT, W0s, n_m, S.bufA, mw, n1, n_m);
+        else rb_dx(S.bufT, a.d0.W, S.bufA, mw, n1, n_m);
         for (int e = threadIdx.x; e < rows_valid * n_m; e += CT) {
             const int r = e / n_m, j = e % n_m;
             a.dcoll[(long)(row0 + r) * n_m + j] = S.bufA[r * mw + j];
@@ -509,7 +583,9 @@ int bwd_post(const BwdPostArgs& a, cudaStream_t s) {
     BwdPostKernelArgs ka;
     ka.a = a;
     ka.maxw = maxw_of({a.n_m, a.d0.n_out, a.n_m_o});
-    const size_t smem = chain_smem_bytes(ka.maxw);
+    const int wfl = staged_floats(ka.maxw, a.n_m_o, a.d0.n_out, a.d0.n_out, a.n_m);
+    ka.staged = wfl > 0;
+    const size_t smem = chain_smem_bytes(ka.maxw) + sizeof(float) * (size_t)wfl;
     MARLC_CHECK(smem <= 200 * 1024, "bwd_post: shared memory %zu B too large", smem);
     static size_t attr = 0;
     if (smem > 48 * 1024 && smem > attr) {

@@ -36,7 +36,6 @@ struct StepPreArgs {
     float* U;             // [M,ldu]: decoder output at column F, position features at F+n_m_o
     long ldu;
     int F, Na, Nb, M;
-    int cnn_smem_floats;
 };
 int step_pre(const StepPreArgs& a, cudaStream_t s);
 

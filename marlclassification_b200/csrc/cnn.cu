@@ -13,23 +13,21 @@ __global__ void __launch_bounds__(256) cnn_fwd_kernel(const CnnFwdArgs a) {
     cnn_fwd_block(a, blockIdx.x, sm);
 }
 
-static int max_act(const CnnDesc& d) {
-    int mx = d.cin[0] * d.f * d.f;
-    for (int l = 0; l < d.L; ++l) mx = max(mx, d.cout[l] * d.hout[l] * d.hout[l]);
-    return mx;
-}
-
 int cnn_fwd(const CnnDesc& d, const float* img, const int* pos, const float* patch, int B, int H, int W, int M,
             float* const* y_save, float* out, long ldo, cudaStream_t s) {
     if (M <= 0) return 0;
     CnnFwdArgs a;
     a.d = d; a.img = img; a.pos = pos; a.patch = patch; a.out = out; a.ldo = ldo;
-    a.B = B; a.H = H; a.W = W; a.M = M; a.bufsz = max_act(d);
+    a.B = B; a.H = H; a.W = W; a.M = M;
+    cnn_fwd_plan(d, &a.padsz, &a.ysz, &a.wbuf);
     for (int l = 0; l < MAX_CNN_LAYERS; ++l) a.y_save[l] = (y_save && l < d.L) ? y_save[l] : nullptr;
-    size_t smem = sizeof(float) * 2 * (size_t)a.bufsz;
+    size_t smem = cnn_fwd_smem_bytes(a);
     MARLC_CHECK(smem <= 200 * 1024, "cnn_fwd: window too large for shared memory (%zu B)", smem);
-    if (smem > 48 * 1024)
+    static size_t attr = 0;
+    if (smem > 48 * 1024 && smem > attr) {
         MARLC_CUDA(cudaFuncSetAttribute(cnn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = smem;
+    }
     cnn_fwd_kernel<<<M, 256, smem, s>>>(a);
     MARLC_LAUNCH_CHECK();
     return 0;
@@ -52,7 +50,7 @@ struct CnnBwdArgs {
     long lddo;
     CnnBwdBuffers buf;
     int offA[MAX_CNN_LAYERS], offY[MAX_CNN_LAYERS], offStat[MAX_CNN_LAYERS];
-    int offD0, offD1;
+    int offD0, offD1, offW, wbuf;
     int B, H, W, M, P;
 };
 
@@ -173,31 +171,46 @@ __global__ void __launch_bounds__(256) cnn_bwd_kernel(const CnnBwdArgs a) {
                 colg[e] = (iy >= 0 && iy < hi && ix >= 0 && ix < hi) ? A[ci * hi * hi + iy * hi + ix] : 0.f;
             }
         }
-        // 4. input gradient dA_l (not needed for the image itself)
+        // 4. input gradient dA_l (not needed for the image itself); weights staged in smem chunks
         if (l > 0) {
             const float* __restrict__ w = d.w[l];
-            const int tin = ci_n * hi * hi;
-            for (int e = tid; e < tin; e += nt) {
-                const int ci = e / (hi * hi), iy = (e / hi) % hi, ix = e % hi;
-                float acc = 0.f;
+            const int tin = ci_n * hi * hi, wrow = ci_n * 9, P = cnn_wpitch(wrow);
+            const int cc = min(co_n, a.wbuf / P);
+            float* ws = sm + a.offW;
+            for (int co0 = 0; co0 < co_n; co0 += cc) {
+                const int ncur = min(cc, co_n - co0);
+                __syncthreads();
+                stage_rows(ws, w + (long)co0 * wrow, ncur, wrow, P);
+                __syncthreads();
+                for (int e = tid; e < tin; e += nt) {
+                    const int ci = e / (hi * hi), iy = (e / hi) % hi, ix = e % hi;
+                    float acc = co0 == 0 ? 0.f : Dprev[e];
 #pragma unroll
-                for (int ky = 0; ky < 3; ++ky) {
-                    const int ty = iy + 1 - ky;
-                    if (ty < 0 || (ty & 1)) continue;
-                    const int oy = ty >> 1;
-                    if (oy >= ho) continue;
+                    for (int ky = 0; ky < 3; ++ky) {
+                        const int ty = iy + 1 - ky;
+                        if (ty < 0 || (ty & 1)) continue;
+                        const int oy = ty >> 1;
+                        if (oy >= ho) continue;
 #pragma unroll
-                    for (int kx = 0; kx < 3; ++kx) {
-                        const int tx = ix + 1 - kx;
-                        if (tx < 0 || (tx & 1)) continue;
-                        const int ox = tx >> 1;
-                        if (ox >= ho) continue;
-                        const float* wp = w + (long)ci * 9 + ky * 3 + kx;
-                        const float* dp = Dcur + oy * ho + ox;
-                        for (int co = 0; co < co_n; ++co) acc = fmaf(dp[co * npos], wp[(long)co * ci_n * 9], acc);
+                        for (int kx = 0; kx < 3; ++kx) {
+                            const int tx = ix + 1 - kx;
+                            if (tx < 0 || (tx & 1)) continue;
+                            const int ox = tx >> 1;
+                            if (ox >= ho) continue;
+                            const float* wp = ws + ci * 9 + ky * 3 + kx;
+                            const float* dp = Dcur + (long)co0 * npos + oy * ho + ox;
+                            float a0 = 0.f, a1 = 0.f;
+                            int cq = 0;
+                            for (; cq + 1 < ncur; cq += 2) {
+                                a0 = fmaf(dp[cq * npos], wp[cq * P], a0);
+                                a1 = fmaf(dp[(cq + 1) * npos], wp[(cq + 1) * P], a1);
+                            }
+                            if (cq < ncur) a0 = fmaf(dp[cq * npos], wp[cq * P], a0);
+                            acc += a0 + a1;
+                        }
                     }
+                    Dprev[e] = acc;
                 }
-                Dprev[e] = acc;
             }
         }
         __syncthreads();
@@ -222,10 +235,19 @@ int cnn_bwd(const CnnDesc& d, const float* img, const int* pos_hist, int B, int 
     }
     a.offD0 = off; off += mx;
     a.offD1 = off; off += mx;
+    {
+        int wmax = 0;
+        for (int l = 1; l < d.L; ++l) wmax = max(wmax, d.cout[l] * cnn_wpitch(d.cin[l] * 9));
+        a.wbuf = min(wmax, 24 * 1024);
+        a.offW = off; off += a.wbuf;
+    }
     size_t smem = sizeof(float) * (size_t)off;
     MARLC_CHECK(smem <= 200 * 1024, "cnn_bwd: window too large for shared memory (%zu B)", smem);
-    if (smem > 48 * 1024)
+    static size_t attr_b = 0;
+    if (smem > 48 * 1024 && smem > attr_b) {
         MARLC_CUDA(cudaFuncSetAttribute(cnn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_b = smem;
+    }
     cnn_bwd_kernel<<<P, 256, smem, s>>>(a);
     MARLC_LAUNCH_CHECK();
     return 0;

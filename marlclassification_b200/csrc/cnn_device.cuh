@@ -15,66 +15,90 @@ struct CnnFwdArgs {
     float* y_save[MAX_CNN_LAYERS];
     float* out;
     long ldo;
-    int B, H, W, M, bufsz;
+    int B, H, W, M;
+    int padsz;  // floats of one zero-bordered activation buffer: max_l cin_l * (hin_l + 2)^2
+    int ysz;    // floats of the raw conv-output buffer: max_l cout_l * hout_l^2
+    int wbuf;   // floats of the weight staging buffer
 };
 
-// One window per call; `sm` holds 2 * a.bufsz floats.  All threads of the CTA participate.
+__host__ __device__ inline int cnn_wpitch(int wrow) { return wrow | 1; }  // odd pitch: conflict-free rows
+
+// One window per call.  `sm` holds 2*padsz + ysz + wbuf floats.  All threads of the CTA participate.
+// Activations live in shared memory with a one-pixel zero border (no bounds checks in the 3x3
+// stride-2 taps); each layer's weights are staged in shared memory (odd pitch) before use, so
+// the inner loops never wait on global memory.
 __device__ __forceinline__ void cnn_fwd_block(const CnnFwdArgs& a, const int m, float* sm) {
     float* in = sm;
-    float* out = sm + a.bufsz;
+    float* nxt = sm + a.padsz;
+    float* yb = nxt + a.padsz;
+    float* ws = yb + a.ysz;
     const CnnDesc& d = a.d;
     const int tid = threadIdx.x, nt = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
     const int f = d.f, ff = f * f;
 
-    // ---- load the window (gather fused; MnistCnn keeps channel 0 only: cin[0] < img_c)
-    if (a.patch) {
-        const float* src = a.patch + (long)m * d.img_c * ff;
-        for (int e = tid; e < d.cin[0] * ff; e += nt) in[e] = src[e];
-    } else {
-        const int b = m % a.B;
-        const int py = a.pos[2 * m], px = a.pos[2 * m + 1];
-        const float* src = a.img + (long)b * d.img_c * a.H * a.W;
-        for (int e = tid; e < d.cin[0] * ff; e += nt) {
-            const int c = e / ff, i = (e / f) % f, j = e % f;
-            in[e] = __ldg(src + ((long)c * a.H + py + i) * a.W + px + j);
+    // ---- load the window into the zero-bordered buffer (gather fused; MnistCnn keeps channel 0
+    //      only: cin[0] < img_c)
+    {
+        const int hp = f + 2, c0 = d.cin[0];
+        for (int e = tid; e < c0 * hp * hp; e += nt) in[e] = 0.f;
+        __syncthreads();
+        if (a.patch) {
+            const float* src = a.patch + (long)m * d.img_c * ff;
+            for (int e = tid; e < c0 * ff; e += nt) {
+                const int c = e / ff, i = (e / f) % f, j = e % f;
+                in[c * hp * hp + (i + 1) * hp + j + 1] = src[e];
+            }
+        } else {
+            const int b = m % a.B;
+            const int py = a.pos[2 * m], px = a.pos[2 * m + 1];
+            const float* src = a.img + (long)b * d.img_c * a.H * a.W;
+            for (int e = tid; e < c0 * ff; e += nt) {
+                const int c = e / ff, i = (e / f) % f, j = e % f;
+                in[c * hp * hp + (i + 1) * hp + j + 1] = __ldg(src + ((long)c * a.H + py + i) * a.W + px + j);
+            }
         }
     }
     __syncthreads();
 
     for (int l = 0; l < d.L; ++l) {
         const int ci_n = d.cin[l], co_n = d.cout[l], hi = d.hin[l], ho = d.hout[l];
-        const int npos = ho * ho, total = co_n * npos;
+        const int hp = hi + 2, hp2 = hp * hp, npos = ho * ho, total = co_n * npos;
+        const int wrow = ci_n * 9, P = cnn_wpitch(wrow);
+        const int cc = min(co_n, a.wbuf / P);
         const float* __restrict__ w = d.w[l];
         const float* __restrict__ bias = d.b[l];
         float* ys = a.y_save[l] ? a.y_save[l] + (long)m * total : nullptr;
-        for (int idx = tid; idx < total; idx += nt) {
-            const int co = idx / npos, oy = (idx / ho) % ho, ox = idx % ho;
-            const float* wb = w + (long)co * ci_n * 9;
-            float acc = bias[co];
-            for (int ci = 0; ci < ci_n; ++ci) {
-                const float* xin = in + ci * hi * hi;
-#pragma unroll
-                for (int ky = 0; ky < 3; ++ky) {
-                    const int iy = 2 * oy - 1 + ky;
-                    if (iy < 0 || iy >= hi) continue;
-#pragma unroll
-                    for (int kx = 0; kx < 3; ++kx) {
-                        const int ix = 2 * ox - 1 + kx;
-                        if (ix < 0 || ix >= hi) continue;
-                        acc = fmaf(wb[ci * 9 + ky * 3 + kx], xin[iy * hi + ix], acc);
-                    }
+        const bool last = (l + 1 == d.L);
+        const int hop = ho + 2;
+        if (!last)
+            for (int e = tid; e < co_n * hop * hop; e += nt) nxt[e] = 0.f;  // border of the next input
+        for (int co0 = 0; co0 < co_n; co0 += cc) {
+            const int ncur = min(cc, co_n - co0);
+            stage_rows(ws, w + (long)co0 * wrow, ncur, wrow, P);
+            __syncthreads();
+            for (int idx = tid; idx < ncur * npos; idx += nt) {
+                const int c = idx / npos, pos = idx - c * npos, oy = pos / ho, ox = pos - oy * ho;
+                const float* wq = ws + c * P;
+                const float* x = in + (2 * oy) * hp + 2 * ox;
+                float a0 = bias[co0 + c], a1 = 0.f, a2 = 0.f;
+                for (int ci = 0; ci < ci_n; ++ci, wq += 9, x += hp2) {
+                    a0 = fmaf(wq[0], x[0], a0); a0 = fmaf(wq[1], x[1], a0); a0 = fmaf(wq[2], x[2], a0);
+                    a1 = fmaf(wq[3], x[hp], a1); a1 = fmaf(wq[4], x[hp + 1], a1); a1 = fmaf(wq[5], x[hp + 2], a1);
+                    a2 = fmaf(wq[6], x[2 * hp], a2); a2 = fmaf(wq[7], x[2 * hp + 1], a2); a2 = fmaf(wq[8], x[2 * hp + 2], a2);
                 }
+                const float acc = a0 + a1 + a2;
+                yb[(co0 + c) * npos + pos] = acc;
+                if (ys) ys[(co0 + c) * npos + pos] = acc;
             }
-            out[idx] = acc;
-            if (ys) ys[idx] = acc;
+            __syncthreads();
         }
-        __syncthreads();
-        // GroupNorm + SiLU in place; the channels of one group are contiguous
+        // GroupNorm + SiLU; the channels of one group are contiguous in yb
         const int G = d.groups[l], cpg = co_n / G, ng = cpg * npos;
         const float inv = 1.0f / (float)ng;
+        float* og = a.out + (long)m * a.ldo;
         for (int g = warp; g < G; g += nwarps) {
-            float* base = out + g * ng;
+            const float* base = yb + g * ng;
             float s = 0.f;
             for (int e = lane; e < ng; e += 32) s += base[e];
             const float mean = warp_sum(s) * inv;
@@ -82,17 +106,30 @@ __device__ __forceinline__ void cnn_fwd_block(const CnnFwdArgs& a, const int m, 
             for (int e = lane; e < ng; e += 32) { float dd = base[e] - mean; v += dd * dd; }
             const float rstd = 1.0f / sqrtf(warp_sum(v) * inv + GN_EPS);
             for (int e = lane; e < ng; e += 32) {
-                const int c = g * cpg + e / npos;
-                base[e] = siluf_((base[e] - mean) * rstd * d.gn_w[l][c] + d.gn_b[l][c]);
+                const int c = g * cpg + e / npos, pos = e % npos;
+                const float o = siluf_((base[e] - mean) * rstd * d.gn_w[l][c] + d.gn_b[l][c]);
+                if (last) og[c * npos + pos] = o;
+                else nxt[c * hop * hop + (pos / ho + 1) * hop + (pos % ho) + 1] = o;
             }
         }
         __syncthreads();
-        float* t = in; in = out; out = t;
+        float* t = in; in = nxt; nxt = t;
     }
-    float* o = a.out + (long)m * a.ldo;
-    for (int e = tid; e < d.out_size; e += nt) o[e] = in[e];
 }
 
+// shared-memory plan (floats) for cnn_fwd_block
+inline void cnn_fwd_plan(const CnnDesc& d, int* padsz, int* ysz, int* wbuf) {
+    int p = 0, y = 0, wmax = 0;
+    for (int l = 0; l < d.L; ++l) {
+        p = max(p, d.cin[l] * (d.hin[l] + 2) * (d.hin[l] + 2));
+        y = max(y, d.cout[l] * d.hout[l] * d.hout[l]);
+        wmax = max(wmax, d.cout[l] * cnn_wpitch(d.cin[l] * 9));
+    }
+    *padsz = (p + 3) & ~3;
+    *ysz = (y + 3) & ~3;
+    *wbuf = min(wmax, 24 * 1024);  // <= 96 KB of staged weights; larger layers go in channel chunks
+}
+inline size_t cnn_fwd_smem_bytes(const CnnFwdArgs& a) { return sizeof(float) * ((size_t)2 * a.padsz + a.ysz + a.wbuf); }
 
 inline int cnn_max_act(const CnnDesc& d) {
     int mx = d.cin[0] * d.f * d.f;

@@ -84,6 +84,54 @@ struct Philox {
 // uniform in [0,1) with 24 bits
 __device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
 
+
+// ---- cooperative global -> shared copy of a dense row-major matrix into padded rows -----------
+// src: nrows x rowlen contiguous floats; dst row pitch `pitch`.  Loads are issued in batches of
+// 8 independent 128-bit requests per thread before any store, so the copy costs a few L2 round
+// trips instead of one per element (the loop is latency-bound otherwise).
+__device__ __forceinline__ void stage_rows(float* dst, const float* __restrict__ src, int nrows, int rowlen, int pitch) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int total = nrows * rowlen;
+    if (((rowlen & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+        constexpr int U = 8;
+        for (int base = tid * 4; base < total; base += nt * 4 * U) {
+            float4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = base + u * nt * 4;
+                if (i < total) v[u] = __ldg(reinterpret_cast<const float4*>(src + i));
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = base + u * nt * 4;
+                if (i < total) {
+                    const int n = i / rowlen, k = i - n * rowlen;
+                    float* d = dst + n * pitch + k;
+                    d[0] = v[u].x; d[1] = v[u].y; d[2] = v[u].z; d[3] = v[u].w;
+                }
+            }
+        }
+    } else {
+        constexpr int U = 8;
+        for (int base = tid; base < total; base += nt * U) {
+            float v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = base + u * nt;
+                if (i < total) v[u] = __ldg(src + i);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = base + u * nt;
+                if (i < total) {
+                    const int n = i / rowlen, k = i - n * rowlen;
+                    dst[n * pitch + k] = v[u];
+                }
+            }
+        }
+    }
+}
+
 // ---- generic fp32 GEMM (SIMT), gemm_simt.cu ----------------------------------
 // C[m,n] (+)= sum_k A(m,k) B(k,n) [+ sum_k2 A2(m,k2) B2(k2,n)] + bias[n] + bias2[n]
 // A(m,k) = A[m*sam + k*sak]; B(k,n) = B[k*sbk + n*sbn]; C[m*ldc + n].

@@ -374,7 +374,8 @@ static int step_networks(marlc_engine* e, int t, const float* img, const int* po
         StepPreArgs pa;
         memset(&pa, 0, sizeof(pa));
         pa.cnn.d = e->cnn; pa.cnn.img = img; pa.cnn.pos = pos; pa.cnn.patch = patch; pa.cnn.out = Ut; pa.cnn.ldo = Kin;
-        pa.cnn.B = c.nb; pa.cnn.H = c.H; pa.cnn.W = c.W; pa.cnn.M = M; pa.cnn.bufsz = cnn_max_act(e->cnn);
+        pa.cnn.B = c.nb; pa.cnn.H = c.H; pa.cnn.W = c.W; pa.cnn.M = M;
+        cnn_fwd_plan(e->cnn, &pa.cnn.padsz, &pa.cnn.ysz, &pa.cnn.wbuf);
         for (int l = 0; l < e->L; ++l) pa.cnn.y_save[l] = e->buf("cnn_y" + std::to_string(l)) + (size_t)t * M * e->cnn_sz[l];
         pa.msg_in = msg_in;
         pa.coll = e->buf("coll") + (size_t)t * M * c.n_m;
