@@ -1,0 +1,153 @@
+"""Roofline micro-measurements used by bench.py (and runnable alone).
+
+Each kernel is launched through the C ABI on the current stream, `reps` times
+back to back after warm-up, bracketed by CUDA events; achieved = ALGORITHMIC
+bytes / flops per launch (restated in DESIGN.md) / mean
+launch time.  Peaks come from MEASURED_PEAKS.json (driver-written); the TF32
+tensor peak is measured live with cuBLAS (torch.matmul, allow_tf32) because the
+file only holds the bf16 figure.
+"""
+from __future__ import annotations
+
+import ctypes as ct
+import json
+import os
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+FALLBACK = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
+
+
+def peaks() -> tuple[dict, str]:
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return json.load(fh), "measured (MEASURED_PEAKS.json)"
+    return dict(FALLBACK), "fallback (B200_PROFILING.md)"
+
+
+def _time(fn, reps: int, warm: int = 5) -> float:
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) * 1e-3 / reps  # seconds per launch
+
+
+def tf32_cublas_peak(dev) -> float:
+    """TFLOP/s of torch.matmul fp32 with TF32 allowed, 8192^3, best of 5 (burst)."""
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a = torch.randn(n, n, device=dev)
+        b = torch.randn(n, n, device=dev)
+        best = min(_time(lambda: torch.matmul(a, b), 3, 2) for _ in range(5))
+        return 2 * n**3 / best / 1e12
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def lstm_pair(M: int, Kin: int, n: int, dev, reps: int = 200) -> dict:
+    """The fused LSTM kernel (both cells, gate GEMMs on tcgen05 + cell epilogue)."""
+    from marlclassification_b200 import _lib
+
+    L = _lib.lib()
+    g = torch.Generator(device=dev).manual_seed(0)
+    rnd = lambda *s: torch.randn(*s, device=dev, generator=g)  # noqa: E731
+    u = rnd(M, Kin)
+    hp, cp = [rnd(M, n), rnd(M, n)], [rnd(M, n), rnd(M, n)]
+    wih, whh = [rnd(4 * n, Kin) * 0.05, rnd(4 * n, Kin) * 0.05], [rnd(4 * n, n) * 0.05, rnd(4 * n, n) * 0.05]
+    bih, bhh = [rnd(4 * n), rnd(4 * n)], [rnd(4 * n), rnd(4 * n)]
+    cn, hn = [torch.empty(M, n, device=dev) for _ in range(2)], [torch.empty(M, n, device=dev) for _ in range(2)]
+    gates = [torch.empty(M, 4 * n, device=dev) for _ in range(2)]
+    arr = lambda ts: (ct.c_void_p * 2)(*[t.data_ptr() for t in ts])  # noqa: E731
+    args = (u.data_ptr(), M, Kin, n, arr(hp), arr(cp), arr(wih), arr(whh), arr(bih), arr(bhh), arr(cn), arr(hn), arr(gates))
+
+    def run():
+        _lib.check(L.marlc_tc_lstm_pair(*args, _lib.stream_ptr(dev)))
+
+    t = _time(run, reps)
+    flops = 2.0 * M * (Kin + n) * 4 * n * 2  # both cells (lstm = 2(K_in+n)4n per row per cell)
+    bytes_min = 4.0 * (M * Kin + 2 * M * n * 2 + 2 * 4 * n * (Kin + n) + 2 * M * 6 * n)
+    return {"kernel": "tc_gemm_kernel<EPI_LSTM> (fused LSTM pair)", "shape": {"M": M, "K_in": Kin, "n": n},
+            "us_per_launch": t * 1e6, "flops_per_launch": flops, "tflops": flops / t / 1e12,
+            "min_bytes_per_launch": bytes_min}
+
+
+def gather(na: int, nb: int, C: int, H: int, W: int, f: int, dev, reps: int = 200) -> dict:
+    """K1 patch gather through Environment.observe's entry point."""
+    from marlclassification_b200 import _lib
+
+    L = _lib.lib()
+    g = torch.Generator(device=dev).manual_seed(0)
+    img = torch.rand(nb, C, H, W, device=dev, generator=g)
+    pos = torch.stack([torch.randint(H - f, (na, nb), device=dev, generator=g),
+                       torch.randint(W - f, (na, nb), device=dev, generator=g)], -1).contiguous()
+    obs = torch.empty(na, nb, C, f, f, device=dev)
+
+    def run():
+        _lib.check(L.marlc_patch_gather(img.data_ptr(), pos.data_ptr(), obs.data_ptr(), na, nb, C, H, W, f,
+                                        _lib.stream_ptr(dev)))
+
+    t = _time(run, reps)
+    M = na * nb
+    bytes_alg = 2.0 * M * C * f * f * 4 + M * 16  # read each needed pixel once + write patch + read pos
+    return {"kernel": "patch_gather_kernel", "shape": {"windows": M, "C": C, "f": f, "image": [H, W]},
+            "us_per_launch": t * 1e6, "bytes_per_launch": bytes_alg, "gbs": bytes_alg / t / 1e9}
+
+
+def roofline_for(model, w: dict, nb: int, dev) -> dict:
+    """The `roofline` object of bench.py's JSON line (+ the secondary kernels)."""
+    pk, src = peaks()
+    d = model.dims
+    M = w["na"] * nb
+    Kin = model.feature_extractor.out_size + d["n_m_o"] + d["n_d"]
+    tf32_peak = tf32_cublas_peak(dev)
+    lstm = lstm_pair(M, Kin, d["n_b"], dev)
+    lstm_big = lstm_pair(4096, Kin, d["n_b"], dev, reps=50)
+    g_small = gather(w["na"], nb, w["C"], w["H"], w["W"], w["f"], dev)
+    g_big = gather(256, 256, w["C"], w["H"], w["W"], w["f"], dev, reps=50)  # 65536 windows: saturating
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as fh:
+            traffic = json.load(fh).get("lstm_pair_dram_bytes_per_launch")
+    return {
+        "bound": "tensor", "kernel": lstm["kernel"], "achieved": lstm["tflops"], "peak": tf32_peak, "unit": "TFLOP/s",
+        "frac": lstm["tflops"] / tf32_peak, "traffic": traffic,
+        "peak_source": "cuBLAS TF32 8192^3 measured in this run (MEASURED_PEAKS.json holds bf16 only: "
+                       f"{pk.get('bf16_tflops')} TFLOP/s burst, {src})",
+        "launch_us": lstm["us_per_launch"], "flops_per_launch": lstm["flops_per_launch"],
+        "note": f"M={M} rows per launch: one 128-row MMA tile, latency-bound (SURVEY 7.3-2); "
+                "the same kernel at M=4096 is listed under 'others'",
+        "others": [
+            {"kernel": lstm_big["kernel"] + " @ M=4096 (config c4 per-GPU rows)", "bound": "tensor",
+             "achieved": lstm_big["tflops"], "peak": tf32_peak, "unit": "TFLOP/s", "frac": lstm_big["tflops"] / tf32_peak,
+             "launch_us": lstm_big["us_per_launch"]},
+            {"kernel": "patch_gather_kernel @ workload", "bound": "hbm", "achieved": g_small["gbs"],
+             "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": g_small["gbs"] / pk["hbm_gbs"],
+             "launch_us": g_small["us_per_launch"], "bytes_per_launch": g_small["bytes_per_launch"]},
+            {"kernel": "patch_gather_kernel @ 65536 windows (saturating)", "bound": "hbm", "achieved": g_big["gbs"],
+             "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": g_big["gbs"] / pk["hbm_gbs"],
+             "launch_us": g_big["us_per_launch"], "bytes_per_launch": g_big["bytes_per_launch"]},
+        ],
+    }
+
+
+if __name__ == "__main__":
+    dev = torch.device("cuda", 0)
+    pk, src = peaks()
+    print("peaks:", pk.get("hbm_gbs"), pk.get("bf16_tflops"), src)
+    print("tf32 cuBLAS peak TFLOP/s:", tf32_cublas_peak(dev))
+    for M in (128, 1024, 4096, 16384):
+        print(json.dumps(lstm_pair(M, 368, 256, dev, reps=50)))
+    for na, nb in ((16, 8), (64, 64), (256, 256)):
+        print(json.dumps(gather(na, nb, 3, 256, 256, 12, dev, reps=50)))
+    print(json.dumps(gather(256, 64, 3, 600, 600, 24, dev, reps=50)))

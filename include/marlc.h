@@ -59,6 +59,17 @@ int marlc_tc_gemm(const float* A, int64_t lda, int a_mn, const float* B, int64_t
                   int64_t lda2, const float* B2, int64_t ldb2, int K2, const float* bias, float* C, int64_t ldc,
                   int M, int N, int K, int accumulate, int allow_split, void* stream);
 
+/* Both LSTM cells of one step (belief + action, models.py:107-123; nn.LSTMCell,
+ * recurrent.py:30) in ONE tcgen05 launch with the cell non-linearities fused into the
+ * epilogue.  Arrays of 2 device pointers (HOST arrays): index 0 = belief, 1 = action.
+ * u f32[M,Kin]; h_prev/c_prev f32[M,n]; w_ih f32[4n,Kin]; w_hh f32[4n,n]; b_* f32[4n];
+ * outputs c_new/h_new f32[M,n], gates f32[M,4n] (activated i,f,g,o, kept for backward).
+ * Needs Kin % 4 == 0 and n % 8 == 0. */
+int marlc_tc_lstm_pair(const float* u, int M, int Kin, int n, const float* const* h_prev, const float* const* c_prev,
+                       const float* const* w_ih, const float* const* w_hh, const float* const* b_ih,
+                       const float* const* b_hh, float* const* c_new, float* const* h_new, float* const* gates,
+                       void* stream);
+
 /* _Generic2dCnnModule.forward, vision.py:47-49: k x [conv3x3 s2 p1 -> GroupNorm ->
  * SiLU] -> flatten on N stand-alone windows patch f32[N,img_c,f,f] (the first
  * cin[0] channels are read) -> out f32[N, cout[k-1]*h_k^2].  w/b/gn_w/gn_b are

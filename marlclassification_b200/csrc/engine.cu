@@ -984,3 +984,22 @@ extern "C" int marlc_tc_gemm(const float* A, int64_t lda, int a_mn, const float*
     a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.bias = bias; a.accumulate = accumulate; a.allow_split = allow_split;
     return tc_gemm(a, (cudaStream_t)stream);
 }
+
+// The fused LSTM pair kernel on caller tensors (unit tests / bench roofline): both cells of
+// models.py:107-123 in ONE launch.  u f32[M,Kin]; for k in {belief, action}: h_prev/c_prev
+// f32[M,n], w_ih f32[4n,Kin], w_hh f32[4n,n], b_ih/b_hh f32[4n] -> c_new/h_new f32[M,n],
+// gates f32[M,4n] (activated i,f,g,o).
+extern "C" int marlc_tc_lstm_pair(const float* u, int M, int Kin, int n, const float* const* h_prev,
+                                  const float* const* c_prev, const float* const* w_ih, const float* const* w_hh,
+                                  const float* const* b_ih, const float* const* b_hh, float* const* c_new,
+                                  float* const* h_new, float* const* gates, void* stream) {
+    TcLstmArgs la[2];
+    for (int k = 0; k < 2; ++k) {
+        TcLstmArgs& a = la[k];
+        a.U = tc_op(u, Kin); a.Hprev = tc_op(h_prev[k], n);
+        a.Wih = w_ih[k]; a.Whh = w_hh[k]; a.bih = b_ih[k]; a.bhh = b_hh[k];
+        a.c_prev = c_prev[k]; a.c_new = c_new[k]; a.h_new = h_new[k]; a.gates = gates[k];
+        a.M = M; a.Kin = Kin; a.n = n;
+    }
+    return tc_lstm_pair(la[0], la[1], (cudaStream_t)stream);
+}

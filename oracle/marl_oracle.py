@@ -320,13 +320,15 @@ class LossParts:
     critic: torch.Tensor  # critic_loss.sum(0).mean()
 
 
-def a2c_loss(step_preds, step_logp, step_values, targets, gamma: float) -> LossParts:
-    """trainer.py:75-111 (+ the meter reads at 119-122)."""
+def a2c_loss(step_preds, step_logp, step_values, targets, gamma: float, adv_stats=None) -> LossParts:
+    """trainer.py:75-111 (+ the meter reads at 119-122).  ``adv_stats=(mean, std)`` overrides
+    the statistics of ``standardize`` (data-parallel shards use the GLOBAL batch's)."""
     T, na, nb, nc = step_preds.shape
     vote = step_preds.mean(dim=1).reshape(T * nb, nc)
     error = F.cross_entropy(vote, targets.repeat(T), reduction="none").view(T, 1, nb)
     returns = discounted_returns(classification_rewards(step_preds, targets), gamma)
-    adv = standardize(returns - step_values)
+    raw_adv = returns - step_values
+    adv = standardize(raw_adv) if adv_stats is None else (raw_adv - adv_stats[0]) / (adv_stats[1] + 1e-8)
     path = -step_logp * adv.detach()
     actor = path + error
     critic = F.smooth_l1_loss(step_values, returns.detach(), reduction="none")
