@@ -27,17 +27,35 @@ def peaks() -> tuple[dict, str]:
     return dict(FALLBACK), "fallback (B200_PROFILING.md)"
 
 
-def _time(fn, reps: int, warm: int = 5) -> float:
-    for _ in range(warm):
-        fn()
+def _time(fn, reps: int, warm: int = 5, graph: bool = True) -> float:
+    """Seconds per launch.  The `reps` launches are captured in ONE CUDA graph and replayed, so
+    the figure is device time of back-to-back launches (as inside the graphed train step), not
+    host launch overhead (each eager call also encodes TMA descriptors on the host)."""
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        for _ in range(warm):
+            fn()
+    torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
+    runner = None
+    if graph:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(reps):
+                fn()
+        runner = g.replay
+        runner()
+        torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    for _ in range(reps):
-        fn()
+    if runner is not None:
+        runner()
+    else:
+        for _ in range(reps):
+            fn()
     b.record()
     torch.cuda.synchronize()
-    return a.elapsed_time(b) * 1e-3 / reps  # seconds per launch
+    return a.elapsed_time(b) * 1e-3 / reps
 
 
 def tf32_cublas_peak(dev) -> float:
@@ -48,7 +66,7 @@ def tf32_cublas_peak(dev) -> float:
         n = 8192
         a = torch.randn(n, n, device=dev)
         b = torch.randn(n, n, device=dev)
-        best = min(_time(lambda: torch.matmul(a, b), 3, 2) for _ in range(5))
+        best = min(_time(lambda: torch.matmul(a, b), 3, 2, graph=False) for _ in range(5))
         return 2 * n**3 / best / 1e12
     finally:
         torch.backends.cuda.matmul.allow_tf32 = old
