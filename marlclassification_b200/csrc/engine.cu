@@ -230,6 +230,8 @@ extern "C" int marlc_engine_create(const marlc_config* c, marlc_engine** out) {
     e->add_buf("tmpS", M * 2 * c->n_m * F4);
     e->add_buf("dcoll", M * c->n_m * F4);
     e->add_buf("dmsg", M * c->n_m * F4);
+    e->add_buf("dh_hist", TM * c->n_b * F4);   // per-step carries dgates(t) Whh (split-K targets, zeroed once)
+    e->add_buf("dhc_hist", TM * c->n_a * F4);
     e->add_buf("dh", M * c->n_b * F4);
     e->add_buf("dc0", M * c->n_b * F4);
     e->add_buf("dc1", M * c->n_b * F4);
@@ -453,12 +455,29 @@ static int step_networks(marlc_engine* e, int t, const float* img, const int* po
         MARLC_TRY(lstm_cell_fwd(ga, cc_in, Cc + (size_t)(t + 1) * M * c.n_a, Hc + (size_t)(t + 1) * M * c.n_a, M, c.n_a, s));
     }
     if (c.use_chains) {
-        // block-0 GEMMs of the encoder and the policy (tensor cores), tails fused in step_act()
-        MARLC_TRY(G_nt(e, H + (size_t)(t + 1) * M * c.n_b, c.n_b, e->prm("encode_msg.0.weight"), c.n_b,
-                       e->prm("encode_msg.0.bias"), e->buf("enc_y1") + (size_t)t * M * 2 * c.n_m, 2 * c.n_m, M,
-                       2 * c.n_m, c.n_b, 0, s));
-        MARLC_TRY(G_nt(e, Hc + (size_t)(t + 1) * M * c.n_a, c.n_a, e->prm("policy.0.weight"), c.n_a,
-                       e->prm("policy.0.bias"), e->buf("pol_y1") + (size_t)t * M * c.nl_a, c.nl_a, M, c.nl_a, c.n_a, 0, s));
+        // block-0 GEMMs of the encoder and the policy (tensor cores, ONE grouped launch), tails fused in step_act()
+        const float* enc_x = H + (size_t)(t + 1) * M * c.n_b;
+        const float* pol_x = Hc + (size_t)(t + 1) * M * c.n_a;
+        float* enc_y1 = e->buf("enc_y1") + (size_t)t * M * 2 * c.n_m;
+        float* pol_y1 = e->buf("pol_y1") + (size_t)t * M * c.nl_a;
+        bool grouped = false;
+        if (c.use_tc && tc_worth(M, 2 * c.n_m, c.n_b) && tc_worth(M, c.nl_a, c.n_a)) {
+            TcGemmArgs g[2];
+            g[0].A = tc_op(enc_x, c.n_b); g[0].B = tc_op(e->prm("encode_msg.0.weight"), c.n_b); g[0].K = c.n_b;
+            g[0].C = enc_y1; g[0].ldc = 2 * c.n_m; g[0].M = M; g[0].N = 2 * c.n_m; g[0].bias = e->prm("encode_msg.0.bias");
+            g[1].A = tc_op(pol_x, c.n_a); g[1].B = tc_op(e->prm("policy.0.weight"), c.n_a); g[1].K = c.n_a;
+            g[1].C = pol_y1; g[1].ldc = c.nl_a; g[1].M = M; g[1].N = c.nl_a; g[1].bias = e->prm("policy.0.bias");
+            if (tc_operand_ok(g[0].A) && tc_operand_ok(g[0].B) && tc_operand_ok(g[1].A) && tc_operand_ok(g[1].B)) {
+                MARLC_TRY(tc_gemm_group(g, 2, s));
+                grouped = true;
+            }
+        }
+        if (!grouped) {
+            MARLC_TRY(G_nt(e, enc_x, c.n_b, e->prm("encode_msg.0.weight"), c.n_b, e->prm("encode_msg.0.bias"), enc_y1,
+                           2 * c.n_m, M, 2 * c.n_m, c.n_b, 0, s));
+            MARLC_TRY(G_nt(e, pol_x, c.n_a, e->prm("policy.0.weight"), c.n_a, e->prm("policy.0.bias"), pol_y1, c.nl_a, M,
+                           c.nl_a, c.n_a, 0, s));
+        }
         return 0;
     }
     // message for the next step                                   (models.py:114-116)
@@ -690,6 +709,12 @@ extern "C" int marlc_episode_backward(marlc_engine* e, const float* img, int acc
     int cur = 0;
     if (c.use_chains) {
         float* dcoll = e->buf("dcoll");
+        float* dh_hist = e->buf("dh_hist");
+        float* dhc_hist = e->buf("dhc_hist");
+        // split-K (atomicAdd) targets of the whole sweep are zeroed once, not once per step
+        MARLC_CUDA(cudaMemsetAsync(dU, 0, sizeof(float) * (size_t)TM * Kin, s));
+        MARLC_CUDA(cudaMemsetAsync(dh_hist, 0, sizeof(float) * (size_t)TM * c.n_b, s));
+        MARLC_CUDA(cudaMemsetAsync(dhc_hist, 0, sizeof(float) * (size_t)TM * c.n_a, s));
         for (int t = T - 1; t >= 0; --t) {
             float* dgb = e->buf("dgates_b") + (size_t)t * M * 4 * c.n_b;
             float* dga = e->buf("dgates_a") + (size_t)t * M * 4 * c.n_a;
@@ -703,8 +728,8 @@ extern "C" int marlc_episode_backward(marlc_engine* e, const float* img, int acc
             bp.enc_y2 = e->buf("enc_y2") + (size_t)t * M * c.n_m;
             bp.d_enc_y1 = e->buf("d_enc_y1") + (size_t)t * M * 2 * c.n_m;
             bp.d_enc_y2 = e->buf("d_enc_y2") + (size_t)t * M * c.n_m;
-            bp.dh_carry[0] = (t < T - 1) ? dh : nullptr;
-            bp.dh_carry[1] = (t < T - 1) ? dhc : nullptr;
+            bp.dh_carry[0] = (t < T - 1) ? dh_hist + (size_t)(t + 1) * M * c.n_b : nullptr;
+            bp.dh_carry[1] = (t < T - 1) ? dhc_hist + (size_t)(t + 1) * M * c.n_a : nullptr;
             bp.dh_heads[0] = e->buf("dH_heads") + (size_t)t * M * c.n_b;
             bp.dh_heads[1] = e->buf("dHc_heads") + (size_t)t * M * c.n_a;
             bp.dc_next[0] = (t < T - 1) ? dc[cur] : nullptr;
@@ -721,56 +746,59 @@ extern "C" int marlc_episode_backward(marlc_engine* e, const float* img, int acc
             bp.Na = c.na; bp.Nb = c.nb; bp.M = M; bp.n_m = c.n_m;
             MARLC_TRY(bwd_pre(bp, s));
             cur ^= 1;
-            // input gradients: du = dg_b Wih_b + dg_a Wih_a ; dh = dg_b Whh_b ; dh^ = dg_a Whh_a
+            // input gradients: du = dg_b Wih_b + dg_a Wih_a ; dh = dg_b Whh_b ; dh^ = dg_a Whh_a  (ONE grouped launch)
             float* dUt = dU + (size_t)t * M * Kin;
+            float* dh_t = dh_hist + (size_t)t * M * c.n_b;
+            float* dhc_t = dhc_hist + (size_t)t * M * c.n_a;
             bool tc_dx = false;
-            if (c.use_tc) {
-                TcGemmArgs a;
-                a.A = tc_op(dgb, 4 * c.n_b); a.B = tc_op(e->prm(std::string(LSTM_B) + "weight_ih"), Kin, true); a.K = 4 * c.n_b;
-                a.A2 = tc_op(dga, 4 * c.n_a); a.B2 = tc_op(e->prm(std::string(LSTM_A) + "weight_ih"), Kin, true); a.K2 = 4 * c.n_a;
-                a.C = dUt; a.ldc = Kin; a.M = M; a.N = Kin; a.allow_split = 1;
-                TcGemmArgs b;
-                b.A = tc_op(dgb, 4 * c.n_b); b.B = tc_op(e->prm(std::string(LSTM_B) + "weight_hh"), c.n_b, true); b.K = 4 * c.n_b;
-                b.C = dh; b.ldc = c.n_b; b.M = M; b.N = c.n_b; b.allow_split = 1;
-                TcGemmArgs d;
-                d.A = tc_op(dga, 4 * c.n_a); d.B = tc_op(e->prm(std::string(LSTM_A) + "weight_hh"), c.n_a, true); d.K = 4 * c.n_a;
-                d.C = dhc; d.ldc = c.n_a; d.M = M; d.N = c.n_a; d.allow_split = 1;
-                if (tc_operand_ok(a.A) && tc_operand_ok(a.B) && tc_operand_ok(a.A2) && tc_operand_ok(a.B2) &&
-                    tc_operand_ok(b.B) && tc_operand_ok(d.B) && c.n_a >= 16 && c.n_b >= 16) {
-                    MARLC_TRY(tc_gemm(a, s));
-                    MARLC_TRY(tc_gemm(b, s));
-                    MARLC_TRY(tc_gemm(d, s));
+            if (c.use_tc && c.n_a >= 16 && c.n_b >= 16) {
+                TcGemmArgs g[3];
+                g[0].A = tc_op(dgb, 4 * c.n_b); g[0].B = tc_op(e->prm(std::string(LSTM_B) + "weight_ih"), Kin, true); g[0].K = 4 * c.n_b;
+                g[0].A2 = tc_op(dga, 4 * c.n_a); g[0].B2 = tc_op(e->prm(std::string(LSTM_A) + "weight_ih"), Kin, true); g[0].K2 = 4 * c.n_a;
+                g[0].C = dUt; g[0].ldc = Kin; g[0].M = M; g[0].N = Kin;
+                g[1].A = tc_op(dgb, 4 * c.n_b); g[1].B = tc_op(e->prm(std::string(LSTM_B) + "weight_hh"), c.n_b, true); g[1].K = 4 * c.n_b;
+                g[1].C = dh_t; g[1].ldc = c.n_b; g[1].M = M; g[1].N = c.n_b;
+                g[2].A = tc_op(dga, 4 * c.n_a); g[2].B = tc_op(e->prm(std::string(LSTM_A) + "weight_hh"), c.n_a, true); g[2].K = 4 * c.n_a;
+                g[2].C = dhc_t; g[2].ldc = c.n_a; g[2].M = M; g[2].N = c.n_a;
+                bool ok = true;
+                for (int q = 0; q < 3; ++q) {
+                    g[q].allow_split = 1; g[q].c_zeroed = 1;
+                    ok = ok && tc_operand_ok(g[q].A) && tc_operand_ok(g[q].B);
+                }
+                ok = ok && tc_operand_ok(g[0].A2) && tc_operand_ok(g[0].B2);
+                if (ok) {
+                    MARLC_TRY(tc_gemm_group(g, t > 0 ? 3 : 1, s));  // at t == 0 nothing consumes dh / dh^
                     tc_dx = true;
                 }
             }
             if (!tc_dx) {
-            GemmGroup gg;
-            memset(&gg, 0, sizeof(gg));
-            gg.count = 3;
-            {
-                GemmProblem& p = gg.p[0];
-                p.A = dgb; p.sam = 4 * c.n_b; p.sak = 1;
-                p.B = e->prm(std::string(LSTM_B) + "weight_ih"); p.sbk = Kin; p.sbn = 1;
-                p.A2 = dga; p.sam2 = 4 * c.n_a; p.sak2 = 1;
-                p.B2 = e->prm(std::string(LSTM_A) + "weight_ih"); p.sbk2 = Kin; p.sbn2 = 1;
-                p.C = dUt; p.ldc = Kin;
-                p.M = M; p.N = Kin; p.K = 4 * c.n_b; p.K2 = 4 * c.n_a;
-            }
-            {
-                GemmProblem& p = gg.p[1];
-                p.A = dgb; p.sam = 4 * c.n_b; p.sak = 1;
-                p.B = e->prm(std::string(LSTM_B) + "weight_hh"); p.sbk = c.n_b; p.sbn = 1;
-                p.C = dh; p.ldc = c.n_b;
-                p.M = M; p.N = c.n_b; p.K = 4 * c.n_b;
-            }
-            {
-                GemmProblem& p = gg.p[2];
-                p.A = dga; p.sam = 4 * c.n_a; p.sak = 1;
-                p.B = e->prm(std::string(LSTM_A) + "weight_hh"); p.sbk = c.n_a; p.sbn = 1;
-                p.C = dhc; p.ldc = c.n_a;
-                p.M = M; p.N = c.n_a; p.K = 4 * c.n_a;
-            }
-            MARLC_TRY(gemm_group(gg, s));
+                GemmGroup gg;
+                memset(&gg, 0, sizeof(gg));
+                gg.count = 3;
+                {
+                    GemmProblem& p = gg.p[0];
+                    p.A = dgb; p.sam = 4 * c.n_b; p.sak = 1;
+                    p.B = e->prm(std::string(LSTM_B) + "weight_ih"); p.sbk = Kin; p.sbn = 1;
+                    p.A2 = dga; p.sam2 = 4 * c.n_a; p.sak2 = 1;
+                    p.B2 = e->prm(std::string(LSTM_A) + "weight_ih"); p.sbk2 = Kin; p.sbn2 = 1;
+                    p.C = dUt; p.ldc = Kin;
+                    p.M = M; p.N = Kin; p.K = 4 * c.n_b; p.K2 = 4 * c.n_a;
+                }
+                {
+                    GemmProblem& p = gg.p[1];
+                    p.A = dgb; p.sam = 4 * c.n_b; p.sak = 1;
+                    p.B = e->prm(std::string(LSTM_B) + "weight_hh"); p.sbk = c.n_b; p.sbn = 1;
+                    p.C = dh_t; p.ldc = c.n_b;
+                    p.M = M; p.N = c.n_b; p.K = 4 * c.n_b;
+                }
+                {
+                    GemmProblem& p = gg.p[2];
+                    p.A = dga; p.sam = 4 * c.n_a; p.sak = 1;
+                    p.B = e->prm(std::string(LSTM_A) + "weight_hh"); p.sbk = c.n_a; p.sbn = 1;
+                    p.C = dhc_t; p.ldc = c.n_a;
+                    p.M = M; p.N = c.n_a; p.K = 4 * c.n_a;
+                }
+                MARLC_TRY(gemm_group(gg, s));
             }
             // fused decoder backward (models.py:97-98) -> dcoll for step t-1
             BwdPostArgs bq;

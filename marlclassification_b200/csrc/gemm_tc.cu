@@ -123,6 +123,10 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
                  : "r"(addr))
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// MUFU-based activations for the tensor-core epilogue (abs error ~1e-7, far below TF32's)
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return fmaf(2.0f, fast_sigmoid(2.0f * x), -1.0f); }
+
 // smem matrix descriptor (cute::UMMA::SmemDescriptor bit layout).
 // layout_type: 2 = SWIZZLE_128B (K-major tiles), 1 = SWIZZLE_128B_BASE32B (MN-major TF32 tiles)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
@@ -153,8 +157,11 @@ struct TcKernelParams {
     float* gates;
     int n_hidden;
 };
-struct TcKernelParams2 {  // two independent problems in one launch (blockIdx.z)
-    TcKernelParams p[2];
+constexpr int TC_MAX_GROUP = 3;
+struct TcKernelGroup {  // up to 3 independent problems in one launch; blockIdx.z -> (problem, K split)
+    TcKernelParams p[TC_MAX_GROUP];
+    int zofs[TC_MAX_GROUP + 1];
+    int count;
 };
 
 template <int BN, int STAGES>
@@ -165,7 +172,7 @@ struct TcSmem {
 };
 
 template <int BN, bool A_MN, bool B_MN, int EPI, int STAGES>
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_constant__ TcKernelParams2 pp) {
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_constant__ TcKernelGroup pp) {
     using S = TcSmem<BN, STAGES>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -176,17 +183,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     __shared__ __align__(8) uint64_t tmem_full_bar;
     __shared__ uint32_t tmem_base_smem;
 
-    const bool two = (EPI == EPI_LSTM);
-    const TcKernelParams& p = pp.p[two ? blockIdx.z : 0];
+    int pi = 0;
+    while (pi + 1 < pp.count && (int)blockIdx.z >= pp.zofs[pi + 1]) ++pi;
+    const TcKernelParams& p = pp.p[pi];
+    const int split = (int)blockIdx.z - pp.zofs[pi];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * BM;
     const int n_tile = blockIdx.x;
+    if (m0 >= p.M || n_tile * BN >= p.N) return;  // grid is sized for the largest problem of the group
     // K-block range of this CTA (split-K over the concatenated list of both pairs)
     const int nkb = p.nk1 + p.nk2;
     int kb_begin = 0, kb_end = nkb;
     if (EPI == EPI_STORE && p.splits > 1) {
         const int per = (nkb + p.splits - 1) / p.splits;
-        kb_begin = blockIdx.z * per;
+        kb_begin = split * per;
         kb_end = min(nkb, kb_begin + per);
     }
     const int my_kb = max(0, kb_end - kb_begin);
@@ -271,24 +281,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
         if (EPI == EPI_STORE) {
             const int nbase = n_tile * BN;
             const bool vec = ((p.ldc & 3) == 0) && (((uintptr_t)p.C & 15) == 0);
-            const bool first_split = (p.splits <= 1) || (blockIdx.z == 0);
+            const bool first_split = (p.splits <= 1) || (split == 0);
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 8) {
-                uint32_t r[8];
-                if (my_kb > 0) { TMEM_LD8(trow + c0, r); tmem_ld_wait(); }
-                else {
+            for (int cb = 0; cb < BN; cb += 32) {
+                uint32_t rr[4][8];
+                if (my_kb > 0) {
+                    TMEM_LD8(trow + cb, rr[0]); TMEM_LD8(trow + cb + 8, rr[1]);
+                    TMEM_LD8(trow + cb + 16, rr[2]); TMEM_LD8(trow + cb + 24, rr[3]);
+                    tmem_ld_wait();
+                } else {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) r[j] = 0u;
+                    for (int q = 0; q < 4; ++q)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) rr[q][j] = 0u;
                 }
-                if (m < p.M) {
+                if (m >= p.M) continue;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int c0 = cb + 8 * q;
+                    if (nbase + c0 >= p.N) break;
                     float v[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const int n = nbase + c0 + j;
-                        v[j] = __uint_as_float(r[j]);
+                        v[j] = __uint_as_float(rr[q][j]);
                         if (first_split && n < p.N) {
-                            if (p.bias) v[j] += p.bias[n];
-                            if (p.bias2) v[j] += p.bias2[n];
+                            if (p.bias) v[j] += __ldg(p.bias + n);
+                            if (p.bias2) v[j] += __ldg(p.bias2 + n);
                         }
                     }
                     float* crow = p.C + (long)m * p.ldc + nbase + c0;
@@ -333,12 +352,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const int col = j0 + jb + j;
-                        gi[j] = sigmoidf_(__uint_as_float(ri[j]) + p.bias[col] + p.bias2[col]);
-                        gf[j] = sigmoidf_(__uint_as_float(rf[j]) + p.bias[n + col] + p.bias2[n + col]);
-                        gc[j] = tanhf(__uint_as_float(rg[j]) + p.bias[2 * n + col] + p.bias2[2 * n + col]);
-                        go[j] = sigmoidf_(__uint_as_float(ro[j]) + p.bias[3 * n + col] + p.bias2[3 * n + col]);
+                        gi[j] = fast_sigmoid(__uint_as_float(ri[j]) + __ldg(p.bias + col) + __ldg(p.bias2 + col));
+                        gf[j] = fast_sigmoid(__uint_as_float(rf[j]) + __ldg(p.bias + n + col) + __ldg(p.bias2 + n + col));
+                        gc[j] = fast_tanh(__uint_as_float(rg[j]) + __ldg(p.bias + 2 * n + col) + __ldg(p.bias2 + 2 * n + col));
+                        go[j] = fast_sigmoid(__uint_as_float(ro[j]) + __ldg(p.bias + 3 * n + col) + __ldg(p.bias2 + 3 * n + col));
                         cn[j] = gf[j] * cp[j] + gi[j] * gc[j];
-                        hn[j] = go[j] * tanhf(cn[j]);
+                        hn[j] = go[j] * fast_tanh(cn[j]);
                     }
                     float* g_row = p.gates + (long)m * 4 * n + j0 + jb;
                     auto st8 = [](float* dst, const float* v) {
@@ -370,7 +389,7 @@ static int operand_map(CUtensorMap* m, const TcOperand& o, int mn_extent, int k_
 }
 
 template <int BN, bool A_MN, bool B_MN>
-static int launch_store(const TcKernelParams2& kp, int gx, int gy, int gz, cudaStream_t s) {
+static int launch_store(const TcKernelGroup& kp, int gx, int gy, int gz, cudaStream_t s) {
     constexpr int STAGES = BN >= 256 ? 3 : 4;
     using S = TcSmem<BN, STAGES>;
     auto kern = tc_gemm_kernel<BN, A_MN, B_MN, EPI_STORE, STAGES>;
@@ -384,53 +403,75 @@ static int launch_store(const TcKernelParams2& kp, int gx, int gy, int gz, cudaS
     return 0;
 }
 
-int tc_gemm(const TcGemmArgs& a, cudaStream_t s) {
-    MARLC_CHECK(tc_operand_ok(a.A) && tc_operand_ok(a.B), "tc_gemm: operand not TMA-addressable");
-    MARLC_CHECK(a.K > 0 && a.M > 0 && a.N > 0, "tc_gemm: empty problem");
-    const bool pair2 = a.K2 > 0;
-    if (pair2) {
-        MARLC_CHECK(tc_operand_ok(a.A2) && tc_operand_ok(a.B2), "tc_gemm: second operand pair not TMA-addressable");
-        MARLC_CHECK(a.A2.mn_major == a.A.mn_major && a.B2.mn_major == a.B.mn_major, "tc_gemm: operand pairs must share majors");
-    }
-    // tile width: keep enough CTAs in flight for small problems
+static int pick_bn(const TcGemmArgs& a) {
     const int mt = (a.M + BM - 1) / BM;
+    if (a.N <= 32) return 32;
+    if (a.N <= 64 || mt * ((a.N + 127) / 128) < MARLC_SMS / 2) return 64;
+    return 128;
+}
+
+// Up to TC_MAX_GROUP problems with the same operand majors in ONE launch.
+int tc_gemm_group(const TcGemmArgs* args, int count, cudaStream_t s) {
+    MARLC_CHECK(count >= 1 && count <= TC_MAX_GROUP, "tc_gemm_group: count=%d", count);
     int BN = 128;
-    if (a.N <= 32) BN = 32;
-    else if (a.N <= 64 || mt * ((a.N + 127) / 128) < MARLC_SMS / 2) BN = 64;
-    TcKernelParams2 kp;
+    for (int i = 0; i < count; ++i) BN = min(BN, pick_bn(args[i]));
+    TcKernelGroup kp;
     memset(&kp, 0, sizeof(kp));
-    TcKernelParams& p = kp.p[0];
-    MARLC_TRY(operand_map(&p.a1, a.A, a.M, a.K, BM));
-    MARLC_TRY(operand_map(&p.b1, a.B, a.N, a.K, BN));
-    p.nk1 = (a.K + BK - 1) / BK;
-    p.slab_a1 = a.A.slab; p.slab_b1 = a.B.slab;
-    if (pair2) {
-        MARLC_TRY(operand_map(&p.a2, a.A2, a.M, a.K2, BM));
-        MARLC_TRY(operand_map(&p.b2, a.B2, a.N, a.K2, BN));
-        p.nk2 = (a.K2 + BK - 1) / BK;
-        p.slab_a2 = a.A2.slab; p.slab_b2 = a.B2.slab;
+    kp.count = count;
+    int gx = 0, gy = 0, ctas = 0;
+    for (int i = 0; i < count; ++i) {
+        const TcGemmArgs& a = args[i];
+        ctas += ((a.M + BM - 1) / BM) * ((a.N + BN - 1) / BN);
     }
-    p.M = a.M; p.N = a.N; p.C = a.C; p.ldc = a.ldc; p.bias = a.bias; p.bias2 = a.bias2;
-    p.accumulate = a.accumulate;
-    const int nt = (a.N + BN - 1) / BN, nkb = p.nk1 + p.nk2;
-    int splits = 1;
-    if (a.allow_split && mt * nt < MARLC_SMS) {
-        splits = min(max(1, nkb / 4), max(1, (2 * MARLC_SMS) / (mt * nt)));
-        // every split must own at least one K block
-        while (splits > 1 && ((nkb + splits - 1) / splits) * (splits - 1) >= nkb) --splits;
+    for (int i = 0; i < count; ++i) {
+        const TcGemmArgs& a = args[i];
+        MARLC_CHECK(tc_operand_ok(a.A) && tc_operand_ok(a.B), "tc_gemm: operand not TMA-addressable");
+        MARLC_CHECK(a.K > 0 && a.M > 0 && a.N > 0, "tc_gemm: empty problem");
+        MARLC_CHECK(a.A.mn_major == args[0].A.mn_major && a.B.mn_major == args[0].B.mn_major,
+                    "tc_gemm_group: all problems must share operand majors");
+        const bool pair2 = a.K2 > 0;
+        if (pair2) {
+            MARLC_CHECK(tc_operand_ok(a.A2) && tc_operand_ok(a.B2), "tc_gemm: second operand pair not TMA-addressable");
+            MARLC_CHECK(a.A2.mn_major == a.A.mn_major && a.B2.mn_major == a.B.mn_major, "tc_gemm: operand pairs must share majors");
+        }
+        TcKernelParams& p = kp.p[i];
+        MARLC_TRY(operand_map(&p.a1, a.A, a.M, a.K, BM));
+        MARLC_TRY(operand_map(&p.b1, a.B, a.N, a.K, BN));
+        p.nk1 = (a.K + BK - 1) / BK;
+        p.slab_a1 = a.A.slab; p.slab_b1 = a.B.slab;
+        if (pair2) {
+            MARLC_TRY(operand_map(&p.a2, a.A2, a.M, a.K2, BM));
+            MARLC_TRY(operand_map(&p.b2, a.B2, a.N, a.K2, BN));
+            p.nk2 = (a.K2 + BK - 1) / BK;
+            p.slab_a2 = a.A2.slab; p.slab_b2 = a.B2.slab;
+        }
+        p.M = a.M; p.N = a.N; p.C = a.C; p.ldc = a.ldc; p.bias = a.bias; p.bias2 = a.bias2;
+        p.accumulate = a.accumulate;
+        const int mt = (a.M + BM - 1) / BM, nt = (a.N + BN - 1) / BN, nkb = p.nk1 + p.nk2;
+        int splits = 1;
+        if (a.allow_split && ctas < MARLC_SMS) {
+            splits = min(max(1, nkb / 4), max(1, (2 * MARLC_SMS) / ctas));
+            // every split must own at least one K block
+            while (splits > 1 && ((nkb + splits - 1) / splits) * (splits - 1) >= nkb) --splits;
+        }
+        p.splits = splits;
+        if (splits > 1 && !a.accumulate && !a.c_zeroed) {
+            if (a.ldc == a.N) MARLC_CUDA(cudaMemsetAsync(a.C, 0, sizeof(float) * (size_t)a.M * a.N, s));
+            else MARLC_CUDA(cudaMemset2DAsync(a.C, sizeof(float) * a.ldc, 0, sizeof(float) * a.N, a.M, s));
+        }
+        kp.zofs[i + 1] = kp.zofs[i] + splits;
+        gx = max(gx, nt);
+        gy = max(gy, mt);
     }
-    p.splits = splits;
-    if (splits > 1 && !a.accumulate) {
-        if (a.ldc == a.N) MARLC_CUDA(cudaMemsetAsync(a.C, 0, sizeof(float) * (size_t)a.M * a.N, s));
-        else MARLC_CUDA(cudaMemset2DAsync(a.C, sizeof(float) * a.ldc, 0, sizeof(float) * a.N, a.M, s));
-    }
-#define DISPATCH(BNv)                                                                     \
-    if (a.A.mn_major) {                                                                   \
-        if (a.B.mn_major) return launch_store<BNv, true, true>(kp, nt, mt, splits, s);    \
-        return launch_store<BNv, true, false>(kp, nt, mt, splits, s);                     \
-    } else {                                                                              \
-        if (a.B.mn_major) return launch_store<BNv, false, true>(kp, nt, mt, splits, s);   \
-        return launch_store<BNv, false, false>(kp, nt, mt, splits, s);                    \
+    const int gz = kp.zofs[count];
+    const bool amn = args[0].A.mn_major, bmn = args[0].B.mn_major;
+#define DISPATCH(BNv)                                                            \
+    if (amn) {                                                                   \
+        if (bmn) return launch_store<BNv, true, true>(kp, gx, gy, gz, s);        \
+        return launch_store<BNv, true, false>(kp, gx, gy, gz, s);                \
+    } else {                                                                     \
+        if (bmn) return launch_store<BNv, false, true>(kp, gx, gy, gz, s);       \
+        return launch_store<BNv, false, false>(kp, gx, gy, gz, s);               \
     }
     if (BN == 32) { DISPATCH(32) }
     if (BN == 64) { DISPATCH(64) }
@@ -438,9 +479,11 @@ int tc_gemm(const TcGemmArgs& a, cudaStream_t s) {
 #undef DISPATCH
 }
 
+int tc_gemm(const TcGemmArgs& a, cudaStream_t s) { return tc_gemm_group(&a, 1, s); }
+
 template <int BN>
-static int launch_lstm(const TcKernelParams2& kp, int gx, int gy, cudaStream_t s) {
-    constexpr int STAGES = 4;
+static int launch_lstm(const TcKernelGroup& kp, int gx, int gy, cudaStream_t s) {
+    constexpr int STAGES = BN >= 128 ? 3 : 4;  // 3 x 32 KB: two CTAs per SM, one's epilogue overlaps the other's mainloop
     using S = TcSmem<BN, STAGES>;
     auto kern = tc_gemm_kernel<BN, false, false, EPI_LSTM, STAGES>;
     static bool attr_done = false;
@@ -467,8 +510,10 @@ int tc_lstm_pair(const TcLstmArgs& c0, const TcLstmArgs& c1, cudaStream_t s) {
     int HU = mt >= 8 ? 32 : (mt >= 2 ? 16 : 8);
     while (HU > 8 && (c0.n % HU != 0 || c1.n % HU != 0)) HU >>= 1;
     MARLC_CHECK(c0.n % HU == 0 && c1.n % HU == 0, "tc_lstm_pair: hidden size not a multiple of %d", HU);
-    TcKernelParams2 kp;
+    TcKernelGroup kp;
     memset(&kp, 0, sizeof(kp));
+    kp.count = 2;
+    kp.zofs[0] = 0; kp.zofs[1] = 1; kp.zofs[2] = 2;
     const TcLstmArgs* cs[2] = {&c0, &c1};
     int gx = 0;
     for (int k = 0; k < 2; ++k) {

@@ -38,8 +38,11 @@ struct TcGemmArgs {
     const float* bias2 = nullptr;
     int accumulate = 0;
     int allow_split = 0;  // split-K with an atomicAdd epilogue when the grid would be small
+    int c_zeroed = 0;     // C is known to be zero already: skip the memset a split-K launch needs
 };
 int tc_gemm(const TcGemmArgs& a, cudaStream_t s);
+// up to 3 problems with the same operand majors in ONE launch (blockIdx.z selects problem / K split)
+int tc_gemm_group(const TcGemmArgs* args, int count, cudaStream_t s);
 
 // One LSTM cell: gates = U Wih^T + Hprev Whh^T + bih + bhh, then the point-wise cell,
 // all in one kernel (recurrent.py:30).  gates receives the ACTIVATED i,f,g,o.
