@@ -51,13 +51,13 @@ struct CnnBwdArgs {
     CnnBwdBuffers buf;
     int offA[MAX_CNN_LAYERS], offY[MAX_CNN_LAYERS], offStat[MAX_CNN_LAYERS];
     int offD0, offD1, offW, wbuf;
-    int B, H, W, M, P;
+    int B, H, W, M, P, p0;
 };
 
 __global__ void __launch_bounds__(256) cnn_bwd_kernel(const CnnBwdArgs a) {
     extern __shared__ float sm[];
     const CnnDesc& d = a.d;
-    const int p = blockIdx.x, m = p % a.M, b = m % a.B;
+    const int p = a.p0 + blockIdx.x, m = p % a.M, b = m % a.B;
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
     const int f = d.f, ff = f * f;
 
@@ -218,10 +218,11 @@ __global__ void __launch_bounds__(256) cnn_bwd_kernel(const CnnBwdArgs a) {
     }
 }
 
-int cnn_bwd(const CnnDesc& d, const float* img, const int* pos_hist, int B, int H, int W, int M, int P,
+int cnn_bwd(const CnnDesc& d, const float* img, const int* pos_hist, int B, int H, int W, int M, int p0, int P,
             const float* const* y_save, const float* dOut, long lddo, const CnnBwdBuffers& buf, cudaStream_t s) {
     if (P <= 0) return 0;
     CnnBwdArgs a;
+    a.p0 = p0;
     a.d = d; a.img = img; a.pos_hist = pos_hist; a.dOut = dOut; a.lddo = lddo; a.buf = buf;
     a.B = B; a.H = H; a.W = W; a.M = M; a.P = P;
     int off = 0, mx = 0;

@@ -54,6 +54,18 @@ struct marlc_engine {
     float* P = nullptr;
     float* G = nullptr;
     int last_launches = 0;
+    // fork/join plumbing for independent branches (works eagerly and under stream capture)
+    cudaStream_t side[2] = {nullptr, nullptr};
+    cudaEvent_t ev[64];
+    int n_ev = 0, ev_i = 0;
+    cudaEvent_t next_event() { cudaEvent_t x = ev[ev_i]; ev_i = (ev_i + 1) % n_ev; return x; }
+    // make `to` wait for everything issued so far on `from`
+    int chain(cudaStream_t from, cudaStream_t to) {
+        cudaEvent_t x = next_event();
+        MARLC_CUDA(cudaEventRecord(x, from));
+        MARLC_CUDA(cudaStreamWaitEvent(to, x, 0));
+        return 0;
+    }
 
     // ---- layout helpers
     void add_param(const std::string& name, std::initializer_list<int64_t> shape) {
@@ -248,7 +260,13 @@ extern "C" int marlc_engine_create(const marlc_config* c, marlc_engine** out) {
     return 0;
 }
 
-extern "C" void marlc_engine_destroy(marlc_engine* e) { delete e; }
+extern "C" void marlc_engine_destroy(marlc_engine* e) {
+    if (!e) return;
+    for (int i = 0; i < e->n_ev; ++i) cudaEventDestroy(e->ev[i]);
+    for (int i = 0; i < 2; ++i)
+        if (e->side[i]) cudaStreamDestroy(e->side[i]);
+    delete e;
+}
 extern "C" int marlc_engine_param_count(const marlc_engine* e) { return (int)e->params.size(); }
 extern "C" int64_t marlc_engine_param_floats(const marlc_engine* e) { return e->param_floats; }
 extern "C" int marlc_engine_param_info(const marlc_engine* e, int idx, char* name, int64_t* offset, int* ndim,
@@ -279,6 +297,13 @@ extern "C" int marlc_engine_bind(marlc_engine* e, void* workspace, float* params
     e->ws = (char*)workspace;
     e->P = params;
     e->G = grads;
+    if (e->n_ev == 0) {
+        for (int i = 0; i < 2; ++i) MARLC_CUDA(cudaStreamCreateWithFlags(&e->side[i], cudaStreamNonBlocking));
+        for (int i = 0; i < 64; ++i) {
+            MARLC_CUDA(cudaEventCreateWithFlags(&e->ev[i], cudaEventDisableTiming));
+            e->n_ev = i + 1;
+        }
+    }
     for (int l = 0; l < e->L; ++l) {
         e->cnn.w[l] = e->prm(CNN_PREFIX + std::to_string(3 * l) + ".weight");
         e->cnn.b[l] = e->prm(CNN_PREFIX + std::to_string(3 * l) + ".bias");
@@ -800,6 +825,21 @@ extern "C" int marlc_episode_backward(marlc_engine* e, const float* img, int acc
                 }
                 MARLC_TRY(gemm_group(gg, s));
             }
+            // the feature extractor's backward for step t only needs du_t: run it on a side stream,
+            // concurrently with the rest of the sweep (the sweep kernels leave most SMs idle)
+            {
+                MARLC_TRY(e->chain(s, e->side[0]));
+                const float* ysave[MAX_CNN_LAYERS];
+                CnnBwdBuffers bb;
+                for (int l = 0; l < e->L; ++l) {
+                    ysave[l] = e->buf("cnn_y" + std::to_string(l));
+                    bb.dY[l] = e->buf("cnn_dY" + std::to_string(l));
+                    bb.col[l] = e->buf("cnn_col" + std::to_string(l));
+                    bb.gnpart[l] = e->buf("cnn_gnpart" + std::to_string(l));
+                }
+                MARLC_TRY(cnn_bwd(e->cnn, img, e->buf<int>("pos_hist"), c.nb, c.H, c.W, M, t * M, M, ysave, dU, Kin, bb,
+                                  e->side[0]));
+            }
             // fused decoder backward (models.py:97-98) -> dcoll for step t-1
             BwdPostArgs bq;
             memset(&bq, 0, sizeof(bq));
@@ -904,7 +944,12 @@ extern "C" int marlc_episode_backward(marlc_engine* e, const float* img, int acc
         }
     }
 
-    // ---- weight gradients, batched over all T*M rows (reduction dim T*M)
+    // ---- weight gradients, batched over all T*M rows (reduction dim T*M).  Three independent
+    //      branches: LSTM (main stream) | encoder / decoder / position features (side 1) |
+    //      feature extractor (side 0, after its per-step backward chunks)
+    const bool par = c.use_chains != 0;
+    cudaStream_t s1 = par ? e->side[1] : s, s0 = par ? e->side[0] : s;
+    if (par) MARLC_TRY(e->chain(s, s1));
     for (int k = 0; k < 2; ++k) {
         const std::string pre = k ? LSTM_A : LSTM_B;
         const int n = k ? c.n_a : c.n_b;
@@ -917,17 +962,17 @@ extern "C" int marlc_episode_backward(marlc_engine* e, const float* img, int acc
     if (T > 1) {
         const int R = (T - 1) * M;  // the last message is never consumed
         MARLC_TRY(G_tn(e, e->buf("d_enc_y2"), c.n_m, e->buf("enc_s1"), 2 * c.n_m, e->grd("encode_msg.3.weight"),
-                          2 * c.n_m, R, c.n_m, 2 * c.n_m, s));
+                       2 * c.n_m, R, c.n_m, 2 * c.n_m, s1));
         MARLC_TRY(G_tn(e, e->buf("d_enc_y1"), 2 * c.n_m, H + (size_t)M * c.n_b, c.n_b, e->grd("encode_msg.0.weight"),
-                          c.n_b, R, 2 * c.n_m, c.n_b, s));
+                       c.n_b, R, 2 * c.n_m, c.n_b, s1));
     }
     MARLC_TRY(G_tn(e, e->buf("d_dec_y2"), c.n_m_o, e->buf("dec_s1"), 2 * c.n_m, e->grd("decode_msg.3.weight"),
-                      2 * c.n_m, TM, c.n_m_o, 2 * c.n_m, s));
+                   2 * c.n_m, TM, c.n_m_o, 2 * c.n_m, s1));
     MARLC_TRY(G_tn(e, e->buf("d_dec_y1"), 2 * c.n_m, e->buf("coll"), c.n_m, e->grd("decode_msg.0.weight"), c.n_m, TM,
-                      2 * c.n_m, c.n_m, s));
+                   2 * c.n_m, c.n_m, s1));
     // position features (state.py:13-17)
-    MARLC_TRY(block_bwd_norm(e, "map_pos", 0, dU + F + c.n_m_o, Kin, e->buf("pos_y"), TM, c.n_d, e->buf("d_pos_y"), s));
-    MARLC_TRY(G_tn(e, e->buf("d_pos_y"), c.n_d, e->buf("npos"), 2, e->grd("map_pos.0.weight"), 2, TM, c.n_d, 2, s));
+    MARLC_TRY(block_bwd_norm(e, "map_pos", 0, dU + F + c.n_m_o, Kin, e->buf("pos_y"), TM, c.n_d, e->buf("d_pos_y"), s1));
+    MARLC_TRY(G_tn(e, e->buf("d_pos_y"), c.n_d, e->buf("npos"), 2, e->grd("map_pos.0.weight"), 2, TM, c.n_d, 2, s1));
     // feature extractor
     {
         const float* ysave[MAX_CNN_LAYERS];
@@ -938,16 +983,20 @@ extern "C" int marlc_episode_backward(marlc_engine* e, const float* img, int acc
             bb.col[l] = e->buf("cnn_col" + std::to_string(l));
             bb.gnpart[l] = e->buf("cnn_gnpart" + std::to_string(l));
         }
-        MARLC_TRY(cnn_bwd(e->cnn, img, e->buf<int>("pos_hist"), c.nb, c.H, c.W, M, TM, ysave, dU, Kin, bb, s));
+        if (!par) MARLC_TRY(cnn_bwd(e->cnn, img, e->buf<int>("pos_hist"), c.nb, c.H, c.W, M, 0, TM, ysave, dU, Kin, bb, s0));
         for (int l = 0; l < e->L; ++l) {
             const CnnDesc& d = e->cnn;
             const int npos = d.hout[l] * d.hout[l], kk = d.cin[l] * 9, co = d.cout[l];
             const std::string cw = CNN_PREFIX + std::to_string(3 * l), gn = CNN_PREFIX + std::to_string(3 * l + 1);
-            MARLC_TRY(G_tn(e, bb.dY[l], co, bb.col[l], kk, e->grd(cw + ".weight"), kk, TM * npos, co, kk, s));
-            MARLC_TRY(colsum_add(bb.dY[l], co, e->grd(cw + ".bias"), TM * npos, co, s));
-            MARLC_TRY(colsum_add(bb.gnpart[l], 2 * co, e->grd(gn + ".weight"), TM, co, s));
-            MARLC_TRY(colsum_add(bb.gnpart[l] + co, 2 * co, e->grd(gn + ".bias"), TM, co, s));
+            MARLC_TRY(G_tn(e, bb.dY[l], co, bb.col[l], kk, e->grd(cw + ".weight"), kk, TM * npos, co, kk, s0));
+            MARLC_TRY(colsum_add(bb.dY[l], co, e->grd(cw + ".bias"), TM * npos, co, s0));
+            MARLC_TRY(colsum_add(bb.gnpart[l], 2 * co, e->grd(gn + ".weight"), TM, co, s0));
+            MARLC_TRY(colsum_add(bb.gnpart[l] + co, 2 * co, e->grd(gn + ".bias"), TM, co, s0));
         }
+    }
+    if (par) {  // join
+        MARLC_TRY(e->chain(s0, s));
+        MARLC_TRY(e->chain(s1, s));
     }
     e->last_launches = g_launch_count - start;
     return 0;

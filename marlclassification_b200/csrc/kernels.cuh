@@ -71,9 +71,10 @@ struct CnnBwdBuffers {
     float* col[MAX_CNN_LAYERS];     // [P*hout^2, cin*9] im2col of the layer input
     float* gnpart[MAX_CNN_LAYERS];  // [P, 2*cout] per-window partial sums for dgamma | dbeta
 };
-// Backward through the CNN for P windows (P = T*M, window p uses image p % M % B ...):
-// re-gathers the input windows, recomputes the activations from y_save, writes dY/col/gnpart.
-int cnn_bwd(const CnnDesc& d, const float* img, const int* pos_hist, int B, int H, int W, int M, int P,
+// Backward through the CNN for windows p0 .. p0+P-1 of the T*M stack (window p uses image
+// (p % M) % B): re-gathers the input windows, recomputes the activations from y_save, writes
+// dY / col / gnpart rows of those windows.  All buffer pointers are for window 0.
+int cnn_bwd(const CnnDesc& d, const float* img, const int* pos_hist, int B, int H, int W, int M, int p0, int P,
             const float* const* y_save, const float* dOut, long lddo, const CnnBwdBuffers& buf, cudaStream_t s);
 
 // ---- loss.cu ------------------------------------------------------------------
