@@ -34,7 +34,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libmarlc.so")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", LIB + ".tmp", *sources()]
+    cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("MARLC_NVCC_EXTRA", "").split(), "-o", LIB + ".tmp", *sources()]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

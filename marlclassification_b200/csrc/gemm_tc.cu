@@ -13,6 +13,7 @@
 // mbarrier ring.  Epilogues: plain store / accumulate / split-K atomic add, and the
 // fused LSTM cell (gates i,f,g,o of one hidden unit live in the same CTA tile).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc.cuh"
@@ -169,24 +170,27 @@ struct TcSmem {
     static constexpr int A_BYTES = BM * BK * 4;
     static constexpr int B_BYTES = BN * BK * 4;
     static constexpr int BYTES = STAGES * (A_BYTES + B_BYTES) + 1024;
+    static constexpr int bytes(int stages) { return stages * (A_BYTES + B_BYTES) + 1024; }
 };
 
-template <int BN, bool A_MN, bool B_MN, int EPI, int STAGES>
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_constant__ TcKernelGroup pp) {
+
+// The body is instantiated once per problem slot so that every access to the kernel parameters
+// (in particular the TMA descriptors) uses a compile-time offset: indexing the parameter block
+// with a runtime problem index costs ~2 us per launch on B200 (measured).
+template <int BN, bool A_MN, bool B_MN, int EPI, int STAGES, int PI>
+__device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int split) {
     using S = TcSmem<BN, STAGES>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    constexpr int stages = STAGES;  // (a runtime ring depth of 2..8 made no measurable difference)
     uint8_t* sA = smem;
-    uint8_t* sB = smem + STAGES * S::A_BYTES;
+    uint8_t* sB = smem + stages * S::A_BYTES;
     __shared__ __align__(8) uint64_t full_bar[STAGES];
     __shared__ __align__(8) uint64_t empty_bar[STAGES];
     __shared__ __align__(8) uint64_t tmem_full_bar;
     __shared__ uint32_t tmem_base_smem;
 
-    int pi = 0;
-    while (pi + 1 < pp.count && (int)blockIdx.z >= pp.zofs[pi + 1]) ++pi;
-    const TcKernelParams& p = pp.p[pi];
-    const int split = (int)blockIdx.z - pp.zofs[pi];
+    const TcKernelParams& p = pp.p[PI];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * BM;
     const int n_tile = blockIdx.x;
@@ -203,7 +207,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(&tmem_full_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -221,7 +225,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
         // ============================ TMA producer ============================
         if (lane == 0) {
             for (int i = 0; i < my_kb; ++i) {
-                const int s = i % STAGES, ph = (i / STAGES) & 1;
+                const int s = i % stages, ph = (i / stages) & 1;
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 mbar_expect_tx(&full_bar[s], S::A_BYTES + S::B_BYTES);
                 const int kb = kb_begin + i;
@@ -254,7 +258,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) |
                                    ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
             for (int i = 0; i < my_kb; ++i) {
-                const int s = i % STAGES, ph = (i / STAGES) & 1;
+                const int s = i % stages, ph = (i / stages) & 1;
                 mbar_wait(&full_bar[s], ph);
                 tc_fence_after();
                 const uint32_t a_addr = smem_u32(sA + s * S::A_BYTES), b_addr = smem_u32(sB + s * S::B_BYTES);
@@ -282,32 +286,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
             const int nbase = n_tile * BN;
             const bool vec = ((p.ldc & 3) == 0) && (((uintptr_t)p.C & 15) == 0);
             const bool first_split = (p.splits <= 1) || (split == 0);
+            // 8 columns per tcgen05.ld + wait: the stores of one chunk overlap the TMEM read of the
+            // next (a 32-column variant with one wait per 4 loads measured 3 us SLOWER per launch)
 #pragma unroll 1
-            for (int cb = 0; cb < BN; cb += 32) {
-                uint32_t rr[4][8];
-                if (my_kb > 0) {
-                    TMEM_LD8(trow + cb, rr[0]); TMEM_LD8(trow + cb + 8, rr[1]);
-                    TMEM_LD8(trow + cb + 16, rr[2]); TMEM_LD8(trow + cb + 24, rr[3]);
-                    tmem_ld_wait();
-                } else {
+            for (int c0 = 0; c0 < BN; c0 += 8) {
+                uint32_t r[8];
+                if (my_kb > 0) { TMEM_LD8(trow + c0, r); tmem_ld_wait(); }
+                else {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q)
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) rr[q][j] = 0u;
+                    for (int j = 0; j < 8; ++j) r[j] = 0u;
                 }
-                if (m >= p.M) continue;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int c0 = cb + 8 * q;
-                    if (nbase + c0 >= p.N) break;
+                if (m < p.M) {
                     float v[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const int n = nbase + c0 + j;
-                        v[j] = __uint_as_float(rr[q][j]);
+                        v[j] = __uint_as_float(r[j]);
                         if (first_split && n < p.N) {
-                            if (p.bias) v[j] += __ldg(p.bias + n);
-                            if (p.bias2) v[j] += __ldg(p.bias2 + n);
+                            if (p.bias) v[j] += p.bias[n];
+                            if (p.bias2) v[j] += p.bias2[n];
                         }
                     }
                     float* crow = p.C + (long)m * p.ldc + nbase + c0;
@@ -379,6 +376,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     }
 }
 
+template <int BN, bool A_MN, bool B_MN, int EPI, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_constant__ TcKernelGroup pp) {
+    const int z = blockIdx.z;
+    if (pp.count >= 3 && z >= pp.zofs[2]) tc_gemm_body<BN, A_MN, B_MN, EPI, STAGES, 2>(pp, z - pp.zofs[2]);
+    else if (pp.count >= 2 && z >= pp.zofs[1]) tc_gemm_body<BN, A_MN, B_MN, EPI, STAGES, 1>(pp, z - pp.zofs[1]);
+    else tc_gemm_body<BN, A_MN, B_MN, EPI, STAGES, 0>(pp, z);
+}
+
 // ---------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------
@@ -389,8 +394,9 @@ static int operand_map(CUtensorMap* m, const TcOperand& o, int mn_extent, int k_
 }
 
 template <int BN, bool A_MN, bool B_MN>
-static int launch_store(const TcKernelGroup& kp, int gx, int gy, int gz, cudaStream_t s) {
-    constexpr int STAGES = BN >= 256 ? 3 : 4;
+static int launch_store(TcKernelGroup& kp, int gx, int gy, int gz, int max_kb, cudaStream_t s) {
+    (void)max_kb;
+    constexpr int STAGES = BN >= 128 ? 3 : 4;  // <= 96 KB: two CTAs per SM (epilogue / main loop overlap)
     using S = TcSmem<BN, STAGES>;
     auto kern = tc_gemm_kernel<BN, A_MN, B_MN, EPI_STORE, STAGES>;
     static bool attr_done = false;
@@ -464,14 +470,19 @@ int tc_gemm_group(const TcGemmArgs* args, int count, cudaStream_t s) {
         gy = max(gy, mt);
     }
     const int gz = kp.zofs[count];
+    int max_kb = 1;
+    for (int i = 0; i < count; ++i) {
+        const int nkb = kp.p[i].nk1 + kp.p[i].nk2;
+        max_kb = max(max_kb, (nkb + kp.p[i].splits - 1) / kp.p[i].splits);
+    }
     const bool amn = args[0].A.mn_major, bmn = args[0].B.mn_major;
-#define DISPATCH(BNv)                                                            \
-    if (amn) {                                                                   \
-        if (bmn) return launch_store<BNv, true, true>(kp, gx, gy, gz, s);        \
-        return launch_store<BNv, true, false>(kp, gx, gy, gz, s);                \
-    } else {                                                                     \
-        if (bmn) return launch_store<BNv, false, true>(kp, gx, gy, gz, s);       \
-        return launch_store<BNv, false, false>(kp, gx, gy, gz, s);               \
+#define DISPATCH(BNv)                                                                    \
+    if (amn) {                                                                           \
+        if (bmn) return launch_store<BNv, true, true>(kp, gx, gy, gz, max_kb, s);        \
+        return launch_store<BNv, true, false>(kp, gx, gy, gz, max_kb, s);                \
+    } else {                                                                             \
+        if (bmn) return launch_store<BNv, false, true>(kp, gx, gy, gz, max_kb, s);       \
+        return launch_store<BNv, false, false>(kp, gx, gy, gz, max_kb, s);               \
     }
     if (BN == 32) { DISPATCH(32) }
     if (BN == 64) { DISPATCH(64) }
@@ -482,8 +493,9 @@ int tc_gemm_group(const TcGemmArgs* args, int count, cudaStream_t s) {
 int tc_gemm(const TcGemmArgs& a, cudaStream_t s) { return tc_gemm_group(&a, 1, s); }
 
 template <int BN>
-static int launch_lstm(const TcKernelGroup& kp, int gx, int gy, cudaStream_t s) {
-    constexpr int STAGES = BN >= 128 ? 3 : 4;  // 3 x 32 KB: two CTAs per SM, one's epilogue overlaps the other's mainloop
+static int launch_lstm(TcKernelGroup& kp, int gx, int gy, int nkb, cudaStream_t s) {
+    (void)nkb;
+    constexpr int STAGES = BN >= 128 ? 3 : 4;  // 3 x 32 KB: two CTAs per SM, one's epilogue overlaps the other's main loop
     using S = TcSmem<BN, STAGES>;
     auto kern = tc_gemm_kernel<BN, false, false, EPI_LSTM, STAGES>;
     static bool attr_done = false;
@@ -534,9 +546,10 @@ int tc_lstm_pair(const TcLstmArgs& c0, const TcLstmArgs& c1, cudaStream_t s) {
         gx = max(gx, c.n / HU);
     }
     MARLC_CHECK(c0.n == c1.n, "tc_lstm_pair: the two cells must have the same hidden size (got %d, %d)", c0.n, c1.n);
-    if (HU == 8) return launch_lstm<32>(kp, gx, mt, s);
-    if (HU == 16) return launch_lstm<64>(kp, gx, mt, s);
-    return launch_lstm<128>(kp, gx, mt, s);
+    const int nkb = kp.p[0].nk1 + kp.p[0].nk2;
+    if (HU == 8) return launch_lstm<32>(kp, gx, mt, nkb, s);
+    if (HU == 16) return launch_lstm<64>(kp, gx, mt, nkb, s);
+    return launch_lstm<128>(kp, gx, mt, nkb, s);
 }
 
 }  // namespace marlc
