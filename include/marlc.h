@@ -145,6 +145,10 @@ int marlc_episode_backward(marlc_engine* e, const float* img, int accumulate, vo
 int marlc_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                     float beta1, float beta2, float eps, float grad_scale, int64_t* step, void* stream);
 
+/* Profiling aid: make marlc_episode_backward return after the head backward (1) or after the
+ * BPTT sweep (2); 0 restores the full backward.  Not for production use. */
+int marlc_engine_debug_stop(marlc_engine* e, int phase);
+
 /* Number of kernels the last forward/backward call launched (for bench accounting). */
 int marlc_engine_last_launches(const marlc_engine* e);
 

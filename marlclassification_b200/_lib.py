@@ -62,6 +62,7 @@ _SIGS = {
     "marlc_episode_backward": (C.c_int, [_P, _P, C.c_int, _P]),
     "marlc_adam_step": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                   _P, _P]),
+    "marlc_engine_debug_stop": (C.c_int, [_P, C.c_int]),
     "marlc_engine_last_launches": (C.c_int, [_P]),
 }
 

@@ -94,6 +94,20 @@ __device__ __forceinline__ void stage_w(float* dst, const float* __restrict__ W,
 }
 __host__ __device__ inline int odd_pitch(int K) { return K | 1; }
 
+// Asynchronous variant for matrices that are only walked column-wise (rb_dx_s: pitch == K needs no
+// padding): 16-byte cp.async requests are issued and the thread moves on; stage_wait() + a
+// __syncthreads() make the data visible.  Lets the copy overlap the first phases of a kernel.
+__device__ __forceinline__ bool stage_w_async(float* dst, const float* __restrict__ W, int N, int K) {
+    if (((K & 3) != 0) || ((reinterpret_cast<uintptr_t>(W) & 15) != 0)) { stage_rows(dst, W, N, K, K); return false; }
+    const int tot4 = (N * K) >> 2;
+    const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(dst);
+    for (int i = threadIdx.x; i < tot4; i += CT)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + 16u * i), "l"(W + 4 * (long)i) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    return true;
+}
+__device__ __forceinline__ void stage_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // rb_linear with W resident in smem (row pitch P odd => conflict-free column walk)
 __device__ void rb_linear_s(const float* xT, const float* Ws, int P, const float* __restrict__ bias, float* ys, int ldy,
                             int N, int K) {
@@ -459,6 +473,46 @@ int step_post(const StepPostArgs& a, cudaStream_t s) {
 // ---------------------------------------------------------------------------------
 // backward "pre" (step t): adjoint message mean -> encoder backward -> dh += ... -> both LSTM cells
 // ---------------------------------------------------------------------------------
+
+// Point-wise LSTM backward for RB rows of one cell (recurrent.py:30).  Columns are strided over the
+// threads, the RB rows are unrolled so their ~9 loads each are all in flight together.
+__device__ __forceinline__ void cell_bwd_rows(const int row0, const int rows_valid, const int n,
+                                              const float* __restrict__ gates, const float* __restrict__ dh_heads,
+                                              const float* __restrict__ dh_carry, const float* __restrict__ dc_next,
+                                              const float* __restrict__ c_prev, const float* __restrict__ c_new,
+                                              const float* dhx, const int ldx, float* __restrict__ dgates,
+                                              float* __restrict__ dc_prev) {
+    for (int j = threadIdx.x; j < n; j += CT) {
+        float gi[RB], gf[RB], gg[RB], go[RB], dh[RB], dcn[RB], cp[RB], cn[RB];
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+            if (r < rows_valid) {
+                const long m = row0 + r, idx = m * n + j;
+                const float* g = gates + m * 4 * n;
+                gi[r] = g[j]; gf[r] = g[n + j]; gg[r] = g[2 * n + j]; go[r] = g[3 * n + j];
+                dh[r] = dh_heads[idx] + (dh_carry ? dh_carry[idx] : 0.f);
+                dcn[r] = dc_next ? dc_next[idx] : 0.f;
+                cp[r] = c_prev[idx]; cn[r] = c_new[idx];
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+            if (r < rows_valid) {
+                const long m = row0 + r, idx = m * n + j;
+                const float dhv = dh[r] + (dhx ? dhx[r * ldx + j] : 0.f);
+                const float tc = tanhf(cn[r]);
+                const float dc = dcn[r] + dhv * go[r] * (1.f - tc * tc);
+                float* dg = dgates + m * 4 * n;
+                dg[j] = dc * gg[r] * gi[r] * (1.f - gi[r]);
+                dg[n + j] = dc * cp[r] * gf[r] * (1.f - gf[r]);
+                dg[2 * n + j] = dc * gi[r] * (1.f - gg[r] * gg[r]);
+                dg[3 * n + j] = dhv * tc * go[r] * (1.f - go[r]);
+                dc_prev[idx] = dc * gf[r];
+            }
+        }
+    }
+}
+
 struct BwdPreKernelArgs { BwdPreArgs a; int maxw; int staged; };
 
 __global__ void __launch_bounds__(CT) bwd_pre_kernel(const BwdPreKernelArgs ka) {
@@ -470,8 +524,15 @@ __global__ void __launch_bounds__(CT) bwd_pre_kernel(const BwdPreKernelArgs ka) 
     float* dhx = S.bufC;  // [RB][mw] encoder contribution to dh (belief cell only)
     float* W3s = S.wres;             // encode_msg.3 weight [n_m][n1]
     float* W0s = W3s + n_m * n1;     // encode_msg.0 weight [n1][nb]
-    if (a.dcoll) {
-        if (ka.staged) { stage_w(W3s, a.e3.W, n_m, n1, n1); stage_w(W0s, a.e0.W, n1, nb, nb); }
+    const bool enc = a.dcoll != nullptr;
+    if (enc && ka.staged) {  // asynchronous: overlaps the action cell and the first encoder phases
+        stage_w_async(W3s, a.e3.W, n_m, n1);
+        stage_w_async(W0s, a.e0.W, n1, nb);
+    }
+    // the action cell does not depend on the encoder chain: do it while the weights stream in
+    cell_bwd_rows(row0, rows_valid, a.n[1], a.gates[1], a.dh_heads[1], a.dh_carry[1], a.dc_next[1], a.c_prev[1],
+                  a.c_new[1], nullptr, 0, a.dgates[1], a.dc_prev[1]);
+    if (enc) {
         // gradient of the message produced at step t = adjoint mean of dcoll(t+1); encoder block 3 backward
         for (int e = threadIdx.x; e < RB * n_m; e += CT) {
             const int r = e / n_m, j = e % n_m;
@@ -482,6 +543,7 @@ __global__ void __launch_bounds__(CT) bwd_pre_kernel(const BwdPreKernelArgs ka) 
         __syncthreads();
         rb_ln_silu_bwd(S.bufA, S.bufB, mw, n_m, a.e3.g, a.e3.be, rows_valid, row0, dhx, S.bufT, a.d_enc_y2, n_m,
                        a.e3.dg, a.e3.dbe, a.e3.db);
+        if (ka.staged) { stage_wait_all(); __syncthreads(); }
         if (ka.staged) rb_dx_s(S.bufT, W3s, n1, S.bufA, mw, n_m, n1);  // ds1 [RB][2n_m]
         else rb_dx(S.bufT, a.e3.W, S.bufA, mw, n_m, n1);
         for (int e = threadIdx.x; e < RB * n1; e += CT) {
@@ -494,27 +556,8 @@ __global__ void __launch_bounds__(CT) bwd_pre_kernel(const BwdPreKernelArgs ka) 
         if (ka.staged) rb_dx_s(S.bufT, W0s, nb, dhx, mw, n1, nb);      // dh contribution [RB][n_b]
         else rb_dx(S.bufT, a.e0.W, dhx, mw, n1, nb);
     }
-    // point-wise LSTM backward, both cells (recurrent.py:30)
-    for (int k = 0; k < 2; ++k) {
-        const int n = a.n[k];
-        for (int e = threadIdx.x; e < rows_valid * n; e += CT) {
-            const int r = e / n, j = e % n;
-            const long m = row0 + r, idx = m * n + j;
-            const float* g = a.gates[k] + m * 4 * n;
-            const float gi = g[j], gf = g[n + j], gg = g[2 * n + j], go = g[3 * n + j];
-            float dh = a.dh_heads[k][idx];
-            if (a.dh_carry[k]) dh += a.dh_carry[k][idx];
-            if (k == 0 && a.dcoll) dh += dhx[r * mw + j];
-            const float tc = tanhf(a.c_new[k][idx]);
-            const float dc = (a.dc_next[k] ? a.dc_next[k][idx] : 0.f) + dh * go * (1.f - tc * tc);
-            float* dg = a.dgates[k] + m * 4 * n;
-            dg[j] = dc * gg * gi * (1.f - gi);
-            dg[n + j] = dc * a.c_prev[k][idx] * gf * (1.f - gf);
-            dg[2 * n + j] = dc * gi * (1.f - gg * gg);
-            dg[3 * n + j] = dh * tc * go * (1.f - go);
-            a.dc_prev[k][idx] = dc * gf;
-        }
-    }
+    cell_bwd_rows(row0, rows_valid, a.n[0], a.gates[0], a.dh_heads[0], a.dh_carry[0], a.dc_next[0], a.c_prev[0],
+                  a.c_new[0], enc ? dhx : nullptr, mw, a.dgates[0], a.dc_prev[0]);
 }
 
 int bwd_pre(const BwdPreArgs& a, cudaStream_t s) {
@@ -549,7 +592,7 @@ __global__ void __launch_bounds__(CT) bwd_post_kernel(const BwdPostKernelArgs ka
     const int n_m = a.n_m, n1 = a.d0.n_out, n2 = a.n_m_o;
     float* W3s = S.wres;           // decode_msg.3 weight [n2][n1]
     float* W0s = W3s + n2 * n1;    // decode_msg.0 weight [n1][n_m]
-    if (ka.staged) { stage_w(W3s, a.d3.W, n2, n1, n1); if (a.dcoll) stage_w(W0s, a.d0.W, n1, n_m, n_m); }
+    if (ka.staged) { stage_w_async(W3s, a.d3.W, n2, n1); if (a.dcoll) stage_w_async(W0s, a.d0.W, n1, n_m); }
     for (int e = threadIdx.x; e < RB * n2; e += CT) {
         const int r = e / n2, j = e % n2;
         const bool ok = r < rows_valid;
@@ -559,6 +602,7 @@ __global__ void __launch_bounds__(CT) bwd_post_kernel(const BwdPostKernelArgs ka
     __syncthreads();
     rb_ln_silu_bwd(S.bufA, S.bufB, mw, n2, a.d3.g, a.d3.be, rows_valid, row0, S.bufC, S.bufT, a.d_dec_y2, n2, a.d3.dg,
                    a.d3.dbe, a.d3.db);
+    if (ka.staged) { stage_wait_all(); __syncthreads(); }
     if (ka.staged) rb_dx_s(S.bufT, W3s, n1, S.bufA, mw, n2, n1);
     else rb_dx(S.bufT, a.d3.W, S.bufA, mw, n2, n1);
     for (int e = threadIdx.x; e < RB * n1; e += CT) {

@@ -54,6 +54,7 @@ struct marlc_engine {
     float* P = nullptr;
     float* G = nullptr;
     int last_launches = 0;
+    int debug_stop = 0;  // profiling aid: 1 = stop backward after the heads, 2 = after the sweep
     // fork/join plumbing for independent branches (works eagerly and under stream capture)
     cudaStream_t side[2] = {nullptr, nullptr};
     cudaEvent_t ev[64];
@@ -720,6 +721,7 @@ extern "C" int marlc_episode_backward(marlc_engine* e, const float* img, int acc
     MARLC_TRY(head_bwd(e, "critic", e->buf("d_values"), 1, e->buf("cri_s1"), e->buf("cri_y1"), Hc + (size_t)M * c.n_a,
                        c.n_a, c.nl_a, e->buf("dHc_heads"), 1, s));
 
+    if (e->debug_stop == 1) { e->last_launches = g_launch_count - start; return 0; }
     // ---- BPTT sweep
     float* dh = e->buf("dh");
     float* dhc = e->buf("dhc");
@@ -944,6 +946,11 @@ extern "C" int marlc_episode_backward(marlc_engine* e, const float* img, int acc
         }
     }
 
+    if (e->debug_stop == 2) {
+        if (c.use_chains) MARLC_TRY(e->chain(e->side[0], s));
+        e->last_launches = g_launch_count - start;
+        return 0;
+    }
     // ---- weight gradients, batched over all T*M rows (reduction dim T*M).  Three independent
     //      branches: LSTM (main stream) | encoder / decoder / position features (side 1) |
     //      feature extractor (side 0, after its per-step backward chunks)
@@ -1080,3 +1087,6 @@ extern "C" int marlc_tc_lstm_pair(const float* u, int M, int Kin, int n, const f
     }
     return tc_lstm_pair(la[0], la[1], (cudaStream_t)stream);
 }
+
+// Profiling aid (scripts/phase_times.py): truncate marlc_episode_backward after a phase.
+extern "C" int marlc_engine_debug_stop(marlc_engine* e, int phase) { e->debug_stop = phase; return 0; }

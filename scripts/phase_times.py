@@ -23,8 +23,14 @@ img = torch.rand(nb, w["C"], w["H"], w["W"], device=dev)
 y = torch.randint(w["nc"], (nb,), device=dev)
 eng = sampler.engine_for(img)
 opt = FlatAdam(model, 1e-4)
-phases = {"forward": lambda: eng.forward(img), "loss": lambda: eng.loss(y), "backward": lambda: eng.backward(img),
-          "adam": lambda: opt.step()}
+def bwd(stop):
+    def f():
+        eng._L.marlc_engine_debug_stop(eng._h, stop)
+        eng.backward(img)
+        eng._L.marlc_engine_debug_stop(eng._h, 0)
+    return f
+phases = {"forward": lambda: eng.forward(img), "loss": lambda: eng.loss(y), "bwd:heads": bwd(1), "bwd:heads+sweep": bwd(2),
+          "backward": lambda: eng.backward(img), "adam": lambda: opt.step()}
 side = torch.cuda.Stream()
 with torch.cuda.stream(side):
     for _ in range(3):
@@ -44,6 +50,6 @@ for name, f in phases.items():
         g.replay()
     b.record(); torch.cuda.synchronize()
     t = a.elapsed_time(b) / 20
-    tot += t
+    tot += 0.0 if name.startswith("bwd:") else t
     print(f"{name:9s} {t * 1e3:9.1f} us   launches {eng.launches.get(name, 2)}")
 print(f"total     {tot * 1e3:9.1f} us  -> {nb / tot * 1e3:.0f} image-episodes/s  ({wl}, batch {nb})")
