@@ -1,0 +1,175 @@
+// Layer-wise backward of the feature extractor, batched over ALL T*M windows of the episode.
+//
+// The per-window fused backward (cnn.cu::cnn_bwd_kernel) spends its time in FFMA loops for the
+// conv input gradient.  Here every conv product is a tensor-core GEMM over all windows instead:
+//     dCol_l = dY_l . W_l              [P*npos_l, cout_l] x [cout_l, cin_l*9]     (input gradient)
+//     dW_l  += dY_l^T . col_l          reduction over P*npos_l rows                (weight gradient)
+// and the only SIMT work left is element-wise per window (one warp per window, this file):
+//   * col2im gather of dCol_{l+1} -> dA_l (or the rows of dU for the top layer),
+//   * GroupNorm + SiLU backward -> dY_l (row layout for the GEMMs) and the per-window
+//     dgamma / dbeta partials,
+//   * im2col of the recomputed activation A_l -> col_{l+1} (operand of dW_{l+1}).
+#include "kernels.cuh"
+
+namespace marlc {
+
+constexpr float GN_EPS2 = 1e-5f;
+
+struct CnnBwdLayerKernelArgs {
+    CnnBwdLayerArgs a;
+    int total, npos, npn, per_warp;  // per_warp: floats of smem per warp (3 * total rounded)
+};
+
+__global__ void __launch_bounds__(256) cnn_bwd_layer_kernel(const CnnBwdLayerKernelArgs ka) {
+    extern __shared__ float sm[];
+    const CnnBwdLayerArgs& a = ka.a;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    const int p = blockIdx.x * wpc + warp;
+    if (p >= a.P) return;
+    const int total = ka.total, npos = ka.npos, ho = a.ho, co_n = a.cout;
+    float* xh = sm + (size_t)warp * ka.per_warp;  // y, then xhat
+    float* dz = xh + total;                       // dA, then dz, then dy
+    float* act = dz + total;                      // SiLU(GN(y))
+    // ---- 1. load y and the incoming gradient dA_l
+    const float* yg = a.Y + (long)p * total;
+    if (a.dOut) {
+        const float* go = a.dOut + (long)p * a.lddo;
+        for (int e = lane; e < total; e += 32) { xh[e] = yg[e]; dz[e] = go[e]; }
+    } else {
+        // col2im: dA[c, iy, ix] = sum over taps (ky,kx) with (iy+1-ky, ix+1-kx) even and in range
+        const int hon = a.ho_next, npn = ka.npn, kk = co_n * 9;
+        const float* dc = a.dColNext + (long)p * npn * kk;
+        for (int e = lane; e < total; e += 32) {
+            xh[e] = yg[e];
+            const int c = e / npos, pos = e - c * npos, iy = pos / ho, ix = pos - iy * ho;
+            float acc = 0.f;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                const int ty = iy + 1 - ky;
+                if (ty < 0 || (ty & 1) || (ty >> 1) >= hon) continue;
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int tx = ix + 1 - kx;
+                    if (tx < 0 || (tx & 1) || (tx >> 1) >= hon) continue;
+                    acc += dc[(long)((ty >> 1) * hon + (tx >> 1)) * kk + c * 9 + ky * 3 + kx];
+                }
+            }
+            dz[e] = acc;
+        }
+    }
+    __syncwarp();
+    // ---- 2. GroupNorm + SiLU backward, group by group (a group's channels are contiguous)
+    const int G = a.groups, cpg = co_n / G, ng = cpg * npos;
+    const float inv = 1.0f / (float)ng;
+    for (int g = 0; g < G; ++g) {
+        float* xg = xh + g * ng;
+        float* dg = dz + g * ng;
+        float* ag = act + g * ng;
+        float s = 0.f;
+        for (int e = lane; e < ng; e += 32) s += xg[e];
+        const float mean = warp_sum(s) * inv;
+        float v = 0.f;
+        for (int e = lane; e < ng; e += 32) { const float d = xg[e] - mean; v += d * d; }
+        const float rstd = 1.0f / sqrtf(warp_sum(v) * inv + GN_EPS2);
+        float s1 = 0.f, s2 = 0.f;
+        for (int e = lane; e < ng; e += 32) {
+            const int c = g * cpg + e / npos;
+            const float gam = a.gn_w[c];
+            const float x = (xg[e] - mean) * rstd, z = x * gam + a.gn_b[c];
+            const float sg = sigmoidf_(z);
+            ag[e] = z * sg;
+            const float d = dg[e] * (sg * (1.f + z * (1.f - sg)));
+            xg[e] = x;
+            dg[e] = d;
+            s1 += d * gam;
+            s2 += d * gam * x;
+        }
+        s1 = warp_sum(s1) * inv;
+        s2 = warp_sum(s2) * inv;
+        __syncwarp();
+        // per-channel partials for dgamma / dbeta (lanes over the group's channels)
+        float* gp = a.gnpart + (long)p * 2 * co_n;
+        for (int cc = lane; cc < cpg; cc += 32) {
+            float t1 = 0.f, t2 = 0.f;
+            for (int q = 0; q < npos; ++q) { const float d = dg[cc * npos + q]; t1 += d * xg[cc * npos + q]; t2 += d; }
+            gp[g * cpg + cc] = t1;
+            gp[co_n + g * cpg + cc] = t2;
+        }
+        __syncwarp();
+        for (int e = lane; e < ng; e += 32) {
+            const int c = g * cpg + e / npos;
+            dg[e] = rstd * (dg[e] * a.gn_w[c] - s1 - xg[e] * s2);
+        }
+    }
+    __syncwarp();
+    // ---- 3. dY rows [pos][co] (GEMM layout), coalesced
+    {
+        float* dyg = a.dY + (long)p * total;
+        for (int e = lane; e < total; e += 32) {
+            const int pos = e / co_n, c = e - pos * co_n;
+            dyg[e] = dz[c * npos + pos];
+        }
+    }
+    // ---- 4. im2col of A_l for the weight gradient of layer l+1
+    if (a.colNext) {
+        const int hon = a.ho_next, npn = ka.npn, kk = co_n * 9;
+        float* cg = a.colNext + (long)p * npn * kk;
+        for (int e = lane; e < npn * kk; e += 32) {
+            const int o = e / kk, r = e - o * kk, c = r / 9, q = r - c * 9, ky = q / 3, kx = q - ky * 3;
+            const int iy = 2 * (o / hon) - 1 + ky, ix = 2 * (o % hon) - 1 + kx;
+            cg[e] = (iy >= 0 && iy < ho && ix >= 0 && ix < ho) ? act[c * npos + iy * ho + ix] : 0.f;
+        }
+    }
+}
+
+int cnn_bwd_layer(const CnnBwdLayerArgs& a, cudaStream_t s) {
+    if (a.P <= 0) return 0;
+    CnnBwdLayerKernelArgs ka;
+    ka.a = a;
+    ka.npos = a.ho * a.ho;
+    ka.total = a.cout * ka.npos;
+    ka.npn = a.ho_next * a.ho_next;
+    ka.per_warp = 3 * ((ka.total + 3) & ~3);
+    int wpc = 8;
+    while (wpc > 1 && (size_t)wpc * ka.per_warp * sizeof(float) > 160 * 1024) wpc >>= 1;
+    const size_t smem = (size_t)wpc * ka.per_warp * sizeof(float);
+    MARLC_CHECK(smem <= 200 * 1024, "cnn_bwd_layer: layer too large for shared memory (%zu B)", smem);
+    static size_t attr = 0;
+    if (smem > 48 * 1024 && smem > attr) {
+        MARLC_CUDA(cudaFuncSetAttribute(cnn_bwd_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = smem;
+    }
+    cnn_bwd_layer_kernel<<<(a.P + wpc - 1) / wpc, wpc * 32, smem, s>>>(ka);
+    MARLC_LAUNCH_CHECK();
+    return 0;
+}
+
+// im2col of the gathered input windows (operand of the first layer's weight gradient):
+// col[(p*npos + o), ci*9 + ky*3 + kx] = img[b, ci, py + 2oy-1+ky, px + 2ox-1+kx] (0 outside the window)
+__global__ void __launch_bounds__(256) cnn_im2col_input_kernel(const float* __restrict__ img,
+                                                               const int* __restrict__ pos_hist, float* __restrict__ col,
+                                                               int P, int M, int B, int img_c, int cin, int H, int W,
+                                                               int f, int ho) {
+    const int lane = threadIdx.x & 31;
+    const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (p >= P) return;
+    const int b = (p % M) % B, py = pos_hist[2 * (long)p], px = pos_hist[2 * (long)p + 1];
+    const float* src = img + (long)b * img_c * H * W;
+    const int kk = cin * 9, npos = ho * ho;
+    float* cg = col + (long)p * npos * kk;
+    for (int e = lane; e < npos * kk; e += 32) {
+        const int o = e / kk, r = e - o * kk, c = r / 9, q = r - c * 9, ky = q / 3, kx = q - ky * 3;
+        const int iy = 2 * (o / ho) - 1 + ky, ix = 2 * (o % ho) - 1 + kx;
+        cg[e] = (iy >= 0 && iy < f && ix >= 0 && ix < f) ? __ldg(src + ((long)c * H + py + iy) * W + px + ix) : 0.f;
+    }
+}
+
+int cnn_im2col_input(const float* img, const int* pos_hist, float* col, int P, int M, int B, int img_c, int cin, int H,
+                     int W, int f, int ho, cudaStream_t s) {
+    if (P <= 0) return 0;
+    cnn_im2col_input_kernel<<<(P * 32 + 255) / 256, 256, 0, s>>>(img, pos_hist, col, P, M, B, img_c, cin, H, W, f, ho);
+    MARLC_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace marlc

@@ -256,6 +256,7 @@ extern "C" int marlc_engine_create(const marlc_config* c, marlc_engine** out) {
         e->add_buf("cnn_dY" + std::to_string(l), TM * npos * d.cout[l] * F4);
         e->add_buf("cnn_col" + std::to_string(l), TM * npos * d.cin[l] * 9 * F4);
         e->add_buf("cnn_gnpart" + std::to_string(l), TM * 2 * d.cout[l] * F4);
+        if (l > 0) e->add_buf("cnn_dcol" + std::to_string(l), TM * npos * d.cin[l] * 9 * F4);
     }
     *out = e;
     return 0;
@@ -348,6 +349,10 @@ static int G_nn(const marlc_engine* e, const float* dY, long lddy, const float* 
         if (tc_operand_ok(a.A) && tc_operand_ok(a.B)) return tc_gemm(a, s);
     }
     return gemm_nn(dY, lddy, W, ldw, dX, lddx, M, N, K, accumulate, s);
+}
+static int G_nn_on(const marlc_engine* e, const float* dY, long lddy, const float* W, long ldw, float* dX, long lddx,
+                   int M, int N, int K, cudaStream_t s) {
+    return G_nn(e, dY, lddy, W, ldw, dX, lddx, M, N, K, 0, s);
 }
 // dW[N,K] += dY[R,N]^T X[R,K]   (reduction over rows R; both operands MN-major)
 static int G_tn(const marlc_engine* e, const float* dY, long lddy, const float* X, long ldx, float* dW, long lddw, int R,
@@ -827,21 +832,6 @@ extern "C" int marlc_episode_backward(marlc_engine* e, const float* img, int acc
                 }
                 MARLC_TRY(gemm_group(gg, s));
             }
-            // the feature extractor's backward for step t only needs du_t: run it on a side stream,
-            // concurrently with the rest of the sweep (the sweep kernels leave most SMs idle)
-            {
-                MARLC_TRY(e->chain(s, e->side[0]));
-                const float* ysave[MAX_CNN_LAYERS];
-                CnnBwdBuffers bb;
-                for (int l = 0; l < e->L; ++l) {
-                    ysave[l] = e->buf("cnn_y" + std::to_string(l));
-                    bb.dY[l] = e->buf("cnn_dY" + std::to_string(l));
-                    bb.col[l] = e->buf("cnn_col" + std::to_string(l));
-                    bb.gnpart[l] = e->buf("cnn_gnpart" + std::to_string(l));
-                }
-                MARLC_TRY(cnn_bwd(e->cnn, img, e->buf<int>("pos_hist"), c.nb, c.H, c.W, M, t * M, M, ysave, dU, Kin, bb,
-                                  e->side[0]));
-            }
             // fused decoder backward (models.py:97-98) -> dcoll for step t-1
             BwdPostArgs bq;
             memset(&bq, 0, sizeof(bq));
@@ -947,7 +937,6 @@ extern "C" int marlc_episode_backward(marlc_engine* e, const float* img, int acc
     }
 
     if (e->debug_stop == 2) {
-        if (c.use_chains) MARLC_TRY(e->chain(e->side[0], s));
         e->last_launches = g_launch_count - start;
         return 0;
     }
@@ -980,25 +969,55 @@ extern "C" int marlc_episode_backward(marlc_engine* e, const float* img, int acc
     // position features (state.py:13-17)
     MARLC_TRY(block_bwd_norm(e, "map_pos", 0, dU + F + c.n_m_o, Kin, e->buf("pos_y"), TM, c.n_d, e->buf("d_pos_y"), s1));
     MARLC_TRY(G_tn(e, e->buf("d_pos_y"), c.n_d, e->buf("npos"), 2, e->grd("map_pos.0.weight"), 2, TM, c.n_d, 2, s1));
-    // feature extractor
+    // feature extractor: layer-wise, batched over all T*M windows (cnn_bwd2.cu); every conv product
+    // (input gradient dCol_l = dY_l W_l, weight gradient dW_l = dY_l^T col_l) is a tensor-core GEMM
     {
+        const CnnDesc& d = e->cnn;
         const float* ysave[MAX_CNN_LAYERS];
         CnnBwdBuffers bb;
+        float* dcol[MAX_CNN_LAYERS] = {nullptr};
         for (int l = 0; l < e->L; ++l) {
             ysave[l] = e->buf("cnn_y" + std::to_string(l));
             bb.dY[l] = e->buf("cnn_dY" + std::to_string(l));
             bb.col[l] = e->buf("cnn_col" + std::to_string(l));
             bb.gnpart[l] = e->buf("cnn_gnpart" + std::to_string(l));
+            if (l > 0) dcol[l] = e->buf("cnn_dcol" + std::to_string(l));
         }
-        if (!par) MARLC_TRY(cnn_bwd(e->cnn, img, e->buf<int>("pos_hist"), c.nb, c.H, c.W, M, 0, TM, ysave, dU, Kin, bb, s0));
-        for (int l = 0; l < e->L; ++l) {
-            const CnnDesc& d = e->cnn;
+        auto weight_grads = [&](int l) -> int {
             const int npos = d.hout[l] * d.hout[l], kk = d.cin[l] * 9, co = d.cout[l];
             const std::string cw = CNN_PREFIX + std::to_string(3 * l), gn = CNN_PREFIX + std::to_string(3 * l + 1);
             MARLC_TRY(G_tn(e, bb.dY[l], co, bb.col[l], kk, e->grd(cw + ".weight"), kk, TM * npos, co, kk, s0));
             MARLC_TRY(colsum_add(bb.dY[l], co, e->grd(cw + ".bias"), TM * npos, co, s0));
             MARLC_TRY(colsum_add(bb.gnpart[l], 2 * co, e->grd(gn + ".weight"), TM, co, s0));
             MARLC_TRY(colsum_add(bb.gnpart[l] + co, 2 * co, e->grd(gn + ".bias"), TM, co, s0));
+            return 0;
+        };
+        if (!par) {
+            MARLC_TRY(cnn_bwd(e->cnn, img, e->buf<int>("pos_hist"), c.nb, c.H, c.W, M, 0, TM, ysave, dU, Kin, bb, s0));
+            for (int l = 0; l < e->L; ++l) MARLC_TRY(weight_grads(l));
+        } else {
+            MARLC_TRY(e->chain(s, s0));
+            for (int l = e->L - 1; l >= 0; --l) {
+                CnnBwdLayerArgs la;
+                memset(&la, 0, sizeof(la));
+                la.cout = d.cout[l]; la.ho = d.hout[l]; la.groups = d.groups[l]; la.P = TM;
+                la.Y = ysave[l]; la.gn_w = d.gn_w[l]; la.gn_b = d.gn_b[l];
+                const bool top = (l == e->L - 1);
+                la.dOut = top ? dU : nullptr; la.lddo = Kin;
+                la.dColNext = top ? nullptr : dcol[l + 1];
+                la.ho_next = top ? 1 : d.hout[l + 1];
+                la.dY = bb.dY[l]; la.gnpart = bb.gnpart[l];
+                la.colNext = top ? nullptr : bb.col[l + 1];
+                MARLC_TRY(cnn_bwd_layer(la, s0));
+                if (!top) MARLC_TRY(weight_grads(l + 1));  // col_{l+1} is now available
+                if (l > 0) {
+                    const int npos = d.hout[l] * d.hout[l], kk = d.cin[l] * 9;
+                    MARLC_TRY(G_nn_on(e, bb.dY[l], d.cout[l], d.w[l], kk, dcol[l], kk, TM * npos, d.cout[l], kk, s0));
+                }
+            }
+            MARLC_TRY(cnn_im2col_input(img, e->buf<int>("pos_hist"), bb.col[0], TM, M, c.nb, c.C, d.cin[0], c.H, c.W,
+                                       c.f, d.hout[0], s0));
+            MARLC_TRY(weight_grads(0));
         }
     }
     if (par) {  // join

@@ -77,6 +77,25 @@ struct CnnBwdBuffers {
 int cnn_bwd(const CnnDesc& d, const float* img, const int* pos_hist, int B, int H, int W, int M, int p0, int P,
             const float* const* y_save, const float* dOut, long lddo, const CnnBwdBuffers& buf, cudaStream_t s);
 
+// ---- cnn_bwd2.cu: layer-wise, batched backward (conv products on the tensor cores) ------------
+struct CnnBwdLayerArgs {
+    int cout, ho, groups;   // this layer's output is [cout][ho*ho] per window
+    int P;                  // number of windows (T*M)
+    const float* Y;         // [P, cout*ho*ho] saved pre-norm conv outputs
+    const float* gn_w;      // GroupNorm affine
+    const float* gn_b;
+    const float* dOut;      // top layer: gradient rows [P, lddo] in (c, pos) order; else nullptr
+    long lddo;
+    const float* dColNext;  // other layers: dCol of layer l+1, [P*ho_next^2, cout*9]
+    int ho_next;
+    float* dY;              // out [P*ho*ho, cout]
+    float* gnpart;          // out [P, 2*cout]
+    float* colNext;         // out im2col of this layer's activation for layer l+1 (nullptr for the top layer)
+};
+int cnn_bwd_layer(const CnnBwdLayerArgs& a, cudaStream_t s);
+int cnn_im2col_input(const float* img, const int* pos_hist, float* col, int P, int M, int B, int img_c, int cin, int H,
+                     int W, int f, int ho, cudaStream_t s);
+
 // ---- loss.cu ------------------------------------------------------------------
 struct LossArgs {
     const float* preds;   // [T,Na,Nb,Nc]
