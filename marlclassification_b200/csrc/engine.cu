@@ -230,6 +230,8 @@ extern "C" int marlc_engine_create(const marlc_config* c, marlc_engine** out) {
     e->add_buf("d_pol_logits", TM * c->n_actions * F4);
     e->add_buf("scratchS", TM * nl_max * F4);
     e->add_buf("scratchY", TM * nl_max * F4);
+    e->add_buf("scratchS2", TM * nl_max * F4);  // second pair: the prediction head runs on a side stream
+    e->add_buf("scratchY2", TM * nl_max * F4);
     e->add_buf("dH_heads", TM * c->n_b * F4);
     e->add_buf("dHc_heads", TM * c->n_a * F4);
     e->add_buf("dgates_b", TM * 4 * c->n_b * F4);
@@ -567,14 +569,17 @@ static int step_act(marlc_engine* e, int t, const int64_t* act_in, cudaStream_t 
 static int value_pred_heads(marlc_engine* e, int R, cudaStream_t s) {
     const marlc_config& c = e->cfg;
     const int M = e->M;
+    cudaStream_t sc = c.use_chains ? e->side[0] : s;  // critic head concurrently with the prediction head
+    if (c.use_chains) MARLC_TRY(e->chain(s, sc));
     MARLC_TRY(block_fwd(e, "critic", 0, e->buf("Hc") + (size_t)M * c.n_a, c.n_a, R, c.n_a, c.nl_a, e->buf("cri_y1"),
-                        e->buf("cri_s1"), c.nl_a, s));
+                        e->buf("cri_s1"), c.nl_a, sc));
     MARLC_TRY(gemm_nt(e->buf("cri_s1"), c.nl_a, e->prm("critic.3.weight"), c.nl_a, e->prm("critic.3.bias"),
-                      e->buf("step_values"), 1, R, 1, c.nl_a, 0, s));
+                      e->buf("step_values"), 1, R, 1, c.nl_a, 0, sc));
     MARLC_TRY(block_fwd(e, "predict", 0, e->buf("H") + (size_t)M * c.n_b, c.n_b, R, c.n_b, c.nl_b, e->buf("prd_y1"),
                         e->buf("prd_s1"), c.nl_b, s));
     MARLC_TRY(G_nt(e, e->buf("prd_s1"), c.nl_b, e->prm("predict.3.weight"), c.nl_b, e->prm("predict.3.bias"),
                    e->buf("step_preds"), c.nb_class, R, c.nb_class, c.nl_b, 0, s));
+    if (c.use_chains) MARLC_TRY(e->chain(sc, s));
     return 0;
 }
 
@@ -688,10 +693,10 @@ static int block_bwd_norm(marlc_engine* e, const std::string& name, int i, const
 // Head backward, batched over all T*M rows: final Linear (N outputs) <- Linear->LN->SiLU <- state
 static int head_bwd(marlc_engine* e, const std::string& name, const float* dOut, int N, const float* s1,
                     const float* y1, const float* state, int n_state, int nl, float* dState, int accumulate_state,
-                    cudaStream_t s) {
+                    cudaStream_t s, int scratch = 0) {
     const int TM = e->TM;
-    float* S = e->buf("scratchS");
-    float* Y = e->buf("scratchY");
+    float* S = e->buf(scratch ? "scratchS2" : "scratchS");
+    float* Y = e->buf(scratch ? "scratchY2" : "scratchY");
     MARLC_TRY(colsum_add(dOut, N, e->grd(name + ".3.bias"), TM, N, s));
     MARLC_TRY(G_tn(e, dOut, N, s1, nl, e->grd(name + ".3.weight"), nl, TM, N, nl, s));
     MARLC_TRY(G_nn(e, dOut, N, e->prm(name + ".3.weight"), nl, S, nl, TM, N, nl, 0, s));
@@ -717,14 +722,18 @@ extern "C" int marlc_episode_backward(marlc_engine* e, const float* img, int acc
     float* dU = e->buf("dU");
 
     // ---- heads, batched over T*M rows (their gradients do not depend on the sweep)
+    // (prediction head on a side stream, policy + critic heads on the main one)
+    cudaStream_t sh = c.use_chains ? e->side[0] : s;
+    if (c.use_chains) MARLC_TRY(e->chain(s, sh));
     MARLC_TRY(head_bwd(e, "predict", e->buf("d_preds"), c.nb_class, e->buf("prd_s1"), e->buf("prd_y1"),
-                       H + (size_t)M * c.n_b, c.n_b, c.nl_b, e->buf("dH_heads"), 0, s));
+                       H + (size_t)M * c.n_b, c.n_b, c.nl_b, e->buf("dH_heads"), 0, sh, 1));
     MARLC_TRY(policy_logit_grad(e->buf("d_logp"), e->buf("probs"), e->buf<int>("act"), e->buf("d_pol_logits"), TM,
                                 c.n_actions, s));
     MARLC_TRY(head_bwd(e, "policy", e->buf("d_pol_logits"), c.n_actions, e->buf("pol_s1"), e->buf("pol_y1"),
                        Hc + (size_t)M * c.n_a, c.n_a, c.nl_a, e->buf("dHc_heads"), 0, s));
     MARLC_TRY(head_bwd(e, "critic", e->buf("d_values"), 1, e->buf("cri_s1"), e->buf("cri_y1"), Hc + (size_t)M * c.n_a,
                        c.n_a, c.nl_a, e->buf("dHc_heads"), 1, s));
+    if (c.use_chains) MARLC_TRY(e->chain(sh, s));
 
     if (e->debug_stop == 1) { e->last_launches = g_launch_count - start; return 0; }
     // ---- BPTT sweep
