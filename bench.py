@@ -165,6 +165,7 @@ def main() -> None:
     ap.add_argument("--fp32", action="store_true", help="exact-fp32 FFMA GEMMs instead of tcgen05 TF32")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true", help="skip the micro-benchmarks (profiling runs)")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
@@ -289,12 +290,13 @@ def main() -> None:
                 "e2e": {"value": e2e_val, "unit": "image-episodes/s", "ms_per_step": e2e_ms,
                         "h2d_bytes_per_step": batch_bytes + nb * 8, "d2h_bytes_per_step": 20},
                 "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches, "clocks": clk}
-        try:
-            from bench_roofline import roofline_for
+        if not args.no_roofline:
+            try:
+                from bench_roofline import roofline_for
 
-            line["roofline"] = roofline_for(model, w, nb, dev)
-        except Exception as exc:  # keep the headline even if the micro-benchmark breaks
-            line["roofline"] = {"error": repr(exc)}
+                line["roofline"] = roofline_for(model, w, nb, dev)
+            except Exception as exc:  # keep the headline even if the micro-benchmark breaks
+                line["roofline"] = {"error": repr(exc)}
         if world == 1 and not args.no_cpu_baseline:
             dt, iters, threads = time_cpu_port(w, w["B"], budget_s=args.cpu_budget, max_iters=20)
             line["cpu_baseline"] = {"value": w["B"] / dt, "unit": "image-episodes/s", "cores": threads, "kind": "port",
