@@ -72,7 +72,7 @@ def tf32_cublas_peak(dev) -> float:
         torch.backends.cuda.matmul.allow_tf32 = old
 
 
-def lstm_pair(M: int, Kin: int, n: int, dev, reps: int = 200) -> dict:
+def lstm_pair(M: int, Kin: int, n: int, dev, reps: int = 200, x3: int = 1) -> dict:
     """The fused LSTM kernel (both cells, gate GEMMs on tcgen05 + cell epilogue)."""
     from marlclassification_b200 import _lib
 
@@ -86,7 +86,7 @@ def lstm_pair(M: int, Kin: int, n: int, dev, reps: int = 200) -> dict:
     cn, hn = [torch.empty(M, n, device=dev) for _ in range(2)], [torch.empty(M, n, device=dev) for _ in range(2)]
     gates = [torch.empty(M, 4 * n, device=dev) for _ in range(2)]
     arr = lambda ts: (ct.c_void_p * 2)(*[t.data_ptr() for t in ts])  # noqa: E731
-    args = (u.data_ptr(), M, Kin, n, arr(hp), arr(cp), arr(wih), arr(whh), arr(bih), arr(bhh), arr(cn), arr(hn), arr(gates))
+    args = (u.data_ptr(), M, Kin, n, arr(hp), arr(cp), arr(wih), arr(whh), arr(bih), arr(bhh), arr(cn), arr(hn), arr(gates), x3)
 
     def run():
         _lib.check(L.marlc_tc_lstm_pair(*args, _lib.stream_ptr(dev)))

@@ -54,10 +54,11 @@ int marlc_msg_mean(const float* msg, float* out, int Na, int Nb, int n, void* st
  * K-major operand: [M|N rows][K contiguous]; MN-major (a_mn/b_mn != 0): [K rows][M|N
  * contiguous].  Pointers 16-byte aligned, leading dimensions multiples of 4.  This is
  * the kernel behind nn.Linear / nn.LSTMCell forward (recurrent.py:30) and their
- * input / weight gradients. */
+ * input / weight gradients.  x3 != 0: error-compensated 3xTF32 (operands split into hi + lo
+ * tiles in shared memory, three MMAs per K step): fp32-class accuracy. */
 int marlc_tc_gemm(const float* A, int64_t lda, int a_mn, const float* B, int64_t ldb, int b_mn, const float* A2,
                   int64_t lda2, const float* B2, int64_t ldb2, int K2, const float* bias, float* C, int64_t ldc,
-                  int M, int N, int K, int accumulate, int allow_split, void* stream);
+                  int M, int N, int K, int accumulate, int allow_split, int x3, void* stream);
 
 /* Both LSTM cells of one step (belief + action, models.py:107-123; nn.LSTMCell,
  * recurrent.py:30) in ONE tcgen05 launch with the cell non-linearities fused into the
@@ -68,7 +69,7 @@ int marlc_tc_gemm(const float* A, int64_t lda, int a_mn, const float* B, int64_t
 int marlc_tc_lstm_pair(const float* u, int M, int Kin, int n, const float* const* h_prev, const float* const* c_prev,
                        const float* const* w_ih, const float* const* w_hh, const float* const* b_ih,
                        const float* const* b_hh, float* const* c_new, float* const* h_new, float* const* gates,
-                       void* stream);
+                       int x3, void* stream);
 
 /* _Generic2dCnnModule.forward, vision.py:47-49: k x [conv3x3 s2 p1 -> GroupNorm ->
  * SiLU] -> flatten on N stand-alone windows patch f32[N,img_c,f,f] (the first
@@ -91,7 +92,8 @@ typedef struct marlc_config {
     /* widths (models.py:37-76) */
     int n_b, n_a, n_m, n_m_o, n_d, nl_b, nl_a, nb_class;
     float gamma;     /* trainer.py:35 */
-    int use_tc;      /* 1: tcgen05 TF32 GEMMs where shapes allow, 0: exact fp32 FFMA everywhere */
+    int use_tc;      /* GEMM arithmetic: 0 = exact fp32 FFMA everywhere; 1 = tcgen05 TF32; 2 = tcgen05 3xTF32
+                        (error-compensated, fp32-class accuracy) where shapes allow */
     int use_chains;  /* 1: fused per-step chain kernels (4 launches fwd / 3 bwd per step), 0: one kernel per op */
 } marlc_config;
 

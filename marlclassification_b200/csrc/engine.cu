@@ -327,6 +327,7 @@ extern "C" int marlc_engine_seed(marlc_engine* e, uint64_t seed, void* stream) {
 
 
 // ---- GEMM dispatch: tcgen05 TF32 when enabled and TMA-addressable, else exact fp32 FFMA ----------
+static inline int x3_of(const marlc_engine* e) { return e->cfg.use_tc == 2 ? 1 : 0; }
 static bool tc_worth(int m_out, int n_out, int k_red) { return n_out >= 16 && k_red >= 32 && m_out >= 1; }
 
 // Y[M,N] = X[M,K] W[N,K]^T + bias
@@ -336,6 +337,7 @@ static int G_nt(const marlc_engine* e, const float* X, long ldx, const float* W,
         TcGemmArgs a;
         a.A = tc_op(X, ldx); a.B = tc_op(W, ldw); a.K = K;
         a.C = Y; a.ldc = ldy; a.M = M; a.N = N; a.bias = bias; a.accumulate = accumulate;
+        a.x3 = x3_of(e);
         if (tc_operand_ok(a.A) && tc_operand_ok(a.B)) return tc_gemm(a, s);
     }
     return gemm_nt(X, ldx, W, ldw, bias, Y, ldy, M, N, K, accumulate, s);
@@ -347,6 +349,7 @@ static int G_nn(const marlc_engine* e, const float* dY, long lddy, const float* 
         TcGemmArgs a;
         a.A = tc_op(dY, lddy); a.B = tc_op(W, ldw, true); a.K = N;
         a.C = dX; a.ldc = lddx; a.M = M; a.N = K; a.accumulate = accumulate;
+        a.x3 = x3_of(e);
         a.allow_split = accumulate ? 0 : 1;
         if (tc_operand_ok(a.A) && tc_operand_ok(a.B)) return tc_gemm(a, s);
     }
@@ -363,6 +366,7 @@ static int G_tn(const marlc_engine* e, const float* dY, long lddy, const float* 
         TcGemmArgs a;
         a.A = tc_op(dY, lddy, true); a.B = tc_op(X, ldx, true); a.K = R;
         a.C = dW; a.ldc = lddw; a.M = N; a.N = K; a.accumulate = 1;
+        a.x3 = x3_of(e);
         a.allow_split = 1;
         if (tc_operand_ok(a.A) && tc_operand_ok(a.B)) return tc_gemm(a, s);
     }
@@ -461,6 +465,7 @@ static int step_networks(marlc_engine* e, int t, const float* img, const int* po
             a.h_new = (k ? Hc : H) + (size_t)(t + 1) * M * n;
             a.gates = k ? ga : gb;
             a.M = M; a.Kin = Kin; a.n = n;
+            a.x3 = x3_of(e);
         }
         if (tc_lstm_supported(la[0]) && tc_lstm_supported(la[1])) {
             MARLC_TRY(tc_lstm_pair(la[0], la[1], s));
@@ -500,6 +505,7 @@ static int step_networks(marlc_engine* e, int t, const float* img, const int* po
             g[0].C = enc_y1; g[0].ldc = 2 * c.n_m; g[0].M = M; g[0].N = 2 * c.n_m; g[0].bias = e->prm("encode_msg.0.bias");
             g[1].A = tc_op(pol_x, c.n_a); g[1].B = tc_op(e->prm("policy.0.weight"), c.n_a); g[1].K = c.n_a;
             g[1].C = pol_y1; g[1].ldc = c.nl_a; g[1].M = M; g[1].N = c.nl_a; g[1].bias = e->prm("policy.0.bias");
+            g[0].x3 = g[1].x3 = x3_of(e);
             if (tc_operand_ok(g[0].A) && tc_operand_ok(g[0].B) && tc_operand_ok(g[1].A) && tc_operand_ok(g[1].B)) {
                 MARLC_TRY(tc_gemm_group(g, 2, s));
                 grouped = true;
@@ -803,7 +809,7 @@ extern "C" int marlc_episode_backward(marlc_engine* e, const float* img, int acc
                 g[2].C = dhc_t; g[2].ldc = c.n_a; g[2].M = M; g[2].N = c.n_a;
                 bool ok = true;
                 for (int q = 0; q < 3; ++q) {
-                    g[q].allow_split = 1; g[q].c_zeroed = 1;
+                    g[q].allow_split = 1; g[q].c_zeroed = 1; g[q].x3 = x3_of(e);
                     ok = ok && tc_operand_ok(g[q].A) && tc_operand_ok(g[q].B);
                 }
                 ok = ok && tc_operand_ok(g[0].A2) && tc_operand_ok(g[0].B2);
@@ -892,6 +898,7 @@ extern "C" int marlc_episode_backward(marlc_engine* e, const float* img, int acc
             TcGemmArgs d;
             d.A = tc_op(dga, 4 * c.n_a); d.B = tc_op(e->prm(std::string(LSTM_A) + "weight_hh"), c.n_a, true); d.K = 4 * c.n_a;
             d.C = dhc; d.ldc = c.n_a; d.M = M; d.N = c.n_a; d.allow_split = 1;
+            a.x3 = b.x3 = d.x3 = x3_of(e);
             if (tc_operand_ok(a.A) && tc_operand_ok(a.B) && tc_operand_ok(a.A2) && tc_operand_ok(a.B2) &&
                 tc_operand_ok(b.B) && tc_operand_ok(d.B) && c.n_a >= 16 && c.n_b >= 16) {
                 MARLC_TRY(tc_gemm(a, s));
@@ -1089,8 +1096,9 @@ extern "C" int marlc_cnn_forward(int layers, const int* cin, const int* cout, co
 // a_mn / b_mn select MN-major operands ([K rows][M|N contiguous]) instead of K-major.
 extern "C" int marlc_tc_gemm(const float* A, int64_t lda, int a_mn, const float* B, int64_t ldb, int b_mn,
                              const float* A2, int64_t lda2, const float* B2, int64_t ldb2, int K2, const float* bias,
-                             float* C, int64_t ldc, int M, int N, int K, int accumulate, int allow_split, void* stream) {
+                             float* C, int64_t ldc, int M, int N, int K, int accumulate, int allow_split, int x3, void* stream) {
     TcGemmArgs a;
+    a.x3 = x3;
     a.A = tc_op(A, lda, a_mn != 0); a.B = tc_op(B, ldb, b_mn != 0); a.K = K;
     if (K2 > 0) { a.A2 = tc_op(A2, lda2, a_mn != 0); a.B2 = tc_op(B2, ldb2, b_mn != 0); a.K2 = K2; }
     a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.bias = bias; a.accumulate = accumulate; a.allow_split = allow_split;
@@ -1104,14 +1112,14 @@ extern "C" int marlc_tc_gemm(const float* A, int64_t lda, int a_mn, const float*
 extern "C" int marlc_tc_lstm_pair(const float* u, int M, int Kin, int n, const float* const* h_prev,
                                   const float* const* c_prev, const float* const* w_ih, const float* const* w_hh,
                                   const float* const* b_ih, const float* const* b_hh, float* const* c_new,
-                                  float* const* h_new, float* const* gates, void* stream) {
+                                  float* const* h_new, float* const* gates, int x3, void* stream) {
     TcLstmArgs la[2];
     for (int k = 0; k < 2; ++k) {
         TcLstmArgs& a = la[k];
         a.U = tc_op(u, Kin); a.Hprev = tc_op(h_prev[k], n);
         a.Wih = w_ih[k]; a.Whh = w_hh[k]; a.bih = b_ih[k]; a.bhh = b_hh[k];
         a.c_prev = c_prev[k]; a.c_new = c_new[k]; a.h_new = h_new[k]; a.gates = gates[k];
-        a.M = M; a.Kin = Kin; a.n = n;
+        a.M = M; a.Kin = Kin; a.n = n; a.x3 = x3;
     }
     return tc_lstm_pair(la[0], la[1], (cudaStream_t)stream);
 }

@@ -165,28 +165,36 @@ struct TcKernelGroup {  // up to 3 independent problems in one launch; blockIdx.
     int count;
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool X3 = false>
 struct TcSmem {
     static constexpr int A_BYTES = BM * BK * 4;
     static constexpr int B_BYTES = BN * BK * 4;
-    static constexpr int BYTES = STAGES * (A_BYTES + B_BYTES) + 1024;
-    static constexpr int bytes(int stages) { return stages * (A_BYTES + B_BYTES) + 1024; }
+    // X3 (error-compensated 3xTF32): every stage also holds the low-order tiles A_lo, B_lo
+    static constexpr int BYTES = STAGES * (A_BYTES + B_BYTES) * (X3 ? 2 : 1) + 1024;
 };
 
 
 // The body is instantiated once per problem slot so that every access to the kernel parameters
 // (in particular the TMA descriptors) uses a compile-time offset: indexing the parameter block
 // with a runtime problem index costs ~2 us per launch on B200 (measured).
-template <int BN, bool A_MN, bool B_MN, int EPI, int STAGES, int PI>
+//
+// X3 = error-compensated "3xTF32": tcgen05 kind::tf32 truncates each fp32 operand to 10 mantissa
+// bits.  The 4 epilogue warps, idle during the main loop, split every landed stage into
+// hi = trunc(x) (what the tensor core sees of the original tile) and lo = x - hi (written to a
+// mirror tile with the same swizzled layout), and the MMA warp issues A.B + A_lo.B + A.B_lo:
+// products keep ~21 mantissa bits, i.e. fp32-class accuracy at 1/3 of the TF32 MMA rate.
+template <int BN, bool A_MN, bool B_MN, int EPI, int STAGES, int PI, bool X3>
 __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int split) {
-    using S = TcSmem<BN, STAGES>;
+    using S = TcSmem<BN, STAGES, X3>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     constexpr int stages = STAGES;  // (a runtime ring depth of 2..8 made no measurable difference)
     uint8_t* sA = smem;
     uint8_t* sB = smem + stages * S::A_BYTES;
+    constexpr int LO_OFF = stages * (S::A_BYTES + S::B_BYTES);  // lo tiles mirror the hi ring at this offset
     __shared__ __align__(8) uint64_t full_bar[STAGES];
     __shared__ __align__(8) uint64_t empty_bar[STAGES];
+    __shared__ __align__(8) uint64_t split_bar[STAGES];
     __shared__ __align__(8) uint64_t tmem_full_bar;
     __shared__ uint32_t tmem_base_smem;
 
@@ -207,7 +215,10 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
     constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1);
+            mbar_init(&split_bar[s], 128);  // the 4 splitter warps
+        }
         mbar_init(&tmem_full_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -259,7 +270,7 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
                                    ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
             for (int i = 0; i < my_kb; ++i) {
                 const int s = i % stages, ph = (i / stages) & 1;
-                mbar_wait(&full_bar[s], ph);
+                mbar_wait(X3 ? &split_bar[s] : &full_bar[s], ph);
                 tc_fence_after();
                 const uint32_t a_addr = smem_u32(sA + s * S::A_BYTES), b_addr = smem_u32(sB + s * S::B_BYTES);
 #pragma unroll
@@ -270,6 +281,11 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
                     const uint64_t ad = A_MN ? make_desc(a_addr + k * 1024, 4096, 512, 1) : make_desc(a_addr + k * 32, 16, 1024, 2);
                     const uint64_t bd = B_MN ? make_desc(b_addr + k * 1024, 4096, 512, 1) : make_desc(b_addr + k * 32, 16, 1024, 2);
                     umma_tf32(tmem_base, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                    if (X3) {  // descriptors of the lo tiles: same layout, start address + LO_OFF
+                        const uint64_t lo = (uint64_t)((LO_OFF >> 4) & 0x3FFF);
+                        umma_tf32(tmem_base, ad + lo, bd, idesc, 1u);
+                        umma_tf32(tmem_base, ad, bd + lo, idesc, 1u);
+                    }
                 }
                 umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs retire
             }
@@ -279,6 +295,33 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
         // ============================ epilogue (warps 2..5) ============================
         const int q = warp & 3;  // TMEM lane quarter this warp may touch
         const int m = m0 + 32 * q + lane;
+        if (X3) {
+            // ---- operand splitter: lo = x - trunc_tf32(x) for every landed stage
+            const int t = threadIdx.x - 64;  // 0..127
+            constexpr int V4 = (S::A_BYTES + S::B_BYTES) / 16;  // float4 per stage (A and B are adjacent per ring? no: separate rings)
+            for (int i = 0; i < my_kb; ++i) {
+                const int s = i % stages, ph = (i / stages) & 1;
+                mbar_wait(&full_bar[s], ph);
+                float4* a_hi = reinterpret_cast<float4*>(sA + s * S::A_BYTES);
+                float4* b_hi = reinterpret_cast<float4*>(sB + s * S::B_BYTES);
+                float4* a_lo = reinterpret_cast<float4*>(sA + s * S::A_BYTES + LO_OFF);
+                float4* b_lo = reinterpret_cast<float4*>(sB + s * S::B_BYTES + LO_OFF);
+                auto lo_of = [](float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); };
+#pragma unroll 4
+                for (int v = t; v < S::A_BYTES / 16; v += 128) {
+                    const float4 x = a_hi[v];
+                    a_lo[v] = make_float4(lo_of(x.x), lo_of(x.y), lo_of(x.z), lo_of(x.w));
+                }
+#pragma unroll 4
+                for (int v = t; v < S::B_BYTES / 16; v += 128) {
+                    const float4 x = b_hi[v];
+                    b_lo[v] = make_float4(lo_of(x.x), lo_of(x.y), lo_of(x.z), lo_of(x.w));
+                }
+                (void)V4;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to UMMA
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&split_bar[s])) : "memory");
+            }
+        }
         mbar_wait(&tmem_full_bar, 0);
         tc_fence_after();
         const uint32_t trow = tmem_base + ((uint32_t)(32 * q) << 16);
@@ -376,12 +419,12 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
     }
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI, int STAGES>
+template <int BN, bool A_MN, bool B_MN, int EPI, int STAGES, bool X3>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_constant__ TcKernelGroup pp) {
     const int z = blockIdx.z;
-    if (pp.count >= 3 && z >= pp.zofs[2]) tc_gemm_body<BN, A_MN, B_MN, EPI, STAGES, 2>(pp, z - pp.zofs[2]);
-    else if (pp.count >= 2 && z >= pp.zofs[1]) tc_gemm_body<BN, A_MN, B_MN, EPI, STAGES, 1>(pp, z - pp.zofs[1]);
-    else tc_gemm_body<BN, A_MN, B_MN, EPI, STAGES, 0>(pp, z);
+    if (pp.count >= 3 && z >= pp.zofs[2]) tc_gemm_body<BN, A_MN, B_MN, EPI, STAGES, 2, X3>(pp, z - pp.zofs[2]);
+    else if (pp.count >= 2 && z >= pp.zofs[1]) tc_gemm_body<BN, A_MN, B_MN, EPI, STAGES, 1, X3>(pp, z - pp.zofs[1]);
+    else tc_gemm_body<BN, A_MN, B_MN, EPI, STAGES, 0, X3>(pp, z);
 }
 
 // ---------------------------------------------------------------------------------
@@ -393,12 +436,12 @@ static int operand_map(CUtensorMap* m, const TcOperand& o, int mn_extent, int k_
     return make_map(m, o.ptr, mn_extent, k_extent, o.slabs, o.ld, o.slab_stride, 32, true);
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool X3>
 static int launch_store(TcKernelGroup& kp, int gx, int gy, int gz, int max_kb, cudaStream_t s) {
     (void)max_kb;
     constexpr int STAGES = BN >= 128 ? 3 : 4;  // <= 96 KB: two CTAs per SM (epilogue / main loop overlap)
-    using S = TcSmem<BN, STAGES>;
-    auto kern = tc_gemm_kernel<BN, A_MN, B_MN, EPI_STORE, STAGES>;
+    using S = TcSmem<BN, STAGES, X3>;
+    auto kern = tc_gemm_kernel<BN, A_MN, B_MN, EPI_STORE, STAGES, X3>;
     static bool attr_done = false;
     if (!attr_done) {
         MARLC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES));
@@ -476,28 +519,33 @@ int tc_gemm_group(const TcGemmArgs* args, int count, cudaStream_t s) {
         max_kb = max(max_kb, (nkb + kp.p[i].splits - 1) / kp.p[i].splits);
     }
     const bool amn = args[0].A.mn_major, bmn = args[0].B.mn_major;
-#define DISPATCH(BNv)                                                                    \
-    if (amn) {                                                                           \
-        if (bmn) return launch_store<BNv, true, true>(kp, gx, gy, gz, max_kb, s);        \
-        return launch_store<BNv, true, false>(kp, gx, gy, gz, max_kb, s);                \
-    } else {                                                                             \
-        if (bmn) return launch_store<BNv, false, true>(kp, gx, gy, gz, max_kb, s);       \
-        return launch_store<BNv, false, false>(kp, gx, gy, gz, max_kb, s);               \
+    const bool x3 = args[0].x3 != 0;
+#define DISPATCH2(BNv, X)                                                                   \
+    if (amn) {                                                                              \
+        if (bmn) return launch_store<BNv, true, true, X>(kp, gx, gy, gz, max_kb, s);        \
+        return launch_store<BNv, true, false, X>(kp, gx, gy, gz, max_kb, s);                \
+    } else {                                                                                \
+        if (bmn) return launch_store<BNv, false, true, X>(kp, gx, gy, gz, max_kb, s);       \
+        return launch_store<BNv, false, false, X>(kp, gx, gy, gz, max_kb, s);               \
     }
+#define DISPATCH(BNv)          \
+    if (x3) { DISPATCH2(BNv, true) } \
+    else { DISPATCH2(BNv, false) }
     if (BN == 32) { DISPATCH(32) }
     if (BN == 64) { DISPATCH(64) }
     DISPATCH(128)
 #undef DISPATCH
+#undef DISPATCH2
 }
 
 int tc_gemm(const TcGemmArgs& a, cudaStream_t s) { return tc_gemm_group(&a, 1, s); }
 
-template <int BN>
+template <int BN, bool X3>
 static int launch_lstm(TcKernelGroup& kp, int gx, int gy, int nkb, cudaStream_t s) {
     (void)nkb;
     constexpr int STAGES = BN >= 128 ? 3 : 4;  // 3 x 32 KB: two CTAs per SM, one's epilogue overlaps the other's main loop
-    using S = TcSmem<BN, STAGES>;
-    auto kern = tc_gemm_kernel<BN, false, false, EPI_LSTM, STAGES>;
+    using S = TcSmem<BN, STAGES, X3>;
+    auto kern = tc_gemm_kernel<BN, false, false, EPI_LSTM, STAGES, X3>;
     static bool attr_done = false;
     if (!attr_done) {
         MARLC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES));
@@ -547,9 +595,14 @@ int tc_lstm_pair(const TcLstmArgs& c0, const TcLstmArgs& c1, cudaStream_t s) {
     }
     MARLC_CHECK(c0.n == c1.n, "tc_lstm_pair: the two cells must have the same hidden size (got %d, %d)", c0.n, c1.n);
     const int nkb = kp.p[0].nk1 + kp.p[0].nk2;
-    if (HU == 8) return launch_lstm<32>(kp, gx, mt, nkb, s);
-    if (HU == 16) return launch_lstm<64>(kp, gx, mt, nkb, s);
-    return launch_lstm<128>(kp, gx, mt, nkb, s);
+    if (c0.x3) {
+        if (HU == 8) return launch_lstm<32, true>(kp, gx, mt, nkb, s);
+        if (HU == 16) return launch_lstm<64, true>(kp, gx, mt, nkb, s);
+        return launch_lstm<128, true>(kp, gx, mt, nkb, s);
+    }
+    if (HU == 8) return launch_lstm<32, false>(kp, gx, mt, nkb, s);
+    if (HU == 16) return launch_lstm<64, false>(kp, gx, mt, nkb, s);
+    return launch_lstm<128, false>(kp, gx, mt, nkb, s);
 }
 
 }  // namespace marlc

@@ -39,6 +39,7 @@ struct TcGemmArgs {
     int accumulate = 0;
     int allow_split = 0;  // split-K with an atomicAdd epilogue when the grid would be small
     int c_zeroed = 0;     // C is known to be zero already: skip the memset a split-K launch needs
+    int x3 = 0;           // error-compensated 3xTF32 (fp32-class accuracy)
 };
 int tc_gemm(const TcGemmArgs& a, cudaStream_t s);
 // up to 3 problems with the same operand majors in ONE launch (blockIdx.z selects problem / K split)
@@ -58,6 +59,7 @@ struct TcLstmArgs {
     float* h_new;
     float* gates;  // [M, 4n]
     int M, Kin, n;
+    int x3 = 0;
 };
 bool tc_lstm_supported(const TcLstmArgs& a);
 int tc_lstm_pair(const TcLstmArgs& belief, const TcLstmArgs& action, cudaStream_t s);

@@ -41,7 +41,9 @@ def build_config(model, *, na: int, nb: int, T: int, C: int, H: int, W: int, act
     cfg.n_b, cfg.n_a, cfg.n_m, cfg.n_m_o, cfg.n_d = d["n_b"], d["n_a"], d["n_m"], d["n_m_o"], d["n_d"]
     cfg.nl_b, cfg.nl_a, cfg.nb_class = d["nl_b"], d["nl_a"], d["nb_class"]
     cfg.gamma = float(gamma)
-    cfg.use_tc = 1 if getattr(model, "use_tc", True) else 0
+    # GEMM arithmetic: "fp32" exact FFMA | "tf32" tcgen05 | "tf32x3" tcgen05, error-compensated
+    prec = getattr(model, "precision", "tf32x3") if getattr(model, "use_tc", True) else "fp32"
+    cfg.use_tc = {"fp32": 0, "tf32": 1, "tf32x3": 2}[prec]
     cfg.use_chains = 1 if getattr(model, "use_chains", True) else 0
     return cfg
 
@@ -194,7 +196,7 @@ def C_void_p():
 def get_engine(model, *, na, nb, T, C, H, W, actions, gamma=0.99) -> EpisodeEngine:
     """Engines are cached on the model per geometry (workspaces are reused across iterations)."""
     model.ensure_flat()
-    key = (na, nb, T, C, H, W, tuple(tuple(a) for a in actions), float(gamma), bool(getattr(model, "use_tc", True)),
+    key = (na, nb, T, C, H, W, tuple(tuple(a) for a in actions), float(gamma), bool(getattr(model, "use_tc", True)), getattr(model, "precision", "tf32x3"),
            bool(getattr(model, "use_chains", True)))
     eng = model._engines.get(key)
     if eng is None:

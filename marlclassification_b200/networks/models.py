@@ -86,7 +86,8 @@ class ModelsWrapper(nn.Module):
         self._flat_params: th.Tensor | None = None
         self._flat_grads: th.Tensor | None = None
         self._engines: dict = {}
-        self.use_tc = True  # tcgen05 TF32 GEMMs where shapes allow; False = exact fp32 everywhere
+        self.use_tc = True  # tensor-core GEMMs where shapes allow; False = exact fp32 FFMA everywhere
+        self.precision = "tf32x3"  # "tf32x3" (error-compensated, fp32-class) | "tf32" (fastest, ~1e-3)
         self.use_chains = True  # fused per-step chain kernels; False = one kernel per op (debug / comparison)
 
     # ---- reference surface ------------------------------------------------------

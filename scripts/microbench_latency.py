@@ -8,6 +8,7 @@ from marlclassification_b200 import _lib
 
 L = _lib.lib()
 dev = "cuda"
+X3 = int(os.environ.get("X3", "0"))
 
 
 def timed_graph(fn, n, reps=20):
@@ -43,12 +44,12 @@ for N in (128, 384):
     print(f"ln_silu_fwd [{M}x{N}]: {timed_graph(lambda: L.marlc_ln_silu(y.data_ptr(), g_.data_ptr(), b_.data_ptr(), o.data_ptr(), M, N, _lib.stream_ptr()), 200):.2f} us")
 for (N, K) in ((128, 64), (128, 256), (384, 256), (1024, 368)):
     A = torch.randn(M, K, device=dev); B = torch.randn(N, K, device=dev); C = torch.empty(M, N, device=dev)
-    f = lambda: L.marlc_tc_gemm(A.data_ptr(), K, 0, B.data_ptr(), K, 0, None, 0, None, 0, 0, None, C.data_ptr(), N, M, N, K, 0, 0, _lib.stream_ptr())
+    f = lambda: L.marlc_tc_gemm(A.data_ptr(), K, 0, B.data_ptr(), K, 0, None, 0, None, 0, 0, None, C.data_ptr(), N, M, N, K, 0, 0, X3, _lib.stream_ptr())
     print(f"tc_gemm NT [{M}x{N}x{K}]: {timed_graph(f, 200):.2f} us")
     f2 = lambda: L.marlc_linear(A.data_ptr(), B.data_ptr(), None, C.data_ptr(), M, N, K, _lib.stream_ptr())
     print(f"simt linear [{M}x{N}x{K}]: {timed_graph(f2, 100):.2f} us")
 for (Mr, N, K) in ((2048, 384, 256), (4096, 1024, 624), (65536, 384, 256)):
     A = torch.randn(Mr, K, device=dev); B = torch.randn(N, K, device=dev); C = torch.empty(Mr, N, device=dev)
-    f = lambda: L.marlc_tc_gemm(A.data_ptr(), K, 0, B.data_ptr(), K, 0, None, 0, None, 0, 0, None, C.data_ptr(), N, Mr, N, K, 0, 0, _lib.stream_ptr())
+    f = lambda: L.marlc_tc_gemm(A.data_ptr(), K, 0, B.data_ptr(), K, 0, None, 0, None, 0, 0, None, C.data_ptr(), N, Mr, N, K, 0, 0, X3, _lib.stream_ptr())
     t = timed_graph(f, 20)
     print(f"tc_gemm NT [{Mr}x{N}x{K}]: {t:.2f} us = {2 * Mr * N * K / t / 1e6:.1f} TFLOP/s")

@@ -18,6 +18,7 @@ model.to(dev)
 for a in sys.argv[3:]:
     if a == "fp32": model.use_tc = False
     if a == "nochains": model.use_chains = False
+    if a == "tf32": model.precision = "tf32"
 sampler = EpisodeSampler(marl, env, w["T"])
 img = torch.rand(nb, w["C"], w["H"], w["W"], device=dev)
 y = torch.randint(w["nc"], (nb,), device=dev)

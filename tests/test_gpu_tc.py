@@ -3,9 +3,11 @@ operand-major combination, ragged edges, split-K, dual operand pairs; and the
 TF32 engine mode (fused LSTM-cell epilogue, tensor-core dX / dW) against the
 fixtures recorded from the reference.
 
-Stated bounds for the TF32 mode (inputs truncated to 10 mantissa bits, fp32
-accumulate): forward outputs rel-L2 <= 5e-3, per-parameter gradients <= 2e-2.
-Inputs that are exactly representable in TF32 must reproduce fp32 to 1e-5.
+Default tensor-core mode = error-compensated 3xTF32 ("tf32x3"): held to the
+north-star fp32 bound, 1e-3 (measured ~1e-5).  Plain TF32 ("tf32", inputs
+truncated to 10 mantissa bits) has the stated looser bound: forward outputs
+rel-L2 <= 5e-3, per-parameter gradients <= 2e-2.  Inputs exactly representable
+in TF32 must reproduce fp32 to 1e-5 in either mode.
 """
 import pytest
 import torch
@@ -16,6 +18,7 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 TF32_FWD_TOL = 5e-3
 TF32_GRAD_TOL = 2e-2
+X3_TOL = 1e-3  # the north-star fp32 bound: the default tensor-core mode (3xTF32) must meet it
 
 
 def tf32_round(x):
@@ -23,7 +26,7 @@ def tf32_round(x):
     return (x.view(torch.int32) & ~0x1FFF).view(torch.float32)
 
 
-def run_tc(A, B, a_mn, b_mn, M, N, K, bias=None, A2=None, B2=None, K2=0, C0=None, accumulate=0, allow_split=0):
+def run_tc(A, B, a_mn, b_mn, M, N, K, bias=None, A2=None, B2=None, K2=0, C0=None, accumulate=0, allow_split=0, x3=0):
     from marlclassification_b200 import _lib
 
     C = torch.zeros(M, N, device=DEV) if C0 is None else C0.clone()
@@ -31,7 +34,7 @@ def run_tc(A, B, a_mn, b_mn, M, N, K, bias=None, A2=None, B2=None, K2=0, C0=None
         A.data_ptr(), A.stride(0), a_mn, B.data_ptr(), B.stride(0), b_mn,
         None if A2 is None else A2.data_ptr(), 0 if A2 is None else A2.stride(0),
         None if B2 is None else B2.data_ptr(), 0 if B2 is None else B2.stride(0), K2,
-        None if bias is None else bias.data_ptr(), C.data_ptr(), C.stride(0), M, N, K, accumulate, allow_split,
+        None if bias is None else bias.data_ptr(), C.data_ptr(), C.stride(0), M, N, K, accumulate, allow_split, x3,
         _lib.stream_ptr()))
     torch.cuda.synchronize()
     return C
@@ -68,6 +71,29 @@ def test_tc_gemm_tf32_error_bound(a_mn, b_mn):
     assert err < 2e-3
 
 
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 256), (200, 96, 160), (128, 1024, 368), (2048, 384, 256)])
+def test_tc_gemm_x3_fp32_class_accuracy(a_mn, b_mn, M, N, K):
+    """Error-compensated 3xTF32: arbitrary fp32 inputs, result within fp32 rounding of fp64."""
+    g = torch.Generator(device=DEV).manual_seed(M + N + K + 2 * a_mn + b_mn)
+    A, B = torch.randn(M, K, device=DEV, generator=g), torch.randn(N, K, device=DEV, generator=g)
+    Am = A.t().contiguous() if a_mn else A
+    Bm = B.t().contiguous() if b_mn else B
+    C = run_tc(Am, Bm, a_mn, b_mn, M, N, K, x3=1)
+    err = rel_l2(C.cpu(), (A.double() @ B.double().t()).cpu())
+    assert err < 5e-6, err
+
+
+def test_tc_gemm_x3_split_k_dual_pair():
+    M, N, K, K2 = 128, 368, 1024, 1024
+    g = torch.Generator(device=DEV).manual_seed(12)
+    A, A2 = torch.randn(M, K, device=DEV, generator=g), torch.randn(M, K2, device=DEV, generator=g)
+    W, W2 = torch.randn(K, N, device=DEV, generator=g), torch.randn(K2, N, device=DEV, generator=g)
+    ref = A.double() @ W.double() + A2.double() @ W2.double()
+    C = run_tc(A, W, 0, 1, M, N, K, A2=A2, B2=W2, K2=K2, allow_split=1, x3=1)
+    assert rel_l2(C.cpu(), ref.cpu()) < 5e-6
+
+
 def test_tc_gemm_split_k_dual_pair_accumulate():
     M, N, K, K2 = 128, 368, 1024, 1024
     g = torch.Generator(device=DEV).manual_seed(11)
@@ -97,18 +123,20 @@ def test_tc_gemm_strided_views():
     from marlclassification_b200 import _lib
 
     _lib.check(_lib.lib().marlc_tc_gemm(A.data_ptr(), 368, 0, B.data_ptr(), K, 0, None, 0, None, 0, 0, None,
-                                        Cv.data_ptr(), 368, M, N, K, 0, 0, _lib.stream_ptr()))
+                                        Cv.data_ptr(), 368, M, N, K, 0, 0, 0, _lib.stream_ptr()))
     torch.cuda.synchronize()
     assert rel_l2(Cv.cpu(), (A.double() @ B.double().t()).cpu()) < 1e-5
     assert Cbig[:, :256].abs().max().item() == 0 and Cbig[:, 256 + N:].abs().max().item() == 0
 
 
+@pytest.mark.parametrize("precision", ["tf32", "tf32x3"])
 @pytest.mark.parametrize("name", ["mnist_ckpt", "resisc_small", "aid_small"])
-def test_tf32_engine_vs_reference(name):
+def test_tf32_engine_vs_reference(name, precision):
     from tests.test_gpu_parity import run_fixture
 
     fx = load_golden(name)
     model, marl, env, sampler, inject = run_fixture(fx, use_tc=True)
+    model.precision = precision
     img = fx["img"].to(DEV)
     eng = sampler.engine_for(img)
     eng.forward(img, **inject)
@@ -119,10 +147,11 @@ def test_tf32_engine_vs_reference(name):
     eng.backward()
     model.attach_grads()
     worst = max(rel_l2(p.grad.cpu(), fx["grads"][k]) for k, p in model.named_parameters() if fx["grads"][k].norm() > 0)
-    print(f"{name} tf32: preds/logp/values rel-L2 = {e[0]:.1e}/{e[1]:.1e}/{e[2]:.1e}, worst grad = {worst:.1e}")
-    assert max(e) < TF32_FWD_TOL
-    assert abs(loss_out[0].item() - fx["logged"]["loss"]) <= TF32_FWD_TOL * abs(fx["logged"]["loss"])
-    assert worst < TF32_GRAD_TOL
+    print(f"{name} {precision}: preds/logp/values rel-L2 = {e[0]:.1e}/{e[1]:.1e}/{e[2]:.1e}, worst grad = {worst:.1e}")
+    fwd_tol, grad_tol = (TF32_FWD_TOL, TF32_GRAD_TOL) if precision == "tf32" else (X3_TOL, X3_TOL)
+    assert max(e) < fwd_tol
+    assert abs(loss_out[0].item() - fx["logged"]["loss"]) <= fwd_tol * abs(fx["logged"]["loss"])
+    assert worst < grad_tol
 
 
 def test_tf32_full_c2_vs_fp32_mode():
@@ -143,8 +172,9 @@ def test_tf32_full_c2_vs_fp32_mode():
     hidden0 = [torch.randn(na, nb, 256, generator=g).to(DEV) for _ in range(4)]
     actions = torch.randint(4, (T, na, nb), generator=g).to(DEV)
     res = {}
-    for use_tc in (False, True):
-        model.use_tc = use_tc
+    for use_tc in (False, True, "tf32"):
+        model.use_tc = bool(use_tc)
+        model.precision = "tf32" if use_tc == "tf32" else "tf32x3"
         sampler = EpisodeSampler(marl, env, T, gamma=0.99)
         eng = sampler.engine_for(img)
         eng.forward(img, pos0, hidden0, actions)
@@ -152,8 +182,9 @@ def test_tf32_full_c2_vs_fp32_mode():
         eng.backward()
         res[use_tc] = (eng.step_preds.clone(), eng.step_values.clone(), loss, model.flat_grads.clone(),
                        eng.step_pos.clone())
-    assert torch.equal(res[True][4], res[False][4])
-    ep, ev = rel_l2(res[True][0].cpu(), res[False][0].cpu()), rel_l2(res[True][1].cpu(), res[False][1].cpu())
-    eg = rel_l2(res[True][3].cpu(), res[False][3].cpu())
-    print(f"c2 tf32 vs fp32: preds {ep:.1e}, values {ev:.1e}, flat grads {eg:.1e}")
-    assert ep < TF32_FWD_TOL and ev < TF32_FWD_TOL and eg < TF32_GRAD_TOL
+    for key, ftol, gtol in ((True, X3_TOL, X3_TOL), ("tf32", TF32_FWD_TOL, TF32_GRAD_TOL)):
+        assert torch.equal(res[key][4], res[False][4])
+        ep, ev = rel_l2(res[key][0].cpu(), res[False][0].cpu()), rel_l2(res[key][1].cpu(), res[False][1].cpu())
+        eg = rel_l2(res[key][3].cpu(), res[False][3].cpu())
+        print(f"c2 {'tf32x3' if key is True else key} vs fp32: preds {ep:.1e}, values {ev:.1e}, flat grads {eg:.1e}")
+        assert ep < ftol and ev < ftol and eg < gtol
