@@ -162,7 +162,9 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--fp32", action="store_true", help="exact-fp32 FFMA GEMMs instead of tcgen05 TF32")
+    ap.add_argument("--fp32", action="store_true", help="exact-fp32 FFMA GEMMs instead of the tensor cores")
+    ap.add_argument("--precision", default="tf32x3", choices=["tf32x3", "tf32"],
+                    help="tensor-core arithmetic: error-compensated 3xTF32 (default, fp32-class parity) or plain TF32")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true", help="skip the micro-benchmarks (profiling runs)")
@@ -217,6 +219,7 @@ def main() -> None:
     torch.manual_seed(0)
     model, marl, env = ModelConfig(**model_config(w)).build_marl(w["na"])
     model.use_tc = not args.fp32
+    model.precision = args.precision
     model.to(dev)
     dp.broadcast_params(model.flat_params)
     sampler = EpisodeSampler(marl, env, w["T"], gamma=0.99)
@@ -286,7 +289,7 @@ def main() -> None:
                 "agent_steps_per_sec": val * w["na"] * w["T"], "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
                 "scaling": "strong" if strong else "weak", "vs_baseline": None,
-                "dtype": "f32" if args.fp32 else "tf32", "data": "synthetic", "config": cfg_out,
+                "dtype": "f32" if args.fp32 else args.precision, "data": "synthetic", "config": cfg_out,
                 "e2e": {"value": e2e_val, "unit": "image-episodes/s", "ms_per_step": e2e_ms,
                         "h2d_bytes_per_step": batch_bytes + nb * 8, "d2h_bytes_per_step": 20},
                 "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches, "clocks": clk}

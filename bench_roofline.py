@@ -128,8 +128,9 @@ def roofline_for(model, w: dict, nb: int, dev) -> dict:
     M = w["na"] * nb
     Kin = model.feature_extractor.out_size + d["n_m_o"] + d["n_d"]
     tf32_peak = tf32_cublas_peak(dev)
-    lstm = lstm_pair(M, Kin, d["n_b"], dev)
-    lstm_big = lstm_pair(4096, Kin, d["n_b"], dev, reps=50)
+    x3 = 1 if getattr(model, "precision", "tf32x3") == "tf32x3" else 0
+    lstm = lstm_pair(M, Kin, d["n_b"], dev, x3=x3)
+    lstm_big = lstm_pair(4096, Kin, d["n_b"], dev, reps=50, x3=x3)
     g_small = gather(w["na"], nb, w["C"], w["H"], w["W"], w["f"], dev)
     g_big = gather(256, 256, w["C"], w["H"], w["W"], w["f"], dev, reps=50)  # 65536 windows: saturating
     traffic = None
@@ -143,6 +144,7 @@ def roofline_for(model, w: dict, nb: int, dev) -> dict:
         "peak_source": "cuBLAS TF32 8192^3 measured in this run (MEASURED_PEAKS.json holds bf16 only: "
                        f"{pk.get('bf16_tflops')} TFLOP/s burst, {src})",
         "launch_us": lstm["us_per_launch"], "flops_per_launch": lstm["flops_per_launch"],
+        "precision": "tf32x3 (3 MMAs per K step; achieved counts ALGORITHMIC flops once)" if x3 else "tf32",
         "note": f"M={M} rows per launch: one 128-row MMA tile, latency-bound (SURVEY 7.3-2); "
                 "the same kernel at M=4096 is listed under 'others'",
         "others": [
