@@ -24,6 +24,8 @@ constexpr int BM = 128;
 constexpr int BK = 32;  // floats = 128 bytes = one swizzle row
 constexpr int UMMA_K = 8;
 constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS_X3 = 320;  // + 4 warps that only split operands (the splitter is throughput-bound)
+constexpr int TC_SPLITTERS = TC_THREADS_X3 - 64;
 
 // ---------------------------------------------------------------------------------
 // host: tensor maps
@@ -217,7 +219,7 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) {
             mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1);
-            mbar_init(&split_bar[s], 128);  // the 4 splitter warps
+            mbar_init(&split_bar[s], TC_SPLITTERS);  // the splitter warps
         }
         mbar_init(&tmem_full_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -297,7 +299,7 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
         const int m = m0 + 32 * q + lane;
         if (X3) {
             // ---- operand splitter: lo = x - trunc_tf32(x) for every landed stage
-            const int t = threadIdx.x - 64;  // 0..127
+            const int t = threadIdx.x - 64;  // 0..TC_SPLITTERS-1
             constexpr int V4 = (S::A_BYTES + S::B_BYTES) / 16;  // float4 per stage (A and B are adjacent per ring? no: separate rings)
             for (int i = 0; i < my_kb; ++i) {
                 const int s = i % stages, ph = (i / stages) & 1;
@@ -308,12 +310,12 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
                 float4* b_lo = reinterpret_cast<float4*>(sB + s * S::B_BYTES + LO_OFF);
                 auto lo_of = [](float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); };
 #pragma unroll 4
-                for (int v = t; v < S::A_BYTES / 16; v += 128) {
+                for (int v = t; v < S::A_BYTES / 16; v += TC_SPLITTERS) {
                     const float4 x = a_hi[v];
                     a_lo[v] = make_float4(lo_of(x.x), lo_of(x.y), lo_of(x.z), lo_of(x.w));
                 }
 #pragma unroll 4
-                for (int v = t; v < S::B_BYTES / 16; v += 128) {
+                for (int v = t; v < S::B_BYTES / 16; v += TC_SPLITTERS) {
                     const float4 x = b_hi[v];
                     b_lo[v] = make_float4(lo_of(x.x), lo_of(x.y), lo_of(x.z), lo_of(x.w));
                 }
@@ -322,6 +324,7 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
                 asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&split_bar[s])) : "memory");
             }
         }
+        if (warp < 6) {  // warps 2..5 own the four TMEM lane quarters
         mbar_wait(&tmem_full_bar, 0);
         tc_fence_after();
         const uint32_t trow = tmem_base + ((uint32_t)(32 * q) << 16);
@@ -410,6 +413,7 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
                 }
             }
         }
+        }  // warp < 6
     }
     tc_fence_before();
     __syncthreads();
@@ -420,7 +424,7 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
 }
 
 template <int BN, bool A_MN, bool B_MN, int EPI, int STAGES, bool X3>
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_constant__ TcKernelGroup pp) {
+__global__ void __launch_bounds__(X3 ? TC_THREADS_X3 : TC_THREADS, 1) tc_gemm_kernel(const __grid_constant__ TcKernelGroup pp) {
     const int z = blockIdx.z;
     if (pp.count >= 3 && z >= pp.zofs[2]) tc_gemm_body<BN, A_MN, B_MN, EPI, STAGES, 2, X3>(pp, z - pp.zofs[2]);
     else if (pp.count >= 2 && z >= pp.zofs[1]) tc_gemm_body<BN, A_MN, B_MN, EPI, STAGES, 1, X3>(pp, z - pp.zofs[1]);
@@ -447,7 +451,7 @@ static int launch_store(TcKernelGroup& kp, int gx, int gy, int gz, int max_kb, c
         MARLC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES));
         attr_done = true;
     }
-    kern<<<dim3(gx, gy, gz), TC_THREADS, S::BYTES, s>>>(kp);
+    kern<<<dim3(gx, gy, gz), X3 ? TC_THREADS_X3 : TC_THREADS, S::BYTES, s>>>(kp);
     MARLC_LAUNCH_CHECK();
     return 0;
 }
@@ -551,7 +555,7 @@ static int launch_lstm(TcKernelGroup& kp, int gx, int gy, int nkb, cudaStream_t 
         MARLC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES));
         attr_done = true;
     }
-    kern<<<dim3(gx, gy, 2), TC_THREADS, S::BYTES, s>>>(kp);
+    kern<<<dim3(gx, gy, 2), X3 ? TC_THREADS_X3 : TC_THREADS, S::BYTES, s>>>(kp);
     MARLC_LAUNCH_CHECK();
     return 0;
 }
