@@ -166,8 +166,9 @@ if __name__ == "__main__":
     pk, src = peaks()
     print("peaks:", pk.get("hbm_gbs"), pk.get("bf16_tflops"), src)
     print("tf32 cuBLAS peak TFLOP/s:", tf32_cublas_peak(dev))
+    x3 = int(os.environ.get("X3", "1"))
     for M in (128, 1024, 4096, 16384):
-        print(json.dumps(lstm_pair(M, 368, 256, dev, reps=50)))
+        print(json.dumps(lstm_pair(M, 368, 256, dev, reps=50, x3=x3)))
     for na, nb in ((16, 8), (64, 64), (256, 256)):
         print(json.dumps(gather(na, nb, 3, 256, 256, 12, dev, reps=50)))
     print(json.dumps(gather(256, 64, 3, 600, 600, 24, dev, reps=50)))

@@ -167,10 +167,15 @@ struct TcKernelGroup {  // up to 3 independent problems in one launch; blockIdx.
     int count;
 };
 
-template <int BN, int STAGES, bool X3 = false>
+// KS = number of 32-float K sub-blocks per pipeline stage.  The single-thread producer / MMA loops
+// pay ~0.15-0.2 us of barrier round trip per stage whatever the ring depth (measured: depth 2..10
+// makes no difference), so latency-bound launches use fat stages (KS = 2 or 4) and a 2-deep ring.
+template <int BN, int STAGES, bool X3 = false, int KS = 1>
 struct TcSmem {
-    static constexpr int A_BYTES = BM * BK * 4;
-    static constexpr int B_BYTES = BN * BK * 4;
+    static constexpr int A_SUB = BM * BK * 4;
+    static constexpr int B_SUB = BN * BK * 4;
+    static constexpr int A_BYTES = KS * A_SUB;
+    static constexpr int B_BYTES = KS * B_SUB;
     // X3 (error-compensated 3xTF32): every stage also holds the low-order tiles A_lo, B_lo
     static constexpr int BYTES = STAGES * (A_BYTES + B_BYTES) * (X3 ? 2 : 1) + 1024;
 };
@@ -185,9 +190,9 @@ struct TcSmem {
 // hi = trunc(x) (what the tensor core sees of the original tile) and lo = x - hi (written to a
 // mirror tile with the same swizzled layout), and the MMA warp issues A.B + A_lo.B + A.B_lo:
 // products keep ~21 mantissa bits, i.e. fp32-class accuracy at 1/3 of the TF32 MMA rate.
-template <int BN, bool A_MN, bool B_MN, int EPI, int STAGES, int PI, bool X3>
+template <int BN, bool A_MN, bool B_MN, int EPI, int STAGES, int PI, bool X3, int KS>
 __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int split) {
-    using S = TcSmem<BN, STAGES, X3>;
+    using S = TcSmem<BN, STAGES, X3, KS>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     constexpr int stages = STAGES;  // (a runtime ring depth of 2..8 made no measurable difference)
@@ -219,7 +224,7 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) {
             mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1);
-            mbar_init(&split_bar[s], TC_SPLITTERS);  // the splitter warps
+            mbar_init(&split_bar[s], TC_SPLITTERS / 2);  // one of the two splitter groups
         }
         mbar_init(&tmem_full_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -243,25 +248,28 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
                 mbar_expect_tx(&full_bar[s], S::A_BYTES + S::B_BYTES);
                 const int kb = kb_begin + i;
                 const bool second = kb >= p.nk1;
-                const int k0 = (second ? kb - p.nk1 : kb) * BK;
                 const CUtensorMap* ma = second ? &p.a2 : &p.a1;
                 const CUtensorMap* mb = second ? &p.b2 : &p.b1;
                 const int za = second ? p.slab_a2 : p.slab_a1, zb = second ? p.slab_b2 : p.slab_b1;
-                uint8_t* a_dst = sA + s * S::A_BYTES;
-                uint8_t* b_dst = sB + s * S::B_BYTES;
-                if (!A_MN) tma_load_3d(a_dst, ma, &full_bar[s], k0, m0, za);
-                else
-                    for (int j = 0; j < BM / 32; ++j) tma_load_3d(a_dst + j * 4096, ma, &full_bar[s], m0 + 32 * j, k0, za);
-                if (EPI == EPI_LSTM) {
-                    // gather the 4 gate row-blocks of HU hidden units: rows g*n + j0 .. +HU
-                    constexpr int HU = BN / 4;
-                    for (int g = 0; g < 4; ++g)
-                        tma_load_3d(b_dst + g * HU * 128, mb, &full_bar[s], k0, g * p.n_hidden + n_tile * HU, zb);
-                } else if (!B_MN) {
-                    tma_load_3d(b_dst, mb, &full_bar[s], k0, n_tile * BN, zb);
-                } else {
-                    for (int j = 0; j < BN / 32; ++j)
-                        tma_load_3d(b_dst + j * 4096, mb, &full_bar[s], n_tile * BN + 32 * j, k0, zb);
+#pragma unroll
+                for (int sub = 0; sub < KS; ++sub) {  // sub-blocks past the end of K are zero-filled by TMA
+                    const int k0 = ((second ? kb - p.nk1 : kb) * KS + sub) * BK;
+                    uint8_t* a_dst = sA + s * S::A_BYTES + sub * S::A_SUB;
+                    uint8_t* b_dst = sB + s * S::B_BYTES + sub * S::B_SUB;
+                    if (!A_MN) tma_load_3d(a_dst, ma, &full_bar[s], k0, m0, za);
+                    else
+                        for (int j = 0; j < BM / 32; ++j) tma_load_3d(a_dst + j * 4096, ma, &full_bar[s], m0 + 32 * j, k0, za);
+                    if (EPI == EPI_LSTM) {
+                        // gather the 4 gate row-blocks of HU hidden units: rows g*n + j0 .. +HU
+                        constexpr int HU = BN / 4;
+                        for (int g = 0; g < 4; ++g)
+                            tma_load_3d(b_dst + g * HU * 128, mb, &full_bar[s], k0, g * p.n_hidden + n_tile * HU, zb);
+                    } else if (!B_MN) {
+                        tma_load_3d(b_dst, mb, &full_bar[s], k0, n_tile * BN, zb);
+                    } else {
+                        for (int j = 0; j < BN / 32; ++j)
+                            tma_load_3d(b_dst + j * 4096, mb, &full_bar[s], n_tile * BN + 32 * j, k0, zb);
+                    }
                 }
             }
         }
@@ -274,7 +282,10 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
                 const int s = i % stages, ph = (i / stages) & 1;
                 mbar_wait(X3 ? &split_bar[s] : &full_bar[s], ph);
                 tc_fence_after();
-                const uint32_t a_addr = smem_u32(sA + s * S::A_BYTES), b_addr = smem_u32(sB + s * S::B_BYTES);
+#pragma unroll
+                for (int sub = 0; sub < KS; ++sub) {
+                const uint32_t a_addr = smem_u32(sA + s * S::A_BYTES + sub * S::A_SUB);
+                const uint32_t b_addr = smem_u32(sB + s * S::B_BYTES + sub * S::B_SUB);
 #pragma unroll
                 for (int k = 0; k < BK / UMMA_K; ++k) {
                     // K-major : advance 32 B inside the swizzled 128 B row; SBO = 1024 (8 rows x 128 B)
@@ -282,12 +293,13 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
                     //           them; LBO = 4096 between the 32-float MN groups (one TMA box each)
                     const uint64_t ad = A_MN ? make_desc(a_addr + k * 1024, 4096, 512, 1) : make_desc(a_addr + k * 32, 16, 1024, 2);
                     const uint64_t bd = B_MN ? make_desc(b_addr + k * 1024, 4096, 512, 1) : make_desc(b_addr + k * 32, 16, 1024, 2);
-                    umma_tf32(tmem_base, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                    umma_tf32(tmem_base, ad, bd, idesc, (i > 0 || k > 0 || sub > 0) ? 1u : 0u);
                     if (X3) {  // descriptors of the lo tiles: same layout, start address + LO_OFF
                         const uint64_t lo = (uint64_t)((LO_OFF >> 4) & 0x3FFF);
                         umma_tf32(tmem_base, ad + lo, bd, idesc, 1u);
                         umma_tf32(tmem_base, ad, bd + lo, idesc, 1u);
                     }
+                }
                 }
                 umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs retire
             }
@@ -299,9 +311,11 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
         const int m = m0 + 32 * q + lane;
         if (X3) {
             // ---- operand splitter: lo = x - trunc_tf32(x) for every landed stage
-            const int t = threadIdx.x - 64;  // 0..TC_SPLITTERS-1
-            constexpr int V4 = (S::A_BYTES + S::B_BYTES) / 16;  // float4 per stage (A and B are adjacent per ring? no: separate rings)
-            for (int i = 0; i < my_kb; ++i) {
+            // two groups of 4 warps take alternate K blocks, so one group's barrier wake-up / proxy
+            // fence / arrive latency overlaps the other group's copy loop
+            constexpr int GRP = TC_SPLITTERS / 2;
+            const int t = (threadIdx.x - 64) % GRP, grp = (threadIdx.x - 64) / GRP;
+            for (int i = grp; i < my_kb; i += 2) {
                 const int s = i % stages, ph = (i / stages) & 1;
                 mbar_wait(&full_bar[s], ph);
                 float4* a_hi = reinterpret_cast<float4*>(sA + s * S::A_BYTES);
@@ -310,16 +324,15 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
                 float4* b_lo = reinterpret_cast<float4*>(sB + s * S::B_BYTES + LO_OFF);
                 auto lo_of = [](float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); };
 #pragma unroll 4
-                for (int v = t; v < S::A_BYTES / 16; v += TC_SPLITTERS) {
+                for (int v = t; v < S::A_BYTES / 16; v += GRP) {
                     const float4 x = a_hi[v];
                     a_lo[v] = make_float4(lo_of(x.x), lo_of(x.y), lo_of(x.z), lo_of(x.w));
                 }
 #pragma unroll 4
-                for (int v = t; v < S::B_BYTES / 16; v += TC_SPLITTERS) {
+                for (int v = t; v < S::B_BYTES / 16; v += GRP) {
                     const float4 x = b_hi[v];
                     b_lo[v] = make_float4(lo_of(x.x), lo_of(x.y), lo_of(x.z), lo_of(x.w));
                 }
-                (void)V4;
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to UMMA
                 asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&split_bar[s])) : "memory");
             }
@@ -423,12 +436,12 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
     }
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI, int STAGES, bool X3>
+template <int BN, bool A_MN, bool B_MN, int EPI, int STAGES, bool X3, int KS>
 __global__ void __launch_bounds__(X3 ? TC_THREADS_X3 : TC_THREADS, 1) tc_gemm_kernel(const __grid_constant__ TcKernelGroup pp) {
     const int z = blockIdx.z;
-    if (pp.count >= 3 && z >= pp.zofs[2]) tc_gemm_body<BN, A_MN, B_MN, EPI, STAGES, 2, X3>(pp, z - pp.zofs[2]);
-    else if (pp.count >= 2 && z >= pp.zofs[1]) tc_gemm_body<BN, A_MN, B_MN, EPI, STAGES, 1, X3>(pp, z - pp.zofs[1]);
-    else tc_gemm_body<BN, A_MN, B_MN, EPI, STAGES, 0, X3>(pp, z);
+    if (pp.count >= 3 && z >= pp.zofs[2]) tc_gemm_body<BN, A_MN, B_MN, EPI, STAGES, 2, X3, KS>(pp, z - pp.zofs[2]);
+    else if (pp.count >= 2 && z >= pp.zofs[1]) tc_gemm_body<BN, A_MN, B_MN, EPI, STAGES, 1, X3, KS>(pp, z - pp.zofs[1]);
+    else tc_gemm_body<BN, A_MN, B_MN, EPI, STAGES, 0, X3, KS>(pp, z);
 }
 
 // ---------------------------------------------------------------------------------
@@ -440,12 +453,14 @@ static int operand_map(CUtensorMap* m, const TcOperand& o, int mn_extent, int k_
     return make_map(m, o.ptr, mn_extent, k_extent, o.slabs, o.ld, o.slab_stride, 32, true);
 }
 
-template <int BN, bool A_MN, bool B_MN, bool X3>
+template <int BN, bool A_MN, bool B_MN, bool X3, int KS>
 static int launch_store(TcKernelGroup& kp, int gx, int gy, int gz, int max_kb, cudaStream_t s) {
     (void)max_kb;
-    constexpr int STAGES = BN >= 128 ? 3 : 4;  // <= 96 KB: two CTAs per SM (epilogue / main loop overlap)
-    using S = TcSmem<BN, STAGES, X3>;
-    auto kern = tc_gemm_kernel<BN, A_MN, B_MN, EPI_STORE, STAGES, X3>;
+    // KS == 1: <= 96 KB per CTA, two CTAs per SM (epilogue / main loop overlap); fat stages: 2-deep ring
+    constexpr int STAGES = KS > 1 ? 2 : (BN >= 128 ? 3 : 4);
+    using S = TcSmem<BN, STAGES, X3, KS>;
+    static_assert(S::BYTES <= 227 * 1024, "tile configuration exceeds shared memory");
+    auto kern = tc_gemm_kernel<BN, A_MN, B_MN, EPI_STORE, STAGES, X3, KS>;
     static bool attr_done = false;
     if (!attr_done) {
         MARLC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES));
@@ -471,11 +486,15 @@ int tc_gemm_group(const TcGemmArgs* args, int count, cudaStream_t s) {
     TcKernelGroup kp;
     memset(&kp, 0, sizeof(kp));
     kp.count = count;
-    int gx = 0, gy = 0, ctas = 0;
+    int gx = 0, gy = 0, ctas = 0, min_k = 1 << 30;
     for (int i = 0; i < count; ++i) {
         const TcGemmArgs& a = args[i];
         ctas += ((a.M + BM - 1) / BM) * ((a.N + BN - 1) / BN);
+        min_k = min(min_k, a.K + a.K2);
     }
+    // fat stages (2 x 32 floats of K per barrier round trip) for latency-bound launches
+    const int KS = (ctas < MARLC_SMS && BN <= 64 && min_k >= 128) ? 2 : 1;
+    const int BKS = BK * KS;
     for (int i = 0; i < count; ++i) {
         const TcGemmArgs& a = args[i];
         MARLC_CHECK(tc_operand_ok(a.A) && tc_operand_ok(a.B), "tc_gemm: operand not TMA-addressable");
@@ -490,12 +509,12 @@ int tc_gemm_group(const TcGemmArgs* args, int count, cudaStream_t s) {
         TcKernelParams& p = kp.p[i];
         MARLC_TRY(operand_map(&p.a1, a.A, a.M, a.K, BM));
         MARLC_TRY(operand_map(&p.b1, a.B, a.N, a.K, BN));
-        p.nk1 = (a.K + BK - 1) / BK;
+        p.nk1 = (a.K + BKS - 1) / BKS;
         p.slab_a1 = a.A.slab; p.slab_b1 = a.B.slab;
         if (pair2) {
             MARLC_TRY(operand_map(&p.a2, a.A2, a.M, a.K2, BM));
             MARLC_TRY(operand_map(&p.b2, a.B2, a.N, a.K2, BN));
-            p.nk2 = (a.K2 + BK - 1) / BK;
+            p.nk2 = (a.K2 + BKS - 1) / BKS;
             p.slab_a2 = a.A2.slab; p.slab_b2 = a.B2.slab;
         }
         p.M = a.M; p.N = a.N; p.C = a.C; p.ldc = a.ldc; p.bias = a.bias; p.bias2 = a.bias2;
@@ -503,7 +522,8 @@ int tc_gemm_group(const TcGemmArgs* args, int count, cudaStream_t s) {
         const int mt = (a.M + BM - 1) / BM, nt = (a.N + BN - 1) / BN, nkb = p.nk1 + p.nk2;
         int splits = 1;
         if (a.allow_split && ctas < MARLC_SMS) {
-            splits = min(max(1, nkb / 4), max(1, (2 * MARLC_SMS) / ctas));
+            splits = min(max(1, nkb * KS / 4), max(1, (2 * MARLC_SMS) / ctas));
+            splits = min(splits, nkb);
             // every split must own at least one K block
             while (splits > 1 && ((nkb + splits - 1) / splits) * (splits - 1) >= nkb) --splits;
         }
@@ -524,32 +544,33 @@ int tc_gemm_group(const TcGemmArgs* args, int count, cudaStream_t s) {
     }
     const bool amn = args[0].A.mn_major, bmn = args[0].B.mn_major;
     const bool x3 = args[0].x3 != 0;
-#define DISPATCH2(BNv, X)                                                                   \
-    if (amn) {                                                                              \
-        if (bmn) return launch_store<BNv, true, true, X>(kp, gx, gy, gz, max_kb, s);        \
-        return launch_store<BNv, true, false, X>(kp, gx, gy, gz, max_kb, s);                \
-    } else {                                                                                \
-        if (bmn) return launch_store<BNv, false, true, X>(kp, gx, gy, gz, max_kb, s);       \
-        return launch_store<BNv, false, false, X>(kp, gx, gy, gz, max_kb, s);               \
+#define DISPATCH3(BNv, X, KSv)                                                                   \
+    if (amn) {                                                                                   \
+        if (bmn) return launch_store<BNv, true, true, X, KSv>(kp, gx, gy, gz, max_kb, s);        \
+        return launch_store<BNv, true, false, X, KSv>(kp, gx, gy, gz, max_kb, s);                \
+    } else {                                                                                     \
+        if (bmn) return launch_store<BNv, false, true, X, KSv>(kp, gx, gy, gz, max_kb, s);       \
+        return launch_store<BNv, false, false, X, KSv>(kp, gx, gy, gz, max_kb, s);               \
     }
-#define DISPATCH(BNv)          \
-    if (x3) { DISPATCH2(BNv, true) } \
-    else { DISPATCH2(BNv, false) }
-    if (BN == 32) { DISPATCH(32) }
-    if (BN == 64) { DISPATCH(64) }
-    DISPATCH(128)
+#define DISPATCH(BNv, KSv)            \
+    if (x3) { DISPATCH3(BNv, true, KSv) } \
+    else { DISPATCH3(BNv, false, KSv) }
+    if (BN == 32) { if (KS == 2) { DISPATCH(32, 2) } DISPATCH(32, 1) }
+    if (BN == 64) { if (KS == 2) { DISPATCH(64, 2) } DISPATCH(64, 1) }
+    DISPATCH(128, 1)
 #undef DISPATCH
-#undef DISPATCH2
+#undef DISPATCH3
 }
 
 int tc_gemm(const TcGemmArgs& a, cudaStream_t s) { return tc_gemm_group(&a, 1, s); }
 
-template <int BN, bool X3>
+template <int BN, bool X3, int KS>
 static int launch_lstm(TcKernelGroup& kp, int gx, int gy, int nkb, cudaStream_t s) {
     (void)nkb;
-    constexpr int STAGES = BN >= 128 ? 3 : 4;  // 3 x 32 KB: two CTAs per SM, one's epilogue overlaps the other's main loop
-    using S = TcSmem<BN, STAGES, X3>;
-    auto kern = tc_gemm_kernel<BN, false, false, EPI_LSTM, STAGES, X3>;
+    constexpr int STAGES = KS > 1 ? 2 : (BN >= 128 ? 3 : 4);  // KS == 1: 3 x 32 KB, two CTAs per SM
+    using S = TcSmem<BN, STAGES, X3, KS>;
+    static_assert(S::BYTES <= 227 * 1024, "tile configuration exceeds shared memory");
+    auto kern = tc_gemm_kernel<BN, false, false, EPI_LSTM, STAGES, X3, KS>;
     static bool attr_done = false;
     if (!attr_done) {
         MARLC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES));
@@ -578,6 +599,10 @@ int tc_lstm_pair(const TcLstmArgs& c0, const TcLstmArgs& c1, cudaStream_t s) {
     memset(&kp, 0, sizeof(kp));
     kp.count = 2;
     kp.zofs[0] = 0; kp.zofs[1] = 1; kp.zofs[2] = 2;
+    // few CTAs (small M): fat stages, KS sub-blocks of 32 floats per barrier round trip
+    const bool fat = HU <= 16 && 2 * mt * (c0.n / HU) <= MARLC_SMS;
+    const int KSv = !fat ? 1 : (c0.x3 ? 2 : (HU == 8 ? 4 : 2));
+    const int BKS = BK * KSv;
     const TcLstmArgs* cs[2] = {&c0, &c1};
     int gx = 0;
     for (int k = 0; k < 2; ++k) {
@@ -587,8 +612,8 @@ int tc_lstm_pair(const TcLstmArgs& c0, const TcLstmArgs& c1, cudaStream_t s) {
         MARLC_TRY(make_map(&p.b1, c.Wih, c.Kin, 4 * c.n, 1, c.Kin, 0, HU));
         MARLC_TRY(make_map(&p.a2, c.Hprev.ptr, c.n, c.M, c.Hprev.slabs, c.Hprev.ld, c.Hprev.slab_stride, BM));
         MARLC_TRY(make_map(&p.b2, c.Whh, c.n, 4 * c.n, 1, c.n, 0, HU));
-        p.nk1 = (c.Kin + BK - 1) / BK;
-        p.nk2 = (c.n + BK - 1) / BK;
+        p.nk1 = (c.Kin + BKS - 1) / BKS;
+        p.nk2 = (c.n + BKS - 1) / BKS;
         p.slab_a1 = c.U.slab; p.slab_a2 = c.Hprev.slab;
         p.M = c.M; p.N = 4 * c.n;
         p.bias = c.bih; p.bias2 = c.bhh;
@@ -599,14 +624,22 @@ int tc_lstm_pair(const TcLstmArgs& c0, const TcLstmArgs& c1, cudaStream_t s) {
     }
     MARLC_CHECK(c0.n == c1.n, "tc_lstm_pair: the two cells must have the same hidden size (got %d, %d)", c0.n, c1.n);
     const int nkb = kp.p[0].nk1 + kp.p[0].nk2;
-    if (c0.x3) {
-        if (HU == 8) return launch_lstm<32, true>(kp, gx, mt, nkb, s);
-        if (HU == 16) return launch_lstm<64, true>(kp, gx, mt, nkb, s);
-        return launch_lstm<128, true>(kp, gx, mt, nkb, s);
+    if (fat) {  // latency-bound (few CTAs): fat stages
+        if (c0.x3) {
+            if (HU == 8) return launch_lstm<32, true, 2>(kp, gx, mt, nkb, s);
+            return launch_lstm<64, true, 2>(kp, gx, mt, nkb, s);
+        }
+        if (HU == 8) return launch_lstm<32, false, 4>(kp, gx, mt, nkb, s);
+        return launch_lstm<64, false, 2>(kp, gx, mt, nkb, s);
     }
-    if (HU == 8) return launch_lstm<32, false>(kp, gx, mt, nkb, s);
-    if (HU == 16) return launch_lstm<64, false>(kp, gx, mt, nkb, s);
-    return launch_lstm<128, false>(kp, gx, mt, nkb, s);
+    if (c0.x3) {
+        if (HU == 8) return launch_lstm<32, true, 1>(kp, gx, mt, nkb, s);
+        if (HU == 16) return launch_lstm<64, true, 1>(kp, gx, mt, nkb, s);
+        return launch_lstm<128, true, 1>(kp, gx, mt, nkb, s);
+    }
+    if (HU == 8) return launch_lstm<32, false, 1>(kp, gx, mt, nkb, s);
+    if (HU == 16) return launch_lstm<64, false, 1>(kp, gx, mt, nkb, s);
+    return launch_lstm<128, false, 1>(kp, gx, mt, nkb, s);
 }
 
 }  // namespace marlc
