@@ -37,6 +37,39 @@ __device__ __forceinline__ void cnn_fwd_block(const CnnFwdArgs& a, const int m, 
     const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
     const int f = d.f, ff = f * f;
 
+    // ---- weight prefetch: if every layer's weights fit in the staging buffer together, ALL of them
+    //      are requested now with cp.async (one commit group per layer) and stream in while the
+    //      window is gathered and the earlier layers compute; otherwise layers are staged one by
+    //      one (synchronously, in output-channel chunks) right before use.
+    int woff[MAX_CNN_LAYERS];
+    bool prefetched;
+    {
+        int tot = 0;
+        for (int l = 0; l < d.L; ++l) { woff[l] = tot; tot += d.cout[l] * (((d.cin[l] * 9 + 3) & ~3) + 4); }
+        prefetched = tot <= a.wbuf;
+        if (prefetched) {
+            for (int l = 0; l < d.L; ++l) {
+                const int wrow = d.cin[l] * 9, Pp = ((wrow + 3) & ~3) + 4, rows = d.cout[l];
+                const float* __restrict__ w = d.w[l];
+                float* dst = ws + woff[l];
+                if ((wrow & 3) == 0 && ((reinterpret_cast<uintptr_t>(w) & 15) == 0)) {
+                    const int w4 = wrow >> 2;
+                    for (int i = tid; i < rows * w4; i += nt) {
+                        const int r = i / w4, c4 = i - r * w4;
+                        const uint32_t da = (uint32_t)__cvta_generic_to_shared(dst + r * Pp + 4 * c4);
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(da), "l"(w + (long)r * wrow + 4 * c4) : "memory");
+                    }
+                } else {
+                    for (int i = tid; i < rows * wrow; i += nt) {
+                        const int r = i / wrow, c1 = i - r * wrow;
+                        const uint32_t da = (uint32_t)__cvta_generic_to_shared(dst + r * Pp + c1);
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(da), "l"(w + i) : "memory");
+                    }
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            }
+        }
+    }
     // ---- load the window into the zero-bordered buffer (gather fused; MnistCnn keeps channel 0
     //      only: cin[0] < img_c)
     {
@@ -64,8 +97,19 @@ __device__ __forceinline__ void cnn_fwd_block(const CnnFwdArgs& a, const int m, 
     for (int l = 0; l < d.L; ++l) {
         const int ci_n = d.cin[l], co_n = d.cout[l], hi = d.hin[l], ho = d.hout[l];
         const int hp = hi + 2, hp2 = hp * hp, npos = ho * ho, total = co_n * npos;
-        const int wrow = ci_n * 9, P = cnn_wpitch(wrow);
-        const int cc = min(co_n, a.wbuf / P);
+        const int wrow = ci_n * 9, P = prefetched ? ((wrow + 3) & ~3) + 4 : cnn_wpitch(wrow);
+        const int cc = prefetched ? co_n : min(co_n, a.wbuf / P);
+        const float* wl_s = prefetched ? ws + woff[l] : ws;
+        if (prefetched) {  // wait for this layer's commit group (groups complete in order)
+            switch (d.L - 1 - l) {
+                case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+                case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+                case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+                case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+                case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+                default: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
+            }
+        }
         const float* __restrict__ w = d.w[l];
         const float* __restrict__ bias = d.b[l];
         float* ys = a.y_save[l] ? a.y_save[l] + (long)m * total : nullptr;
@@ -75,11 +119,11 @@ __device__ __forceinline__ void cnn_fwd_block(const CnnFwdArgs& a, const int m, 
             for (int e = tid; e < co_n * hop * hop; e += nt) nxt[e] = 0.f;  // border of the next input
         for (int co0 = 0; co0 < co_n; co0 += cc) {
             const int ncur = min(cc, co_n - co0);
-            stage_rows(ws, w + (long)co0 * wrow, ncur, wrow, P);
+            if (!prefetched) stage_rows(ws, w + (long)co0 * wrow, ncur, wrow, P);
             __syncthreads();
             for (int idx = tid; idx < ncur * npos; idx += nt) {
                 const int c = idx / npos, pos = idx - c * npos, oy = pos / ho, ox = pos - oy * ho;
-                const float* wq = ws + c * P;
+                const float* wq = wl_s + c * P;
                 const float* x = in + (2 * oy) * hp + 2 * ox;
                 float a0 = bias[co0 + c], a1 = 0.f, a2 = 0.f;
                 for (int ci = 0; ci < ci_n; ++ci, wq += 9, x += hp2) {
@@ -127,7 +171,10 @@ inline void cnn_fwd_plan(const CnnDesc& d, int* padsz, int* ysz, int* wbuf) {
     }
     *padsz = (p + 3) & ~3;
     *ysz = (y + 3) & ~3;
-    *wbuf = min(wmax, 24 * 1024);  // <= 96 KB of staged weights; larger layers go in channel chunks
+    int wall = 0;  // all layers at once, rows padded to a multiple of 4 floats + 4 (cp.async alignment)
+    for (int l = 0; l < d.L; ++l) wall += d.cout[l] * (((d.cin[l] * 9 + 3) & ~3) + 4);
+    // <= 100 KB of staged weights: everything prefetched if it fits, else channel chunks per layer
+    *wbuf = wall <= 25 * 1024 ? wall : min(wmax, 24 * 1024);
 }
 inline size_t cnn_fwd_smem_bytes(const CnnFwdArgs& a) { return sizeof(float) * ((size_t)2 * a.padsz + a.ysz + a.wbuf); }
 
