@@ -121,6 +121,28 @@ def gather(na: int, nb: int, C: int, H: int, W: int, f: int, dev, reps: int = 20
             "us_per_launch": t * 1e6, "bytes_per_launch": bytes_alg, "gbs": bytes_alg / t / 1e9}
 
 
+def transition(M: int, H: int, W: int, f: int, dev, reps: int = 100) -> dict:
+    """K2 integer transition through Environment.step's entry point."""
+    from marlclassification_b200 import _lib
+
+    L = _lib.lib()
+    g = torch.Generator(device=dev).manual_seed(0)
+    pos = torch.stack([torch.randint(H - f, (M,), device=dev, generator=g), torch.randint(W - f, (M,), device=dev, generator=g)], -1).contiguous()
+    act = torch.randint(4, (M,), device=dev, generator=g)
+    table = torch.tensor([[1, 0], [-1, 0], [0, 1], [0, -1]], device=dev)
+    npos = torch.empty(M, 2, device=dev)
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def run():
+        _lib.check(L.marlc_transition(pos.data_ptr(), act.data_ptr(), table.data_ptr(), 4, M, f, H, W, npos.data_ptr(),
+                                      err.data_ptr(), _lib.stream_ptr(dev)))
+
+    t = _time(run, reps)
+    bytes_alg = 48.0 * M  # read pos 16 + action 8, write pos 16 + normalised pos 8 (SURVEY 8d)
+    return {"kernel": "transition_i64_kernel", "shape": {"agents": M}, "us_per_launch": t * 1e6,
+            "bytes_per_launch": bytes_alg, "gbs": bytes_alg / t / 1e9}
+
+
 def roofline_for(model, w: dict, nb: int, dev) -> dict:
     """The `roofline` object of bench.py's JSON line (+ the secondary kernels)."""
     pk, src = peaks()
@@ -133,6 +155,7 @@ def roofline_for(model, w: dict, nb: int, dev) -> dict:
     lstm_big = lstm_pair(4096, Kin, d["n_b"], dev, reps=50, x3=x3)
     g_small = gather(w["na"], nb, w["C"], w["H"], w["W"], w["f"], dev)
     g_big = gather(256, 256, w["C"], w["H"], w["W"], w["f"], dev, reps=50)  # 65536 windows: saturating
+    tr_big = transition(1 << 24, w["H"], w["W"], w["f"], dev, reps=20)
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
@@ -157,6 +180,9 @@ def roofline_for(model, w: dict, nb: int, dev) -> dict:
             {"kernel": "patch_gather_kernel @ 65536 windows (saturating)", "bound": "hbm", "achieved": g_big["gbs"],
              "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": g_big["gbs"] / pk["hbm_gbs"],
              "launch_us": g_big["us_per_launch"], "bytes_per_launch": g_big["bytes_per_launch"]},
+            {"kernel": "transition_i64_kernel @ 16.8 M agents (saturating)", "bound": "hbm", "achieved": tr_big["gbs"],
+             "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": tr_big["gbs"] / pk["hbm_gbs"],
+             "launch_us": tr_big["us_per_launch"], "bytes_per_launch": tr_big["bytes_per_launch"]},
         ],
     }
 
@@ -172,3 +198,5 @@ if __name__ == "__main__":
     for na, nb in ((16, 8), (64, 64), (256, 256)):
         print(json.dumps(gather(na, nb, 3, 256, 256, 12, dev, reps=50)))
     print(json.dumps(gather(256, 64, 3, 600, 600, 24, dev, reps=50)))
+    for M in (128, 1 << 20, 1 << 24):
+        print(json.dumps(transition(M, 256, 256, 12, dev, reps=20)))

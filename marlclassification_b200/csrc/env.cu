@@ -9,55 +9,43 @@ namespace marlc {
 // ---------------------------------------------------------------------------
 // K1 patch gather (environment.py:96-126):
 //   obs[a,b,c,i,j] = img[b,c,pos[a,b,0]+i,pos[a,b,1]+j]
-// One CTA per (a,b) window.  Source rows are read as ALIGNED 128-bit vectors
-// (aligned-down start, covering the f-float segment) into shared memory, then
-// the contiguous C*f*f output is written as 128-bit vectors.  Falls back to
-// scalar accesses when W or the patch size is not a multiple of 4.
+// (The first version staged aligned 128-bit row reads through shared memory, one CTA per window:
+// 2.4 TB/s at 65 536 windows.  Two block barriers and the index math per window dominated.)
 // ---------------------------------------------------------------------------
-template <typename PosT>
-__global__ void __launch_bounds__(128)
-patch_gather_kernel(const float* __restrict__ img, const PosT* __restrict__ pos, float* __restrict__ obs, int B, int C,
-                    int H, int W, int f, int vec_ok) {
-    extern __shared__ __align__(16) float stage[];  // [C*f][pitch]
-    const int m = blockIdx.x;                        // a*B + b
-    const int b = m % B;
+// One WARP per window, no shared memory, no block barrier: lane-strided over the contiguous
+// C*f*f output (perfectly coalesced 128 B stores); each warp-load covers 32 consecutive output
+// elements = 32/f source row segments (coalesced within a segment).  All iterations' loads are
+// issued before the first store (UNROLL independent requests per lane) so a window costs about
+// one memory round trip.  Measured 2.4 -> see profiles/README.md for the achieved GB/s.
+template <typename PosT, int UNROLL>
+__global__ void __launch_bounds__(256)
+patch_gather_kernel(const float* __restrict__ img, const PosT* __restrict__ pos, float* __restrict__ obs, int Na, int B,
+                    int C, int H, int W, int f) {
+    const int lane = threadIdx.x & 31;
+    // consecutive warps take the agents of ONE image (b-major): an image is then read in a burst
+    // while its DRAM pages are open / its sectors are in L2, instead of once per agent row
+    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (g >= Na * B) return;
+    const int b = g / Na, m = (g - b * Na) * B + b;  // output row m = a*B + b
     const int py = (int)pos[2 * (long)m], px = (int)pos[2 * (long)m + 1];
-    const int rows = C * f;
-    const float* src = img + (long)b * C * H * W;
-    float* dst = obs + (long)m * rows * f;
-    if (vec_ok) {
-        const int x0 = px & ~3;
-        const int nv = (px + f - x0 + 3) >> 2;  // float4 per row segment
-        const int pitch = ((f + 3) & ~3) + 8;   // floats, multiple of 4
-        for (int e = threadIdx.x; e < rows * nv; e += blockDim.x) {
-            const int r = e / nv, v = e % nv;
-            const int c = r / f, i = r % f;
-            const int x = x0 + 4 * v;
-            const float* p = src + ((long)c * H + (py + i)) * W + x;
-            float4 val;
-            if (x + 3 < W) val = __ldg(reinterpret_cast<const float4*>(p));
-            else {  // last vector of an image row may overhang (never dereference past the row)
-                val.x = x < W ? p[0] : 0.f; val.y = x + 1 < W ? p[1] : 0.f;
-                val.z = x + 2 < W ? p[2] : 0.f; val.w = 0.f;
-            }
-            *reinterpret_cast<float4*>(&stage[r * pitch + 4 * v]) = val;
-        }
-        __syncthreads();
-        const int off = px - x0;
-        const int total4 = (rows * f) >> 2;
-        for (int e = threadIdx.x; e < total4; e += blockDim.x) {
-            float o[4];
+    const int ff = f * f, total = C * ff;
+    const float* src = img + (long)b * C * H * W + (long)py * W + px;
+    float* dst = obs + (long)m * total;
+    const long plane = (long)H * W;
+    for (int e0 = lane; e0 < total; e0 += 32 * UNROLL) {
+        float v[UNROLL];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int idx = 4 * e + q, r = idx / f, j = idx % f;
-                o[q] = stage[r * pitch + off + j];
+        for (int u = 0; u < UNROLL; ++u) {
+            const int e = e0 + 32 * u;
+            if (e < total) {
+                const int c = e / ff, r = e - c * ff, i = r / f, j = r - i * f;
+                v[u] = __ldg(src + c * plane + (long)i * W + j);
             }
-            reinterpret_cast<float4*>(dst)[e] = make_float4(o[0], o[1], o[2], o[3]);
         }
-    } else {
-        for (int e = threadIdx.x; e < rows * f; e += blockDim.x) {
-            const int r = e / f, j = e % f, c = r / f, i = r % f;
-            dst[e] = __ldg(src + ((long)c * H + (py + i)) * W + px + j);
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const int e = e0 + 32 * u;
+            if (e < total) dst[e] = v[u];
         }
     }
 }
@@ -68,13 +56,9 @@ static int patch_gather_t(const float* img, const PosT* pos, float* obs, int Na,
     MARLC_CHECK(f >= 1 && f <= H && f <= W, "patch_gather: window f=%d does not fit %dx%d", f, H, W);
     const int M = Na * B;
     if (M <= 0) return 0;
-    int vec_ok = (W % 4 == 0) && ((C * f * f) % 4 == 0) && (((uintptr_t)img & 15) == 0) && (((uintptr_t)obs & 15) == 0);
-    const int pitch = ((f + 3) & ~3) + 8;
-    size_t smem = vec_ok ? sizeof(float) * (size_t)C * f * pitch : 0;
-    if (smem > 200 * 1024) { vec_ok = 0; smem = 0; }
-    if (smem > 48 * 1024)
-        MARLC_CUDA(cudaFuncSetAttribute(patch_gather_kernel<PosT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    patch_gather_kernel<PosT><<<M, 128, smem, s>>>(img, pos, obs, B, C, H, W, f, vec_ok);
+    const int blocks = (M + 7) / 8;  // 8 warps = 8 windows per CTA
+    if (C * f * f <= 32 * 8) patch_gather_kernel<PosT, 8><<<blocks, 256, 0, s>>>(img, pos, obs, Na, B, C, H, W, f);
+    else patch_gather_kernel<PosT, 16><<<blocks, 256, 0, s>>>(img, pos, obs, Na, B, C, H, W, f);
     MARLC_LAUNCH_CHECK();
     return 0;
 }
@@ -103,18 +87,22 @@ __global__ void transition_i64_kernel(int64_t* __restrict__ pos, const int64_t* 
                                       float* __restrict__ npos, int* __restrict__ err) {
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= M) return;
-    int py = (int)pos[2 * m], px = (int)pos[2 * m + 1];
+    // one 16-byte load / store per agent for the (y, x) pair, 8-byte for the action and the float2
+    longlong2 p = reinterpret_cast<const longlong2*>(pos)[m];
+    int py = (int)p.x, px = (int)p.y;
     const int64_t a = act[m];
     if (a < 0 || a >= nA) { if (err) atomicExch(err, 1); }
-    else apply_move(py, px, (int)table[2 * a], (int)table[2 * a + 1], f, H, W);
-    pos[2 * m] = py; pos[2 * m + 1] = px;
-    if (npos) { npos[2 * m] = (float)py / (float)H; npos[2 * m + 1] = (float)px / (float)W; }
+    else apply_move(py, px, (int)__ldg(table + 2 * a), (int)__ldg(table + 2 * a + 1), f, H, W);
+    p.x = py; p.y = px;
+    reinterpret_cast<longlong2*>(pos)[m] = p;
+    if (npos) reinterpret_cast<float2*>(npos)[m] = make_float2((float)py / (float)H, (float)px / (float)W);
 }
 
 int transition_i64(int64_t* pos, const int64_t* act, const int64_t* table, int nA, int M, int f, int H, int W,
                    float* npos, int* err, cudaStream_t s) {
     if (M <= 0) return 0;
-    transition_i64_kernel<<<(M + 127) / 128, 128, 0, s>>>(pos, act, table, nA, M, f, H, W, npos, err);
+    MARLC_CHECK(((uintptr_t)pos & 15) == 0 && ((uintptr_t)npos & 7) == 0, "transition: positions must be 16-byte aligned");
+    transition_i64_kernel<<<(M + 255) / 256, 256, 0, s>>>(pos, act, table, nA, M, f, H, W, npos, err);
     MARLC_LAUNCH_CHECK();
     return 0;
 }
