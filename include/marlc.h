@@ -41,6 +41,12 @@ int marlc_transition(int64_t* pos, const int64_t* act, const int64_t* table, int
 /* Environment.normalized_positions, environment.py:74-81. */
 int marlc_normalized_positions(const int64_t* pos, float* out, int M, int H, int W, void* stream);
 
+/* Input pipeline, device side: what torchvision's ToTensor does on the host in the reference
+ * (registry.py:56-57, applied per image by the DataLoader workers of train.py:91-107):
+ * uint8 pixels -> fp32 / 255, NCHW.  src is u8[B,H,W,C] (PIL order) when src_hwc != 0, else
+ * u8[B,C,H,W]; dst is f32[B,C,H,W].  Bit-identical to ToTensor. */
+int marlc_images_u8_to_f32(const uint8_t* src, float* dst, int B, int C, int H, int W, int src_hwc, void* stream);
+
 /* ---- building blocks, exposed for unit parity tests ------------------------ */
 
 /* nn.Linear forward: Y[M,N] = X[M,K] W[N,K]^T + bias (bias may be NULL). */

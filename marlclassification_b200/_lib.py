@@ -37,6 +37,7 @@ _SIGS = {
     "marlc_patch_gather": (C.c_int, [_P, _P, _P] + [C.c_int] * 6 + [_P]),
     "marlc_transition": (C.c_int, [_P, _P, _P] + [C.c_int] * 5 + [_P, _P, _P]),
     "marlc_normalized_positions": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "marlc_images_u8_to_f32": (C.c_int, [_P, _P] + [C.c_int] * 5 + [_P]),
     "marlc_linear": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "marlc_ln_silu": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _P]),
     "marlc_msg_mean": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P]),

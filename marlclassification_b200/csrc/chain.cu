@@ -146,7 +146,7 @@ __device__ void rb_dx_s(const float* dyT, const float* Ws, int P, float* out, in
 //   s_g   : optional global output          sT: optional smem output, transposed [n][RB]
 __device__ void rb_ln_silu(const float* ys, int ldy, int N, const float* __restrict__ gamma,
                            const float* __restrict__ beta, int rows_valid, long row0, float* pre_g, long ld_pre,
-                           float* s_g, long ld_s, float* sT) {
+                           float* s_g, long ld_s, float* sT, float* s_lo = nullptr) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp < RB) {
         const int r = warp;
@@ -164,6 +164,7 @@ __device__ void rb_ln_silu(const float* ys, int ldy, int N, const float* __restr
                 if (pre_g) pre_g[(row0 + r) * ld_pre + n] = yv;
                 const float o = siluf_((yv - mean) * rstd * gamma[n] + beta[n]);
                 if (s_g) s_g[(row0 + r) * ld_s + n] = o;
+                if (s_lo) s_lo[(row0 + r) * ld_s + n] = tf32_lo(o);
                 if (sT) sT[n * RB + r] = o;
             }
         } else if (sT) {
@@ -303,7 +304,8 @@ __global__ void __launch_bounds__(CT) step_pre_kernel(const StepPreKernelArgs ka
     rb_ln_silu(S.bufA, ka.maxw, n1, a.d0.g, a.d0.be, rows_valid, row0, a.dec_y1, n1, a.dec_s1, n1, S.bufT);
     if (ka.staged) rb_linear_s(S.bufT, W3s, P3, a.d3.b, S.bufA, ka.maxw, n2, n1);
     else rb_linear(S.bufT, a.d3.W, a.d3.b, S.bufA, ka.maxw, n2, n1, S.wt);
-    rb_ln_silu(S.bufA, ka.maxw, n2, a.d3.g, a.d3.be, rows_valid, row0, a.dec_y2, n2, a.U + a.F, a.ldu, nullptr);
+    rb_ln_silu(S.bufA, ka.maxw, n2, a.d3.g, a.d3.be, rows_valid, row0, a.dec_y2, n2, a.U + a.F, a.ldu, nullptr,
+               a.U_lo ? a.U_lo + a.F : nullptr);
     // position features                                                  state.py:7-17
     {
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nd = a.pos.n_out;
@@ -323,8 +325,12 @@ __global__ void __launch_bounds__(CT) step_pre_kernel(const StepPreKernelArgs ka
             for (int j = lane; j < nd; j += 32) { const float d = S.bufB[warp * ka.maxw + j] - mean; v += d * d; }
             const float rstd = 1.0f / sqrtf(warp_sum(v) * inv + LN_EPS_C);
             float* o = a.U + m * a.ldu + a.F + n2;
-            for (int j = lane; j < nd; j += 32)
-                o[j] = siluf_((S.bufB[warp * ka.maxw + j] - mean) * rstd * a.pos.g[j] + a.pos.be[j]);
+            float* ol = a.U_lo ? a.U_lo + m * a.ldu + a.F + n2 : nullptr;
+            for (int j = lane; j < nd; j += 32) {
+                const float v2 = siluf_((S.bufB[warp * ka.maxw + j] - mean) * rstd * a.pos.g[j] + a.pos.be[j]);
+                o[j] = v2;
+                if (ol) ol[j] = tf32_lo(v2);
+            }
         }
     }
 }
@@ -481,7 +487,7 @@ __device__ __forceinline__ void cell_bwd_rows(const int row0, const int rows_val
                                               const float* __restrict__ dh_carry, const float* __restrict__ dc_next,
                                               const float* __restrict__ c_prev, const float* __restrict__ c_new,
                                               const float* dhx, const int ldx, float* __restrict__ dgates,
-                                              float* __restrict__ dc_prev) {
+                                              float* __restrict__ dgates_lo, float* __restrict__ dc_prev) {
     for (int j = threadIdx.x; j < n; j += CT) {
         float gi[RB], gf[RB], gg[RB], go[RB], dh[RB], dcn[RB], cp[RB], cn[RB];
 #pragma unroll
@@ -503,10 +509,15 @@ __device__ __forceinline__ void cell_bwd_rows(const int row0, const int rows_val
                 const float tc = tanhf(cn[r]);
                 const float dc = dcn[r] + dhv * go[r] * (1.f - tc * tc);
                 float* dg = dgates + m * 4 * n;
-                dg[j] = dc * gg[r] * gi[r] * (1.f - gi[r]);
-                dg[n + j] = dc * cp[r] * gf[r] * (1.f - gf[r]);
-                dg[2 * n + j] = dc * gi[r] * (1.f - gg[r] * gg[r]);
-                dg[3 * n + j] = dhv * tc * go[r] * (1.f - go[r]);
+                const float d_i = dc * gg[r] * gi[r] * (1.f - gi[r]);
+                const float d_f = dc * cp[r] * gf[r] * (1.f - gf[r]);
+                const float d_g = dc * gi[r] * (1.f - gg[r] * gg[r]);
+                const float d_o = dhv * tc * go[r] * (1.f - go[r]);
+                dg[j] = d_i; dg[n + j] = d_f; dg[2 * n + j] = d_g; dg[3 * n + j] = d_o;
+                if (dgates_lo) {
+                    float* dl = dgates_lo + m * 4 * n;
+                    dl[j] = tf32_lo(d_i); dl[n + j] = tf32_lo(d_f); dl[2 * n + j] = tf32_lo(d_g); dl[3 * n + j] = tf32_lo(d_o);
+                }
                 dc_prev[idx] = dc * gf[r];
             }
         }
@@ -531,7 +542,7 @@ __global__ void __launch_bounds__(CT) bwd_pre_kernel(const BwdPreKernelArgs ka) 
     }
     // the action cell does not depend on the encoder chain: do it while the weights stream in
     cell_bwd_rows(row0, rows_valid, a.n[1], a.gates[1], a.dh_heads[1], a.dh_carry[1], a.dc_next[1], a.c_prev[1],
-                  a.c_new[1], nullptr, 0, a.dgates[1], a.dc_prev[1]);
+                  a.c_new[1], nullptr, 0, a.dgates[1], a.dgates_lo[1], a.dc_prev[1]);
     if (enc) {
         // gradient of the message produced at step t = adjoint mean of dcoll(t+1); encoder block 3 backward
         for (int e = threadIdx.x; e < RB * n_m; e += CT) {
@@ -557,7 +568,7 @@ __global__ void __launch_bounds__(CT) bwd_pre_kernel(const BwdPreKernelArgs ka) 
         else rb_dx(S.bufT, a.e0.W, dhx, mw, n1, nb);
     }
     cell_bwd_rows(row0, rows_valid, a.n[0], a.gates[0], a.dh_heads[0], a.dh_carry[0], a.dc_next[0], a.c_prev[0],
-                  a.c_new[0], enc ? dhx : nullptr, mw, a.dgates[0], a.dc_prev[0]);
+                  a.c_new[0], enc ? dhx : nullptr, mw, a.dgates[0], a.dgates_lo[0], a.dc_prev[0]);
 }
 
 int bwd_pre(const BwdPreArgs& a, cudaStream_t s) {

@@ -34,6 +34,7 @@ struct StepPreArgs {
     ChainLin pos;         // map_pos.{0,1}
     float* pos_y;         // [M,n_d] pre-norm, saved
     float* U;             // [M,ldu]: decoder output at column F, position features at F+n_m_o
+    float* U_lo = nullptr;  // optional [M,ldu]: tf32_lo(U) (pre-split 3xTF32 operand of the LSTM GEMM)
     long ldu;
     int F, Na, Nb, M;
 };
@@ -73,6 +74,7 @@ struct BwdPreArgs {
     const float* c_prev[2];
     const float* c_new[2];
     float* dgates[2];
+    float* dgates_lo[2] = {nullptr, nullptr};  // optional tf32_lo(dgates)
     float* dc_prev[2];
     int n[2];
     int Na, Nb, M, n_m;

@@ -14,6 +14,7 @@ struct CnnFwdArgs {
     const float* patch;
     float* y_save[MAX_CNN_LAYERS];
     float* out;
+    float* out_lo = nullptr;  // optional: tf32_lo(out), same leading dimension (pre-split 3xTF32 operand)
     long ldo;
     int B, H, W, M;
     int padsz;  // floats of one zero-bordered activation buffer: max_l cin_l * (hin_l + 2)^2
@@ -141,6 +142,7 @@ __device__ __forceinline__ void cnn_fwd_block(const CnnFwdArgs& a, const int m, 
         const int G = d.groups[l], cpg = co_n / G, ng = cpg * npos;
         const float inv = 1.0f / (float)ng;
         float* og = a.out + (long)m * a.ldo;
+        float* ogl = a.out_lo ? a.out_lo + (long)m * a.ldo : nullptr;
         for (int g = warp; g < G; g += nwarps) {
             const float* base = yb + g * ng;
             float s = 0.f;
@@ -152,7 +154,7 @@ __device__ __forceinline__ void cnn_fwd_block(const CnnFwdArgs& a, const int m, 
             for (int e = lane; e < ng; e += 32) {
                 const int c = g * cpg + e / npos, pos = e % npos;
                 const float o = siluf_((base[e] - mean) * rstd * d.gn_w[l][c] + d.gn_b[l][c]);
-                if (last) og[c * npos + pos] = o;
+                if (last) { og[c * npos + pos] = o; if (ogl) ogl[c * npos + pos] = tf32_lo(o); }
                 else nxt[c * hop * hop + (pos / ho + 1) * hop + (pos % ho) + 1] = o;
             }
         }

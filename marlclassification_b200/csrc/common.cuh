@@ -8,6 +8,9 @@
 #define MARLC_SMS 148
 
 namespace marlc {
+// low-order part of a float for the error-compensated 3xTF32 product: x - trunc_tf32(x) (exact in fp32)
+__device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
 
 // ---- error plumbing (C-ABI returns int, message via marlc_last_error) -----
 void set_error(const char* fmt, ...);

@@ -92,6 +92,27 @@ struct marlc_engine {
         return nullptr;
     }
     float* prm(const std::string& suffix) const { return P + find_param(suffix)->offset; }
+    // ---- pre-split low-order parts for 3xTF32 (see tc.cuh): parameters are split once per forward,
+    // activations next to where they are produced.  lo_of(p) is the lo twin of a pointer into the
+    // parameter block / H / Hc / U / dgates history, or nullptr (the GEMM then splits in-kernel).
+    bool lo_on = false;
+    const float* lo_of(const float* p) const {
+        if (!lo_on || !p) return nullptr;
+        struct R { const float* base; size_t n; const float* lo; };
+        const size_t Ms = (size_t)M, T1 = (size_t)cfg.T + 1;
+        const R r[] = {{P, (size_t)param_floats, buf("params_lo")},
+                       {buf("H"), T1 * Ms * cfg.n_b, buf("H_lo")},
+                       {buf("Hc"), T1 * Ms * cfg.n_a, buf("Hc_lo")}
+                       };
+        for (const R& q : r)
+            if (q.lo && p >= q.base && p < q.base + q.n) return q.lo + (p - q.base);
+        return nullptr;
+    }
+    TcOperand op(const float* p, long ld, bool mn = false) const {
+        TcOperand o = tc_op(p, ld, mn);
+        o.lo = lo_of(p);
+        return o;
+    }
     float* grd(const std::string& suffix) const { return G + find_param(suffix)->offset; }
     template <typename T = float>
     T* buf(const std::string& name) const {
@@ -153,6 +174,7 @@ extern "C" int marlc_engine_create(const marlc_config* c, marlc_engine** out) {
     d.out_size = e->cnn_sz[e->L - 1];
     e->F = d.out_size;
     e->Kin = e->F + c->n_m_o + c->n_d;
+    e->lo_on = c->use_tc == 2 && e->cfg.use_chains;
 
     // ---- parameters, in the reference's registration order (models.py:55-76)
     for (int l = 0; l < e->L; ++l) {
@@ -253,6 +275,14 @@ extern "C" int marlc_engine_create(const marlc_config* c, marlc_engine** out) {
     e->add_buf("dhc", M * c->n_a * F4);
     e->add_buf("dcc0", M * c->n_a * F4);
     e->add_buf("dcc1", M * c->n_a * F4);
+    if (e->lo_on) {
+        e->add_buf("params_lo", (size_t)e->param_floats * F4);
+        e->add_buf("U_lo", M * e->Kin * F4);  // one step at a time: only the per-step LSTM GEMM reads it
+        e->add_buf("H_lo", (T + 1) * M * c->n_b * F4);
+        e->add_buf("Hc_lo", (T + 1) * M * c->n_a * F4);
+        e->add_buf("dgates_b_lo", M * 4 * c->n_b * F4);  // one step at a time (the dX GEMMs of the sweep)
+        e->add_buf("dgates_a_lo", M * 4 * c->n_a * F4);
+    }
     for (int l = 0; l < e->L; ++l) {
         const size_t npos = (size_t)d.hout[l] * d.hout[l];
         e->add_buf("cnn_dY" + std::to_string(l), TM * npos * d.cout[l] * F4);
@@ -325,6 +355,40 @@ extern "C" int marlc_engine_seed(marlc_engine* e, uint64_t seed, void* stream) {
     return 0;
 }
 
+
+static inline TcOperand tc_op_lo(const float* p, const float* lo, long ld) {
+    TcOperand o = tc_op(p, ld);
+    o.lo = lo;
+    return o;
+}
+// tf32_lo of up to three arrays in one launch (parameters, h_0, h^_0)
+struct SplitLoArgs { const float* src[3]; float* dst[3]; long n[3]; };
+__global__ void __launch_bounds__(256) split_lo_kernel(const SplitLoArgs a) {
+    const int k = blockIdx.y;
+    const long n4 = a.n[k] >> 2;
+    const float4* s4 = reinterpret_cast<const float4*>(a.src[k]);
+    float4* d4 = reinterpret_cast<float4*>(a.dst[k]);
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+        float4 v = s4[i];
+        v.x = tf32_lo(v.x); v.y = tf32_lo(v.y); v.z = tf32_lo(v.z); v.w = tf32_lo(v.w);
+        d4[i] = v;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (a.n[k] & 3)) {  // ragged tail
+        const long i = (n4 << 2) + threadIdx.x;
+        a.dst[k][i] = tf32_lo(a.src[k][i]);
+    }
+}
+// h0 / hc0: the first step's recurrent inputs (nullptr: skip; only the parameters are refreshed)
+static int refresh_lo(marlc_engine* e, const float* h0, const float* hc0, cudaStream_t s) {
+    if (!e->lo_on) return 0;
+    SplitLoArgs a;
+    a.src[0] = e->P; a.dst[0] = e->buf("params_lo"); a.n[0] = e->param_floats;  // slots are multiples of 64 floats
+    a.src[1] = h0; a.dst[1] = const_cast<float*>(e->lo_of(h0)); a.n[1] = (h0 && a.dst[1]) ? (long)e->M * e->cfg.n_b : 0;
+    a.src[2] = hc0; a.dst[2] = const_cast<float*>(e->lo_of(hc0)); a.n[2] = (hc0 && a.dst[2]) ? (long)e->M * e->cfg.n_a : 0;
+    split_lo_kernel<<<dim3(296, 3), 256, 0, s>>>(a);
+    MARLC_LAUNCH_CHECK();
+    return 0;
+}
 
 // ---- GEMM dispatch: tcgen05 TF32 when enabled and TMA-addressable, else exact fp32 FFMA ----------
 static inline int x3_of(const marlc_engine* e) { return e->cfg.use_tc == 2 ? 1 : 0; }
@@ -413,6 +477,7 @@ static int step_networks(marlc_engine* e, int t, const float* img, const int* po
         StepPreArgs pa;
         memset(&pa, 0, sizeof(pa));
         pa.cnn.d = e->cnn; pa.cnn.img = img; pa.cnn.pos = pos; pa.cnn.patch = patch; pa.cnn.out = Ut; pa.cnn.ldo = Kin;
+        pa.cnn.out_lo = pa.U_lo = e->lo_on ? e->buf("U_lo") : nullptr;
         pa.cnn.B = c.nb; pa.cnn.H = c.H; pa.cnn.W = c.W; pa.cnn.M = M;
         cnn_fwd_plan(e->cnn, &pa.cnn.padsz, &pa.cnn.ysz, &pa.cnn.wbuf);
         for (int l = 0; l < e->L; ++l) pa.cnn.y_save[l] = e->buf("cnn_y" + std::to_string(l)) + (size_t)t * M * e->cnn_sz[l];
@@ -457,12 +522,15 @@ static int step_networks(marlc_engine* e, int t, const float* img, const int* po
             const int n = k ? c.n_a : c.n_b;
             TcLstmArgs& a = la[k];
             a.U = tc_op(Ut, Kin);
-            a.Hprev = tc_op(k ? hc_in : h_in, n);
+            a.U.lo = (e->lo_on && c.use_chains) ? e->buf("U_lo") : nullptr;
+            a.Hprev = e->op(k ? hc_in : h_in, n);
             a.Wih = e->prm(pre + "weight_ih"); a.Whh = e->prm(pre + "weight_hh");
+            a.Wih_lo = e->lo_of(a.Wih); a.Whh_lo = e->lo_of(a.Whh);
             a.bih = e->prm(pre + "bias_ih"); a.bhh = e->prm(pre + "bias_hh");
             a.c_prev = k ? cc_in : c_in;
             a.c_new = (k ? Cc : Cb) + (size_t)(t + 1) * M * n;
             a.h_new = (k ? Hc : H) + (size_t)(t + 1) * M * n;
+            a.h_new_lo = const_cast<float*>(e->lo_of(a.h_new));
             a.gates = k ? ga : gb;
             a.M = M; a.Kin = Kin; a.n = n;
             a.x3 = x3_of(e);
@@ -501,9 +569,9 @@ static int step_networks(marlc_engine* e, int t, const float* img, const int* po
         bool grouped = false;
         if (c.use_tc && tc_worth(M, 2 * c.n_m, c.n_b) && tc_worth(M, c.nl_a, c.n_a)) {
             TcGemmArgs g[2];
-            g[0].A = tc_op(enc_x, c.n_b); g[0].B = tc_op(e->prm("encode_msg.0.weight"), c.n_b); g[0].K = c.n_b;
+            g[0].A = e->op(enc_x, c.n_b); g[0].B = e->op(e->prm("encode_msg.0.weight"), c.n_b); g[0].K = c.n_b;
             g[0].C = enc_y1; g[0].ldc = 2 * c.n_m; g[0].M = M; g[0].N = 2 * c.n_m; g[0].bias = e->prm("encode_msg.0.bias");
-            g[1].A = tc_op(pol_x, c.n_a); g[1].B = tc_op(e->prm("policy.0.weight"), c.n_a); g[1].K = c.n_a;
+            g[1].A = e->op(pol_x, c.n_a); g[1].B = e->op(e->prm("policy.0.weight"), c.n_a); g[1].K = c.n_a;
             g[1].C = pol_y1; g[1].ldc = c.nl_a; g[1].M = M; g[1].N = c.nl_a; g[1].bias = e->prm("policy.0.bias");
             g[0].x3 = g[1].x3 = x3_of(e);
             if (tc_operand_ok(g[0].A) && tc_operand_ok(g[0].B) && tc_operand_ok(g[1].A) && tc_operand_ok(g[1].B)) {
@@ -619,6 +687,7 @@ extern "C" int marlc_episode_forward(marlc_engine* e, const float* img, const in
     ia.width[2] = ia.width[3] = c.n_a;
     ia.M = M; ia.n_m = c.n_m; ia.H = c.H; ia.W = c.W; ia.f = c.f;
     MARLC_TRY(episode_init(ia, s));
+    MARLC_TRY(refresh_lo(e, H, Hc, s));
 
     for (int t = 0; t < T; ++t) {
         MARLC_TRY(step_networks(e, t, img, pos_hist + (size_t)t * M * 2, nullptr, msg + (size_t)t * M * c.n_m,
@@ -644,6 +713,7 @@ extern "C" int marlc_model_step(marlc_engine* e, const float* patch, const float
                 "model_step: null input");
     cudaStream_t s = (cudaStream_t)stream;
     const int start = g_launch_count;
+    MARLC_TRY(refresh_lo(e, nullptr, nullptr, s));
     MARLC_TRY(step_networks(e, 0, nullptr, nullptr, patch, msg, npos, hidden[0], hidden[1], hidden[2], hidden[3], s));
     // the tail also needs an action to form log p[a]; use the all-zero index buffer
     // (only probs are read back by ModelsWrapper.forward)
@@ -765,6 +835,8 @@ extern "C" int marlc_episode_backward(marlc_engine* e, const float* img, int acc
         for (int t = T - 1; t >= 0; --t) {
             float* dgb = e->buf("dgates_b") + (size_t)t * M * 4 * c.n_b;
             float* dga = e->buf("dgates_a") + (size_t)t * M * 4 * c.n_a;
+            float* dgb_lo = e->lo_on ? e->buf("dgates_b_lo") : nullptr;
+            float* dga_lo = e->lo_on ? e->buf("dgates_a_lo") : nullptr;
             // fused: adjoint mean + encoder backward + dh accumulation + both LSTM cells' point-wise backward
             BwdPreArgs bp;
             memset(&bp, 0, sizeof(bp));
@@ -788,6 +860,7 @@ extern "C" int marlc_episode_backward(marlc_engine* e, const float* img, int acc
             bp.c_new[0] = Cb + (size_t)(t + 1) * M * c.n_b;
             bp.c_new[1] = Cc + (size_t)(t + 1) * M * c.n_a;
             bp.dgates[0] = dgb; bp.dgates[1] = dga;
+            bp.dgates_lo[0] = dgb_lo; bp.dgates_lo[1] = dga_lo;
             bp.dc_prev[0] = dc[cur ^ 1]; bp.dc_prev[1] = dcc[cur ^ 1];
             bp.n[0] = c.n_b; bp.n[1] = c.n_a;
             bp.Na = c.na; bp.Nb = c.nb; bp.M = M; bp.n_m = c.n_m;
@@ -800,12 +873,12 @@ extern "C" int marlc_episode_backward(marlc_engine* e, const float* img, int acc
             bool tc_dx = false;
             if (c.use_tc && c.n_a >= 16 && c.n_b >= 16) {
                 TcGemmArgs g[3];
-                g[0].A = tc_op(dgb, 4 * c.n_b); g[0].B = tc_op(e->prm(std::string(LSTM_B) + "weight_ih"), Kin, true); g[0].K = 4 * c.n_b;
-                g[0].A2 = tc_op(dga, 4 * c.n_a); g[0].B2 = tc_op(e->prm(std::string(LSTM_A) + "weight_ih"), Kin, true); g[0].K2 = 4 * c.n_a;
+                g[0].A = tc_op_lo(dgb, dgb_lo, 4 * c.n_b); g[0].B = e->op(e->prm(std::string(LSTM_B) + "weight_ih"), Kin, true); g[0].K = 4 * c.n_b;
+                g[0].A2 = tc_op_lo(dga, dga_lo, 4 * c.n_a); g[0].B2 = e->op(e->prm(std::string(LSTM_A) + "weight_ih"), Kin, true); g[0].K2 = 4 * c.n_a;
                 g[0].C = dUt; g[0].ldc = Kin; g[0].M = M; g[0].N = Kin;
-                g[1].A = tc_op(dgb, 4 * c.n_b); g[1].B = tc_op(e->prm(std::string(LSTM_B) + "weight_hh"), c.n_b, true); g[1].K = 4 * c.n_b;
+                g[1].A = tc_op_lo(dgb, dgb_lo, 4 * c.n_b); g[1].B = e->op(e->prm(std::string(LSTM_B) + "weight_hh"), c.n_b, true); g[1].K = 4 * c.n_b;
                 g[1].C = dh_t; g[1].ldc = c.n_b; g[1].M = M; g[1].N = c.n_b;
-                g[2].A = tc_op(dga, 4 * c.n_a); g[2].B = tc_op(e->prm(std::string(LSTM_A) + "weight_hh"), c.n_a, true); g[2].K = 4 * c.n_a;
+                g[2].A = tc_op_lo(dga, dga_lo, 4 * c.n_a); g[2].B = e->op(e->prm(std::string(LSTM_A) + "weight_hh"), c.n_a, true); g[2].K = 4 * c.n_a;
                 g[2].C = dhc_t; g[2].ldc = c.n_a; g[2].M = M; g[2].N = c.n_a;
                 bool ok = true;
                 for (int q = 0; q < 3; ++q) {

@@ -144,6 +144,12 @@ enum { EPI_STORE = 0, EPI_LSTM = 1 };
 
 struct TcKernelParams {
     CUtensorMap a1, b1, a2, b2;  // second pair unused when nk2 == 0
+    // 3xTF32 with PRE-SPLIT operands: low-order parts kept in global memory by the producer of the
+    // tensor (weights: refreshed once per forward; activations: written next to the value) and
+    // fetched by TMA into the lo ring, so no CTA has to split them (at small M every CTA of a
+    // launch would otherwise re-split the same A tiles)
+    CUtensorMap a1l, b1l, a2l, b2l;
+    int a_lo_g, b_lo_g;          // 1: the lo part of A / B comes from global memory
     int nk1, nk2;                // K blocks of each pair
     int slab_a1, slab_b1, slab_a2, slab_b2;
     int M, N;
@@ -157,6 +163,7 @@ struct TcKernelParams {
     const float* c_prev;
     float* c_new;
     float* h_new;
+    float* h_new_lo;  // optional: lo part of h_new for the next consumer's pre-split A operand
     float* gates;
     int n_hidden;
 };
@@ -245,20 +252,28 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
             for (int i = 0; i < my_kb; ++i) {
                 const int s = i % stages, ph = (i / stages) & 1;
                 mbar_wait(&empty_bar[s], ph ^ 1);
-                mbar_expect_tx(&full_bar[s], S::A_BYTES + S::B_BYTES);
+                mbar_expect_tx(&full_bar[s], S::A_BYTES + S::B_BYTES + ((X3 && p.a_lo_g) ? S::A_BYTES : 0) +
+                                                 ((X3 && p.b_lo_g) ? S::B_BYTES : 0));
                 const int kb = kb_begin + i;
                 const bool second = kb >= p.nk1;
-                const CUtensorMap* ma = second ? &p.a2 : &p.a1;
-                const CUtensorMap* mb = second ? &p.b2 : &p.b1;
                 const int za = second ? p.slab_a2 : p.slab_a1, zb = second ? p.slab_b2 : p.slab_b1;
+                const int nlo = X3 ? 2 : 1;
+                for (int hl = 0; hl < nlo; ++hl) {  // hl == 1: the pre-split lo tiles (when provided)
+                if (hl == 1 && !p.a_lo_g && !p.b_lo_g) break;
+                const CUtensorMap* ma = hl ? (second ? &p.a2l : &p.a1l) : (second ? &p.a2 : &p.a1);
+                const CUtensorMap* mb = hl ? (second ? &p.b2l : &p.b1l) : (second ? &p.b2 : &p.b1);
+                const bool do_a = hl == 0 || p.a_lo_g, do_b = hl == 0 || p.b_lo_g;
 #pragma unroll
                 for (int sub = 0; sub < KS; ++sub) {  // sub-blocks past the end of K are zero-filled by TMA
                     const int k0 = ((second ? kb - p.nk1 : kb) * KS + sub) * BK;
-                    uint8_t* a_dst = sA + s * S::A_BYTES + sub * S::A_SUB;
-                    uint8_t* b_dst = sB + s * S::B_BYTES + sub * S::B_SUB;
-                    if (!A_MN) tma_load_3d(a_dst, ma, &full_bar[s], k0, m0, za);
-                    else
-                        for (int j = 0; j < BM / 32; ++j) tma_load_3d(a_dst + j * 4096, ma, &full_bar[s], m0 + 32 * j, k0, za);
+                    uint8_t* a_dst = sA + s * S::A_BYTES + sub * S::A_SUB + hl * LO_OFF;
+                    uint8_t* b_dst = sB + s * S::B_BYTES + sub * S::B_SUB + hl * LO_OFF;
+                    if (do_a) {
+                        if (!A_MN) tma_load_3d(a_dst, ma, &full_bar[s], k0, m0, za);
+                        else
+                            for (int j = 0; j < BM / 32; ++j) tma_load_3d(a_dst + j * 4096, ma, &full_bar[s], m0 + 32 * j, k0, za);
+                    }
+                    if (!do_b) continue;
                     if (EPI == EPI_LSTM) {
                         // gather the 4 gate row-blocks of HU hidden units: rows g*n + j0 .. +HU
                         constexpr int HU = BN / 4;
@@ -271,6 +286,7 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
                             tma_load_3d(b_dst + j * 4096, mb, &full_bar[s], n_tile * BN + 32 * j, k0, zb);
                     }
                 }
+                }
             }
         }
     } else if (warp == 1) {
@@ -280,7 +296,7 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
                                    ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
             for (int i = 0; i < my_kb; ++i) {
                 const int s = i % stages, ph = (i / stages) & 1;
-                mbar_wait(X3 ? &split_bar[s] : &full_bar[s], ph);
+                mbar_wait((X3 && !(p.a_lo_g && p.b_lo_g)) ? &split_bar[s] : &full_bar[s], ph);
                 tc_fence_after();
 #pragma unroll
                 for (int sub = 0; sub < KS; ++sub) {
@@ -315,7 +331,8 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
             // fence / arrive latency overlaps the other group's copy loop
             constexpr int GRP = TC_SPLITTERS / 2;
             const int t = (threadIdx.x - 64) % GRP, grp = (threadIdx.x - 64) / GRP;
-            for (int i = grp; i < my_kb; i += 2) {
+            const bool split_a = !p.a_lo_g, split_b = !p.b_lo_g;
+            for (int i = grp; (split_a || split_b) && i < my_kb; i += 2) {
                 const int s = i % stages, ph = (i / stages) & 1;
                 mbar_wait(&full_bar[s], ph);
                 float4* a_hi = reinterpret_cast<float4*>(sA + s * S::A_BYTES);
@@ -324,12 +341,12 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
                 float4* b_lo = reinterpret_cast<float4*>(sB + s * S::B_BYTES + LO_OFF);
                 auto lo_of = [](float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); };
 #pragma unroll 4
-                for (int v = t; v < S::A_BYTES / 16; v += GRP) {
+                for (int v = t; split_a && v < S::A_BYTES / 16; v += GRP) {
                     const float4 x = a_hi[v];
                     a_lo[v] = make_float4(lo_of(x.x), lo_of(x.y), lo_of(x.z), lo_of(x.w));
                 }
 #pragma unroll 4
-                for (int v = t; v < S::B_BYTES / 16; v += GRP) {
+                for (int v = t; split_b && v < S::B_BYTES / 16; v += GRP) {
                     const float4 x = b_hi[v];
                     b_lo[v] = make_float4(lo_of(x.x), lo_of(x.y), lo_of(x.z), lo_of(x.w));
                 }
@@ -423,6 +440,12 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
                     st8(g_row, gi); st8(g_row + n, gf); st8(g_row + 2 * n, gc); st8(g_row + 3 * n, go);
                     st8(p.c_new + off, cn);
                     st8(p.h_new + off, hn);
+                    if (p.h_new_lo) {
+                        float hl[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) hl[j] = hn[j] - __uint_as_float(__float_as_uint(hn[j]) & 0xFFFFE000u);
+                        st8(p.h_new_lo + off, hl);
+                    }
                 }
             }
         }
@@ -511,11 +534,17 @@ int tc_gemm_group(const TcGemmArgs* args, int count, cudaStream_t s) {
         MARLC_TRY(operand_map(&p.b1, a.B, a.N, a.K, BN));
         p.nk1 = (a.K + BKS - 1) / BKS;
         p.slab_a1 = a.A.slab; p.slab_b1 = a.B.slab;
+        p.a_lo_g = (a.x3 && a.A.lo && (!pair2 || a.A2.lo)) ? 1 : 0;
+        p.b_lo_g = (a.x3 && a.B.lo && (!pair2 || a.B2.lo)) ? 1 : 0;
+        if (p.a_lo_g) { TcOperand o = a.A; o.ptr = a.A.lo; MARLC_TRY(operand_map(&p.a1l, o, a.M, a.K, BM)); }
+        if (p.b_lo_g) { TcOperand o = a.B; o.ptr = a.B.lo; MARLC_TRY(operand_map(&p.b1l, o, a.N, a.K, BN)); }
         if (pair2) {
             MARLC_TRY(operand_map(&p.a2, a.A2, a.M, a.K2, BM));
             MARLC_TRY(operand_map(&p.b2, a.B2, a.N, a.K2, BN));
             p.nk2 = (a.K2 + BKS - 1) / BKS;
             p.slab_a2 = a.A2.slab; p.slab_b2 = a.B2.slab;
+            if (p.a_lo_g) { TcOperand o = a.A2; o.ptr = a.A2.lo; MARLC_TRY(operand_map(&p.a2l, o, a.M, a.K2, BM)); }
+            if (p.b_lo_g) { TcOperand o = a.B2; o.ptr = a.B2.lo; MARLC_TRY(operand_map(&p.b2l, o, a.N, a.K2, BN)); }
         }
         p.M = a.M; p.N = a.N; p.C = a.C; p.ldc = a.ldc; p.bias = a.bias; p.bias2 = a.bias2;
         p.accumulate = a.accumulate;
@@ -614,6 +643,17 @@ int tc_lstm_pair(const TcLstmArgs& c0, const TcLstmArgs& c1, cudaStream_t s) {
         MARLC_TRY(make_map(&p.b2, c.Whh, c.n, 4 * c.n, 1, c.n, 0, HU));
         p.nk1 = (c.Kin + BKS - 1) / BKS;
         p.nk2 = (c.n + BKS - 1) / BKS;
+        p.a_lo_g = (c.x3 && c.U.lo && c.Hprev.lo) ? 1 : 0;
+        p.b_lo_g = (c.x3 && c.Wih_lo && c.Whh_lo) ? 1 : 0;
+        if (p.a_lo_g) {
+            MARLC_TRY(make_map(&p.a1l, c.U.lo, c.Kin, c.M, c.U.slabs, c.U.ld, c.U.slab_stride, BM));
+            MARLC_TRY(make_map(&p.a2l, c.Hprev.lo, c.n, c.M, c.Hprev.slabs, c.Hprev.ld, c.Hprev.slab_stride, BM));
+        }
+        if (p.b_lo_g) {
+            MARLC_TRY(make_map(&p.b1l, c.Wih_lo, c.Kin, 4 * c.n, 1, c.Kin, 0, HU));
+            MARLC_TRY(make_map(&p.b2l, c.Whh_lo, c.n, 4 * c.n, 1, c.n, 0, HU));
+        }
+        p.h_new_lo = c.h_new_lo;
         p.slab_a1 = c.U.slab; p.slab_a2 = c.Hprev.slab;
         p.M = c.M; p.N = 4 * c.n;
         p.bias = c.bih; p.bias2 = c.bhh;

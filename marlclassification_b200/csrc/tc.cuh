@@ -12,6 +12,7 @@ namespace marlc {
 // Optionally one slab of a [slabs][rows][ld] stack (time-stacked activations).
 struct TcOperand {
     const float* ptr = nullptr;
+    const float* lo = nullptr;  // optional pre-split low-order part (x - trunc_tf32(x)), same layout
     long ld = 0;
     bool mn_major = false;
     int slabs = 1;
@@ -52,6 +53,9 @@ struct TcLstmArgs {
     TcOperand Hprev;   // [M, n]
     const float* Wih;  // [4n, Kin]
     const float* Whh;  // [4n, n]
+    const float* Wih_lo = nullptr;  // optional pre-split low-order parts of the weights
+    const float* Whh_lo = nullptr;
+    float* h_new_lo = nullptr;      // optional output: low-order part of h_new
     const float* bih;
     const float* bhh;
     const float* c_prev;  // [M, n]

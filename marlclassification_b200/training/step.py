@@ -12,6 +12,7 @@ from typing import Optional
 import torch as th
 
 from ..engine import EpisodeEngine
+from ..input_pipeline import StagedBatch
 from ..parallel import DataParallelContext
 from .optim import FlatAdam
 
@@ -80,7 +81,11 @@ class TrainStep:
         return eng.loss_out
 
     def __call__(self, img: th.Tensor, y: th.Tensor, **inject) -> th.Tensor:
-        """img / y may live on the host (pinned -> async H2D) or on the device."""
+        """img / y may live on the host (pinned -> async H2D) or on the device, or be a
+        StagedBatch from the DevicePrefetcher (copy already in flight on the copy stream)."""
+        if isinstance(img, StagedBatch):
+            img.deliver(self.static_img, self.static_y)
+            return self.run_static()
         if inject.get("pos0") is not None or inject.get("hidden0") is not None or inject.get("actions") is not None:
             return self._run_injected(img, y, inject)
         self.static_img.copy_(img, non_blocking=True)

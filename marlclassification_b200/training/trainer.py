@@ -14,6 +14,7 @@ import torch as th
 from tqdm import tqdm
 
 from ..core import EpisodeSampler
+from ..input_pipeline import DevicePrefetcher, StagedBatch
 from ..metrics import ConfusionMeter, LossMeter
 from ..networks import ModelsWrapper
 from ..parallel import DataParallelContext
@@ -61,7 +62,8 @@ class Trainer:
     def train_step(self, x: th.Tensor, y: th.Tensor, episode_sampler: EpisodeSampler, **inject) -> th.Tensor:
         """One optimisation step (trainer.py:66-116): rollout, loss, backward, Adam.
         Returns the device tensor [loss, path, error, actor, critic] without
-        synchronising.  ``x`` / ``y`` may be host (pinned) or device tensors."""
+        synchronising.  ``x`` / ``y`` may be host (pinned) or device tensors, or ``x`` a
+        StagedBatch produced by :meth:`prefetch` (then ``y`` is ignored)."""
         eng = episode_sampler.engine_for(x, gamma=self.__gamma)
         step = self.__steps.get(id(eng))
         if step is None:
@@ -69,14 +71,18 @@ class Trainer:
             self.__steps[id(eng)] = step
         return step(x, y, **inject)
 
+    def prefetch(self, batches, *, hwc: bool = True) -> DevicePrefetcher:
+        """Wrap an iterable of host ``(images, labels)`` batches (fp32 NCHW as the reference's
+        DataLoader yields them, or raw uint8) so that the copy of batch i+1 overlaps step i."""
+        return DevicePrefetcher(batches, self.__model.device, hwc=hwc)
+
     def train_epoch(self, dataloader, epoch_index: int, episode_sampler: EpisodeSampler) -> None:
         self.__model.train()
-        device = self.__model.device
-        tqdm_bar = tqdm(dataloader)
-        for x_train, y_train in tqdm_bar:
-            loss_out = self.train_step(x_train, y_train, episode_sampler)
-            y_train = y_train.to(device, non_blocking=True)
-            eng = episode_sampler.engine_for(x_train, gamma=self.__gamma)
+        tqdm_bar = tqdm(self.prefetch(dataloader))
+        for staged in tqdm_bar:
+            loss_out = self.train_step(staged, None, episode_sampler)
+            eng = episode_sampler.engine_for(staged, gamma=self.__gamma)
+            y_train = self.__steps[id(eng)].static_y.clone()
             # meters: one packed D2H read of the five scalars
             loss_item, path_item, error_item, actor_item, critic_item = loss_out[:5].tolist()
             self.__conf_meter.add(eng.step_preds[-1].mean(dim=0), y_train)
@@ -101,12 +107,11 @@ class Trainer:
 
     def eval_epoch(self, dataloader, epoch_index: int, episode_sampler: EpisodeSampler) -> ConfusionMeter:
         self.__model.eval()
-        device = self.__model.device
         conf_meter = ConfusionMeter(self.__nb_class, None)
         with th.no_grad():
-            tqdm_bar = tqdm(dataloader)
-            for x_test, y_test in tqdm_bar:
-                x_test, y_test = x_test.to(device), y_test.to(device)
+            tqdm_bar = tqdm(self.prefetch(dataloader))
+            for staged in tqdm_bar:
+                x_test, y_test = staged.deliver()
                 output = episode_sampler.run_episode_get_last_step(x_test)
                 conf_meter.add(output.prediction.mean(dim=0), y_test)  # mean over agents
                 pr = th.stack((conf_meter.precision().mean(), conf_meter.recall().mean())).tolist()

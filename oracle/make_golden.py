@@ -221,10 +221,39 @@ def run_case(name: str, spec: dict) -> dict:
     return fx
 
 
+def run_input_pipeline_case() -> dict:
+    """The reference's host-side image pipeline (registry.py:56-57: Compose([ToTensor()])) applied,
+    as its DataLoader does, per PIL image (datasets.py:17-22 converts to RGB first); batches are
+    the default collate (stack).  Sizes: MNIST-like, odd, W not a multiple of 4, single channel."""
+    import numpy as np
+    from PIL import Image
+
+    from marl_classification.registry import default_image_pipeline
+
+    pipe = default_image_pipeline()
+    g = torch.Generator().manual_seed(7)
+    fx = {"cases": []}
+    for (b, h, w, c) in [(4, 28, 28, 3), (3, 7, 9, 3), (2, 12, 16, 3), (2, 10, 6, 1), (1, 64, 64, 3)]:
+        u8 = torch.randint(0, 256, (b, h, w, c), dtype=torch.uint8, generator=g)
+        u8[0].view(-1)[:2] = torch.tensor([0, 255], dtype=torch.uint8)  # both ends of the range
+        imgs = [Image.fromarray(u8[i].numpy().squeeze(-1) if c == 1 else u8[i].numpy()) for i in range(b)]
+        out = torch.stack([pipe(im) for im in imgs])
+        fx["cases"].append({"u8_hwc": u8, "f32_chw": out})
+    return fx
+
+
 def main() -> None:
     _import_reference()
     os.makedirs(OUT, exist_ok=True)
+    only = set(sys.argv[1:])
+    if not only or "input_pipeline" in only:
+        fx = run_input_pipeline_case()
+        path = os.path.join(OUT, "input_pipeline.pt")
+        torch.save(fx, path)
+        print(f"input_pipeline: wrote {path} ({os.path.getsize(path) / 1e3:.0f} kB)")
     for name, spec in CASES.items():
+        if only and name not in only:
+            continue
         fx = run_case(name, spec)
         path = os.path.join(OUT, f"{name}.pt")
         torch.save(fx, path)

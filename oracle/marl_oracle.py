@@ -95,6 +95,12 @@ class OracleConfig:
 # --------------------------------------------------------------------------
 # Environment (core/environment.py)
 # --------------------------------------------------------------------------
+def to_tensor_batch(u8_hwc: torch.Tensor) -> torch.Tensor:
+    """torchvision ``ToTensor`` on a batch of decoded images (registry.py:56-57 applied per sample by
+    the DataLoader of train.py:91-107): u8[B,H,W,C] -> f32[B,C,H,W] = permute, cast, true-divide by 255."""
+    return u8_hwc.permute(0, 3, 1, 2).contiguous().to(torch.float32).div(255)
+
+
 def observation_masked(img: torch.Tensor, pos: torch.Tensor, f: int) -> torch.Tensor:
     """The reference's own algorithm, environment.py:96-126: per-dim window
     masks, AND-ed and broadcast over [Na,B,C,H,W], then ``masked_select``.
