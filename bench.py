@@ -110,25 +110,27 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------
 # CPU port (oracle) timing: cpu_baseline and --impl reference
 # ------------------------------------------------------------------------------------
-def cpu_port_iteration_fn(w: dict, nb: int, threads: int):
+def cpu_port_iteration_fn(w: dict, nb: int, threads: int, device: str = "cpu"):
     """Returns a closure running ONE train iteration of the reference algorithm on
     the CPU (oracle port: rollout with the reference's mask+masked_select gather,
-    loss, autograd backward, Adam)."""
+    loss, autograd backward, Adam).  ``device="cuda"`` runs the same eager-PyTorch
+    port on the GPU (the reference's ``--cuda`` mode; SURVEY.md 8(d) like-for-like line)."""
     from oracle import marl_oracle as O
 
     torch.set_num_threads(threads)
     ocfg = O.OracleConfig(ft_extr=w["ft"], f=w["f"], n_b=w["n_b"], n_a=w["n_a"], n_m=w["n_m"], n_m_o=w["n_m_o"],
                           n_d=w["n_d"], nb_class=w["nc"], nl_b=w["nl"], nl_a=w["nl"], actions=w["actions"])
-    params = {k: v.requires_grad_(True) for k, v in O.init_params(ocfg, seed=0).items()}
+    params = {k: v.to(device).requires_grad_(True) for k, v in O.init_params(ocfg, seed=0).items()}
     opt = torch.optim.Adam(list(params.values()), lr=1e-4)
     g = torch.Generator().manual_seed(1234)
-    img = torch.rand(nb, w["C"], w["H"], w["W"], generator=g)
-    y = torch.randint(w["nc"], (nb,), generator=g)
+    img = torch.rand(nb, w["C"], w["H"], w["W"], generator=g).to(device)
+    y = torch.randint(w["nc"], (nb,), generator=g).to(device)
     na, T = w["na"], w["T"]
 
     def one_iteration() -> float:
-        pos0 = torch.stack([torch.randint(w["H"] - w["f"], (na, nb)), torch.randint(w["W"] - w["f"], (na, nb))], -1)
-        hidden0 = [torch.randn(na, nb, n) for n in (ocfg.n_b, ocfg.n_b, ocfg.n_a, ocfg.n_a)]
+        pos0 = torch.stack([torch.randint(w["H"] - w["f"], (na, nb), device=device),
+                            torch.randint(w["W"] - w["f"], (na, nb), device=device)], -1)
+        hidden0 = [torch.randn(na, nb, n, device=device) for n in (ocfg.n_b, ocfg.n_b, ocfg.n_a, ocfg.n_a)]
         ro = O.rollout(params, ocfg, img, pos0, hidden0, None, T, faithful_gather=True)
         parts = O.a2c_loss(ro.step_preds, ro.step_log_probas, ro.step_values, y, 0.99)
         opt.zero_grad()
@@ -139,9 +141,9 @@ def cpu_port_iteration_fn(w: dict, nb: int, threads: int):
     return one_iteration
 
 
-def time_cpu_port(w: dict, nb: int, budget_s: float, max_iters: int, warmup: int = 1):
+def time_cpu_port(w: dict, nb: int, budget_s: float, max_iters: int, warmup: int = 1, device: str = "cpu"):
     threads = os.cpu_count() or 1
-    fn = cpu_port_iteration_fn(w, nb, threads)
+    fn = cpu_port_iteration_fn(w, nb, threads, device)  # float(loss) at the end of fn synchronises
     t0 = time.perf_counter()
     for _ in range(warmup):
         fn()
@@ -267,6 +269,17 @@ def main() -> None:
     # the step stream is saturated only if the host keeps ahead; report the slower of
     # device-event time and wall time so host-bound runs are not flattered
     step_ms = max(dev_ms, wall_ms) / args.steps
+    def run_eval(pool, steps):
+        """Forward-only episodes (Trainer.eval_step, the eval_epoch path), inputs resident."""
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_wall = time.perf_counter()
+        a.record()
+        for i in range(steps):
+            trainer.eval_step(pool[i % len(pool)], sampler)
+        b.record()
+        torch.cuda.synchronize()
+        return max(a.elapsed_time(b), (time.perf_counter() - t_wall) * 1e3) / steps
+
     def run_e2e(pool, ys, steps):
         """The public API end to end: Trainer.prefetch (copy stream, one batch ahead) feeding
         Trainer.train_step from PINNED HOST batches, the step's five loss scalars read back every
@@ -296,13 +309,17 @@ def main() -> None:
     barrier()
     u8_dev_ms, u8_wall_ms = run_e2e(u8_pool, host_y, args.steps)
     barrier()
-    clk = clocks.stop() if clocks else None
     e2e_u8_ms = max(u8_dev_ms, u8_wall_ms) / args.steps
+    run_eval(dev_pool, 4)
+    barrier()
+    eval_ms = run_eval(dev_pool, args.steps)
+    barrier()
+    clk = clocks.stop() if clocks else None
 
-    t = torch.tensor([step_ms, e2e_ms, e2e_u8_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([step_ms, e2e_ms, e2e_u8_ms, eval_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    step_ms, e2e_ms, e2e_u8_ms = t.tolist()
+    step_ms, e2e_ms, e2e_u8_ms, eval_ms = t.tolist()
 
     eng = sampler.engine_for(dev_pool[0], gamma=0.99)
     launches = eng.launches["forward"] + eng.launches["loss"] + eng.launches["backward"] + 2
@@ -320,6 +337,8 @@ def main() -> None:
                         "u8_input": {"value": global_batch / (e2e_u8_ms * 1e-3), "ms_per_step": e2e_u8_ms,
                                      "h2d_bytes_per_step": batch_bytes // 4 + nb * 8,
                                      "input": "pinned host u8[B,H,W,C] (decoded image bytes), ToTensor on the device"}},
+                "eval": {"value": global_batch / (eval_ms * 1e-3), "unit": "image-episodes/s", "ms_per_step": eval_ms,
+                         "what": "forward-only episode + agent-mean vote (Trainer.eval_step), inputs in HBM"},
                 "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches, "clocks": clk}
         if not args.no_roofline:
             try:
@@ -333,6 +352,13 @@ def main() -> None:
             line["cpu_baseline"] = {"value": w["B"] / dt, "unit": "image-episodes/s", "cores": threads, "kind": "port",
                                     "sample": f"{iters} full train iterations of the same workload (batch {w['B']}) "
                                               f"by the CPU oracle port, after 1 warm-up"}
+            try:  # the same eager-PyTorch port on the GPU itself (the reference's --cuda mode)
+                dtg, itg, _ = time_cpu_port(w, w["B"], budget_s=5.0, max_iters=20, warmup=2, device=str(dev))
+                line["cpu_baseline"]["eager_gpu_port"] = {"value": w["B"] / dtg, "unit": "image-episodes/s",
+                                                          "sample": f"{itg} iterations of the oracle port run with "
+                                                                    f"device=cuda (eager PyTorch, ~10^4 launches/iteration)"}
+            except Exception as exc:
+                line["cpu_baseline"]["eager_gpu_port"] = {"error": repr(exc)[:200]}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

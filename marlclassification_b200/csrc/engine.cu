@@ -54,7 +54,10 @@ struct marlc_engine {
     float* P = nullptr;
     float* G = nullptr;
     int last_launches = 0;
-    int debug_stop = 0;  // profiling aid: 1 = stop backward after the heads, 2 = after the sweep
+    // profiling aid (scripts/phase_times.py).  backward: 1 = stop after the heads, 2 = after the sweep,
+    // 21 / 22 = sweep with only bwd_pre / bwd_pre + dX GEMMs per step.  forward: 11 / 12 / 13 = per step
+    // only step_pre / + LSTM / + block-0 GEMMs, 14 = whole loop without the batched heads.
+    int debug_stop = 0;
     // fork/join plumbing for independent branches (works eagerly and under stream capture)
     cudaStream_t side[2] = {nullptr, nullptr};
     cudaEvent_t ev[64];
@@ -493,6 +496,7 @@ static int step_networks(marlc_engine* e, int t, const float* img, const int* po
         pa.pos_y = e->buf("pos_y") + (size_t)t * M * c.n_d;
         pa.U = Ut; pa.ldu = Kin; pa.F = F; pa.Na = c.na; pa.Nb = c.nb; pa.M = M;
         MARLC_TRY(step_pre(pa, s));
+        if (e->debug_stop == 11) return 0;
     } else {
         // b_t: gather + CNN straight into u_t[:, 0:F]                (models.py:92-94)
         float* ysave[MAX_CNN_LAYERS];
@@ -560,6 +564,7 @@ static int step_networks(marlc_engine* e, int t, const float* img, const int* po
         MARLC_TRY(lstm_cell_fwd(gb, c_in, Cb + (size_t)(t + 1) * M * c.n_b, H + (size_t)(t + 1) * M * c.n_b, M, c.n_b, s));
         MARLC_TRY(lstm_cell_fwd(ga, cc_in, Cc + (size_t)(t + 1) * M * c.n_a, Hc + (size_t)(t + 1) * M * c.n_a, M, c.n_a, s));
     }
+    if (e->debug_stop == 12) return 0;
     if (c.use_chains) {
         // block-0 GEMMs of the encoder and the policy (tensor cores, ONE grouped launch), tails fused in step_act()
         const float* enc_x = H + (size_t)(t + 1) * M * c.n_b;
@@ -693,8 +698,10 @@ extern "C" int marlc_episode_forward(marlc_engine* e, const float* img, const in
         MARLC_TRY(step_networks(e, t, img, pos_hist + (size_t)t * M * 2, nullptr, msg + (size_t)t * M * c.n_m,
                                 npos + (size_t)t * M * 2, H + (size_t)t * M * c.n_b, Cb + (size_t)t * M * c.n_b,
                                 Hc + (size_t)t * M * c.n_a, Cc + (size_t)t * M * c.n_a, s));
+        if (e->debug_stop >= 11 && e->debug_stop <= 13) continue;  // profiling: skip the tail
         MARLC_TRY(step_act(e, t, actions ? actions + (size_t)t * M : nullptr, s));
     }
+    if (e->debug_stop >= 11 && e->debug_stop <= 14) { e->last_launches = g_launch_count - start; return 0; }
     // critic and prediction heads do not feed back into the trajectory: batch them
     // over all T steps (R = T*M rows)
     MARLC_TRY(value_pred_heads(e, e->TM, s));
@@ -866,6 +873,7 @@ extern "C" int marlc_episode_backward(marlc_engine* e, const float* img, int acc
             bp.Na = c.na; bp.Nb = c.nb; bp.M = M; bp.n_m = c.n_m;
             MARLC_TRY(bwd_pre(bp, s));
             cur ^= 1;
+            if (e->debug_stop == 21) continue;
             // input gradients: du = dg_b Wih_b + dg_a Wih_a ; dh = dg_b Whh_b ; dh^ = dg_a Whh_a  (ONE grouped launch)
             float* dUt = dU + (size_t)t * M * Kin;
             float* dh_t = dh_hist + (size_t)t * M * c.n_b;
@@ -921,6 +929,7 @@ extern "C" int marlc_episode_backward(marlc_engine* e, const float* img, int acc
                 MARLC_TRY(gemm_group(gg, s));
             }
             // fused decoder backward (models.py:97-98) -> dcoll for step t-1
+            if (e->debug_stop == 22) continue;
             BwdPostArgs bq;
             memset(&bq, 0, sizeof(bq));
             bq.dU = dUt; bq.ldu = Kin; bq.F = F;
@@ -1025,7 +1034,7 @@ extern "C" int marlc_episode_backward(marlc_engine* e, const float* img, int acc
         }
     }
 
-    if (e->debug_stop == 2) {
+    if (e->debug_stop == 2 || e->debug_stop == 21 || e->debug_stop == 22) {
         e->last_launches = g_launch_count - start;
         return 0;
     }

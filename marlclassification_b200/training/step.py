@@ -105,3 +105,42 @@ class TrainStep:
         dp.all_reduce_grads_sum(eng.model.flat_grads)
         self._seg_update()
         return eng.loss_out
+
+
+class EvalStep:
+    """Forward-only rollout for a fixed geometry (trainer.py:164-196: ``no_grad`` episode, vote =
+    mean over agents of the last step's predictions), replayed as one CUDA graph."""
+
+    def __init__(self, engine: EpisodeEngine, use_graph: bool = True) -> None:
+        self.engine, self.use_graph = engine, use_graph
+        dev = engine.device
+        self.static_img = th.zeros(engine.nb, engine.C, engine.H, engine.W, dtype=th.float32, device=dev)
+        self.static_y = th.zeros(engine.nb, dtype=th.int64, device=dev)
+        self.vote = th.zeros(engine.nb, engine.step_preds.shape[-1], dtype=th.float32, device=dev)
+        self._graph: Optional[th.cuda.CUDAGraph] = None
+        self._warm = 0
+
+    def _body(self) -> None:
+        self.engine.forward(self.static_img)
+        th.mean(self.engine.step_preds[-1], dim=0, out=self.vote)  # prediction.mean(0), trainer.py:180
+
+    def run_static(self) -> th.Tensor:
+        if self.use_graph and self._graph is None and self._warm >= 2:
+            g = th.cuda.CUDAGraph()
+            with th.cuda.graph(g):
+                self._body()
+            self._graph = g
+        if self._graph is not None:
+            self._graph.replay()
+        else:
+            self._body()
+            self._warm += 1
+        return self.vote
+
+    def __call__(self, img) -> th.Tensor:
+        """Returns the [Nb, Nc] vote (a static buffer: clone it to keep it across calls)."""
+        if isinstance(img, StagedBatch):
+            img.deliver(self.static_img, self.static_y)
+        else:
+            self.static_img.copy_(img, non_blocking=True)
+        return self.run_static()

@@ -19,7 +19,7 @@ from ..metrics import ConfusionMeter, LossMeter
 from ..networks import ModelsWrapper
 from ..parallel import DataParallelContext
 from .optim import FlatAdam
-from .step import TrainStep
+from .step import EvalStep, TrainStep
 
 MetricLogger = Callable[[int, Dict[str, float]], None]
 
@@ -43,6 +43,7 @@ class Trainer:
         self.__optim = FlatAdam(model, lr=learning_rate)  # th.optim.Adam semantics, trainer.py:33
         self.__cuda_graph = cuda_graph
         self.__steps: dict = {}
+        self.__eval_steps: dict = {}
         self.__nb_class = nb_class
         self.__gamma = gamma
         self.__metric_logger = metric_logger
@@ -70,6 +71,17 @@ class Trainer:
             step = TrainStep(eng, self.__optim, self.__dp, use_graph=self.__cuda_graph)
             self.__steps[id(eng)] = step
         return step(x, y, **inject)
+
+    def eval_step(self, x, episode_sampler: EpisodeSampler) -> th.Tensor:
+        """Forward-only episode; returns the [Nb, Nc] agent-mean prediction of the last step
+        (static device buffer, overwritten by the next call).  ``x``: tensor or StagedBatch."""
+        eng = episode_sampler.engine_for(x, gamma=self.__gamma)
+        step = self.__eval_steps.get(id(eng))
+        if step is None:
+            step = EvalStep(eng, use_graph=self.__cuda_graph)
+            self.__eval_steps[id(eng)] = step
+        with th.no_grad():
+            return step(x)
 
     def prefetch(self, batches, *, hwc: bool = True) -> DevicePrefetcher:
         """Wrap an iterable of host ``(images, labels)`` batches (fp32 NCHW as the reference's
@@ -111,9 +123,9 @@ class Trainer:
         with th.no_grad():
             tqdm_bar = tqdm(self.prefetch(dataloader))
             for staged in tqdm_bar:
-                x_test, y_test = staged.deliver()
-                output = episode_sampler.run_episode_get_last_step(x_test)
-                conf_meter.add(output.prediction.mean(dim=0), y_test)  # mean over agents
+                vote = self.eval_step(staged, episode_sampler)  # mean over agents, trainer.py:180
+                eng = episode_sampler.engine_for(staged, gamma=self.__gamma)
+                conf_meter.add(vote, self.__eval_steps[id(eng)].static_y.clone())
                 pr = th.stack((conf_meter.precision().mean(), conf_meter.recall().mean())).tolist()
                 tqdm_bar.set_description(
                     f"Epoch {epoch_index} - Eval, eval_prec = {pr[0]:.4f}, eval_rec = {pr[1]:.4f}"

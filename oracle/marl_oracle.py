@@ -256,11 +256,11 @@ def rollout(
     (agent.py:53-55).  ``actions=None`` samples with torch.multinomial."""
     sizes = list(img.shape[2:])
     gather = observation_masked if faithful_gather else observation
-    table = torch.tensor(cfg.actions, dtype=torch.long)
+    table = torch.tensor(cfg.actions, dtype=torch.long, device=img.device)
     na, nb = pos0.shape[:2]
     pos = pos0.clone()
     hid = tuple(hidden0)
-    msg = torch.zeros(na, nb, cfg.n_m)
+    msg = torch.zeros(na, nb, cfg.n_m, device=img.device)
     obs = gather(img, pos, cfg.f)
     patches = [obs]
     preds_l, logp_l, val_l, pos_l, prob_l, act_l = [], [], [], [], [], []

@@ -30,7 +30,14 @@ def bwd(stop):
         eng.backward(img)
         eng._L.marlc_engine_debug_stop(eng._h, 0)
     return f
-phases = {"forward": lambda: eng.forward(img), "loss": lambda: eng.loss(y), "bwd:heads": bwd(1), "bwd:heads+sweep": bwd(2),
+def fwd(stop):
+    def f():
+        eng._L.marlc_engine_debug_stop(eng._h, stop)
+        eng.forward(img)
+        eng._L.marlc_engine_debug_stop(eng._h, 0)
+    return f
+phases = {"fwd:pre": fwd(11), "fwd:pre+lstm": fwd(12), "fwd:pre+lstm+g0": fwd(13), "fwd:loop": fwd(14),
+          "forward": lambda: eng.forward(img), "loss": lambda: eng.loss(y), "bwd:heads": bwd(1), "bwd:heads+pre": bwd(21), "bwd:heads+pre+dx": bwd(22), "bwd:heads+sweep": bwd(2),
           "backward": lambda: eng.backward(img), "adam": lambda: opt.step()}
 side = torch.cuda.Stream()
 with torch.cuda.stream(side):
@@ -51,6 +58,6 @@ for name, f in phases.items():
         g.replay()
     b.record(); torch.cuda.synchronize()
     t = a.elapsed_time(b) / 20
-    tot += 0.0 if name.startswith("bwd:") else t
-    print(f"{name:9s} {t * 1e3:9.1f} us   launches {eng.launches.get(name, 2)}")
+    tot += 0.0 if ":" in name else t
+    print(f"{name:18s} {t * 1e3:9.1f} us   launches {eng.launches.get(name, 2)}")
 print(f"total     {tot * 1e3:9.1f} us  -> {nb / tot * 1e3:.0f} image-episodes/s  ({wl}, batch {nb})")
