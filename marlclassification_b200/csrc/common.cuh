@@ -167,6 +167,9 @@ int gemm_tn(const float* dY, long lddy, const float* X, long ldx, float* dW, lon
 int ln_silu_fwd(const float* Y, long ldy, const float* gamma, const float* beta, float* S, long lds, int R, int N,
                 cudaStream_t s);
 // dY = d(LN->SiLU)/dY * dS ; accumulates dgamma/dbeta/dbias (column sums) atomically
+int ln_silu_bwd_fused(const float* dS, long ldds, const float* dOut, int No, const float* W3, const float* Y, long ldy,
+                      const float* gamma, const float* beta, float* dY, long lddy, float* dgamma, float* dbeta,
+                      float* dbias, int R, int N, cudaStream_t s);
 int ln_silu_bwd(const float* dS, long ldds, const float* Y, long ldy, const float* gamma, const float* beta, float* dY,
                 long lddy, float* dgamma, float* dbeta, float* dbias, int R, int N, cudaStream_t s);
 int colsum_add(const float* X, long ldx, float* out, int R, int N, cudaStream_t s);

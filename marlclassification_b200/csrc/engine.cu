@@ -257,6 +257,8 @@ extern "C" int marlc_engine_create(const marlc_config* c, marlc_engine** out) {
     e->add_buf("scratchY", TM * nl_max * F4);
     e->add_buf("scratchS2", TM * nl_max * F4);  // second pair: the prediction head runs on a side stream
     e->add_buf("scratchY2", TM * nl_max * F4);
+    e->add_buf("scratchS3", TM * nl_max * F4);  // third pair: the critic head
+    e->add_buf("scratchY3", TM * nl_max * F4);
     e->add_buf("dH_heads", TM * c->n_b * F4);
     e->add_buf("dHc_heads", TM * c->n_a * F4);
     e->add_buf("dgates_b", TM * 4 * c->n_b * F4);
@@ -789,6 +791,28 @@ static int head_bwd(marlc_engine* e, const std::string& name, const float* dOut,
     return 0;
 }
 
+// The same head backward split in two: the part the BPTT sweep waits for (the gradient that flows
+// back into the recurrent state) and the parameter gradients, which nothing downstream consumes and
+// which therefore run on a side stream underneath the sweep.
+//   head_bwd_state: dS = dOut W3 ; dY = LN/SiLU backward(dS)     (also LN affine + block-0 bias grads)
+//   head_bwd_params: db3 += colsum(dOut) ; dW3 += dOut^T s1 ; dW0 += dY^T state
+static int head_bwd_state(marlc_engine* e, const std::string& name, const float* dOut, int N, const float* y1, int nl,
+                          float* S, float* Y, cudaStream_t s) {
+    if (N <= 64 && nl <= 1024 && (size_t)(N + 3) * nl * sizeof(float) <= 160 * 1024)  // fused: dS never materialised
+        return ln_silu_bwd_fused(nullptr, 0, dOut, N, e->prm(name + ".3.weight"), y1, nl, e->prm(name + ".1.weight"),
+                                 e->prm(name + ".1.bias"), Y, nl, e->grd(name + ".1.weight"), e->grd(name + ".1.bias"),
+                                 e->grd(name + ".0.bias"), e->TM, nl, s);
+    MARLC_TRY(G_nn(e, dOut, N, e->prm(name + ".3.weight"), nl, S, nl, e->TM, N, nl, 0, s));
+    return block_bwd_norm(e, name, 0, S, nl, y1, e->TM, nl, Y, s);
+}
+static int head_bwd_params(marlc_engine* e, const std::string& name, const float* dOut, int N, const float* s1,
+                           const float* Y, const float* state, int n_state, int nl, cudaStream_t s) {
+    const int TM = e->TM;
+    MARLC_TRY(colsum_add(dOut, N, e->grd(name + ".3.bias"), TM, N, s));
+    MARLC_TRY(G_tn(e, dOut, N, s1, nl, e->grd(name + ".3.weight"), nl, TM, N, nl, s));
+    return G_tn(e, Y, nl, state, n_state, e->grd(name + ".0.weight"), n_state, TM, nl, n_state, s);
+}
+
 extern "C" int marlc_episode_backward(marlc_engine* e, const float* img, int accumulate, void* stream) {
     MARLC_CHECK(e && e->ws && e->G, "backward: engine not bound (need a grads buffer)");
     MARLC_CHECK(img, "null image batch");
@@ -806,19 +830,64 @@ extern "C" int marlc_episode_backward(marlc_engine* e, const float* img, int acc
 
     // ---- heads, batched over T*M rows (their gradients do not depend on the sweep)
     // (prediction head on a side stream, policy + critic heads on the main one)
-    cudaStream_t sh = c.use_chains ? e->side[0] : s;
-    if (c.use_chains) MARLC_TRY(e->chain(s, sh));
-    MARLC_TRY(head_bwd(e, "predict", e->buf("d_preds"), c.nb_class, e->buf("prd_s1"), e->buf("prd_y1"),
-                       H + (size_t)M * c.n_b, c.n_b, c.nl_b, e->buf("dH_heads"), 0, sh, 1));
-    MARLC_TRY(policy_logit_grad(e->buf("d_logp"), e->buf("probs"), e->buf<int>("act"), e->buf("d_pol_logits"), TM,
-                                c.n_actions, s));
-    MARLC_TRY(head_bwd(e, "policy", e->buf("d_pol_logits"), c.n_actions, e->buf("pol_s1"), e->buf("pol_y1"),
-                       Hc + (size_t)M * c.n_a, c.n_a, c.nl_a, e->buf("dHc_heads"), 0, s));
-    MARLC_TRY(head_bwd(e, "critic", e->buf("d_values"), 1, e->buf("cri_s1"), e->buf("cri_y1"), Hc + (size_t)M * c.n_a,
-                       c.n_a, c.nl_a, e->buf("dHc_heads"), 1, s));
-    if (c.use_chains) MARLC_TRY(e->chain(sh, s));
+    if (c.use_chains) {
+        // three heads on three streams up to dY; the policy and critic heads share their input h^, so
+        // their state gradients are ONE dual-pair GEMM: dh^ = dY_pol W0_pol + dY_cri W0_cri
+        cudaStream_t sp = e->side[0], sc = e->side[1];
+        float *Yp = e->buf("scratchY"), *Yq = e->buf("scratchY2"), *Yc = e->buf("scratchY3");
+        MARLC_TRY(e->chain(s, sp));
+        MARLC_TRY(e->chain(s, sc));
+        MARLC_TRY(head_bwd_state(e, "predict", e->buf("d_preds"), c.nb_class, e->buf("prd_y1"), c.nl_b,
+                                 e->buf("scratchS2"), Yq, sp));
+        MARLC_TRY(G_nn(e, Yq, c.nl_b, e->prm("predict.0.weight"), c.n_b, e->buf("dH_heads"), c.n_b, TM, c.nl_b, c.n_b, 0, sp));
+        MARLC_TRY(head_bwd_state(e, "critic", e->buf("d_values"), 1, e->buf("cri_y1"), c.nl_a, e->buf("scratchS3"), Yc, sc));
+        MARLC_TRY(policy_logit_grad(e->buf("d_logp"), e->buf("probs"), e->buf<int>("act"), e->buf("d_pol_logits"), TM,
+                                    c.n_actions, s));
+        MARLC_TRY(head_bwd_state(e, "policy", e->buf("d_pol_logits"), c.n_actions, e->buf("pol_y1"), c.nl_a,
+                                 e->buf("scratchS"), Yp, s));
+        MARLC_TRY(e->chain(sc, s));
+        bool dual = false;
+        if (c.use_tc && tc_worth(TM, c.n_a, c.nl_a)) {
+            TcGemmArgs a;
+            a.A = tc_op(Yp, c.nl_a); a.B = e->op(e->prm("policy.0.weight"), c.n_a, true); a.K = c.nl_a;
+            a.A2 = tc_op(Yc, c.nl_a); a.B2 = e->op(e->prm("critic.0.weight"), c.n_a, true); a.K2 = c.nl_a;
+            a.C = e->buf("dHc_heads"); a.ldc = c.n_a; a.M = TM; a.N = c.n_a; a.x3 = x3_of(e); a.allow_split = 1;
+            if (tc_operand_ok(a.A) && tc_operand_ok(a.B) && tc_operand_ok(a.A2) && tc_operand_ok(a.B2)) {
+                MARLC_TRY(tc_gemm(a, s));
+                dual = true;
+            }
+        }
+        if (!dual) {
+            MARLC_TRY(G_nn(e, Yp, c.nl_a, e->prm("policy.0.weight"), c.n_a, e->buf("dHc_heads"), c.n_a, TM, c.nl_a, c.n_a, 0, s));
+            MARLC_TRY(G_nn(e, Yc, c.nl_a, e->prm("critic.0.weight"), c.n_a, e->buf("dHc_heads"), c.n_a, TM, c.nl_a, c.n_a, 1, s));
+        }
+        MARLC_TRY(e->chain(sp, s));  // the sweep needs dH_heads
+        // parameter gradients of the heads: side streams, underneath the sweep (joined at the end)
+        MARLC_TRY(head_bwd_params(e, "predict", e->buf("d_preds"), c.nb_class, e->buf("prd_s1"), Yq,
+                                  H + (size_t)M * c.n_b, c.n_b, c.nl_b, sp));
+        MARLC_TRY(e->chain(s, sc));  // dY_pol is produced on the main stream
+        MARLC_TRY(head_bwd_params(e, "policy", e->buf("d_pol_logits"), c.n_actions, e->buf("pol_s1"), Yp,
+                                  Hc + (size_t)M * c.n_a, c.n_a, c.nl_a, sc));
+        MARLC_TRY(head_bwd_params(e, "critic", e->buf("d_values"), 1, e->buf("cri_s1"), Yc, Hc + (size_t)M * c.n_a,
+                                  c.n_a, c.nl_a, sc));
+    } else {
+        MARLC_TRY(head_bwd(e, "predict", e->buf("d_preds"), c.nb_class, e->buf("prd_s1"), e->buf("prd_y1"),
+                           H + (size_t)M * c.n_b, c.n_b, c.nl_b, e->buf("dH_heads"), 0, s, 1));
+        MARLC_TRY(policy_logit_grad(e->buf("d_logp"), e->buf("probs"), e->buf<int>("act"), e->buf("d_pol_logits"), TM,
+                                    c.n_actions, s));
+        MARLC_TRY(head_bwd(e, "policy", e->buf("d_pol_logits"), c.n_actions, e->buf("pol_s1"), e->buf("pol_y1"),
+                           Hc + (size_t)M * c.n_a, c.n_a, c.nl_a, e->buf("dHc_heads"), 0, s));
+        MARLC_TRY(head_bwd(e, "critic", e->buf("d_values"), 1, e->buf("cri_s1"), e->buf("cri_y1"), Hc + (size_t)M * c.n_a,
+                           c.n_a, c.nl_a, e->buf("dHc_heads"), 1, s));
+    }
 
-    if (e->debug_stop == 1) { e->last_launches = g_launch_count - start; return 0; }
+    auto join_sides = [&]() -> int {  // early (profiling) exits must not leave forked work unjoined
+        if (!c.use_chains) return 0;
+        MARLC_TRY(e->chain(e->side[0], s));
+        MARLC_TRY(e->chain(e->side[1], s));
+        return 0;
+    };
+    if (e->debug_stop == 1) { MARLC_TRY(join_sides()); e->last_launches = g_launch_count - start; return 0; }
     // ---- BPTT sweep
     float* dh = e->buf("dh");
     float* dhc = e->buf("dhc");
@@ -1035,6 +1104,7 @@ extern "C" int marlc_episode_backward(marlc_engine* e, const float* img, int acc
     }
 
     if (e->debug_stop == 2 || e->debug_stop == 21 || e->debug_stop == 22) {
+        MARLC_TRY(join_sides());
         e->last_launches = g_launch_count - start;
         return 0;
     }

@@ -105,9 +105,160 @@ __global__ void ln_silu_bwd_kernel(const float* __restrict__ dS, long ldds, cons
     }
 }
 
+// ---------------------------------------------------------------------------
+// Register-accumulating variant used on the hot path (N <= 32*NC):
+//   * each lane owns columns lane, lane+32, ...; dgamma / dbeta / dbias partial sums stay in
+//     registers across all rows of the warp, then one shared atomic per lane-column per warp and
+//     one global atomic per column per CTA (the kernel above does three shared atomics per element);
+//   * optionally fuses the preceding tiny product dS = dOut[R,No] . W3[No,N] of a head's final
+//     Linear (No = nb_action, 1 or nb_class): W3 is staged in shared memory once per CTA and the
+//     row of dOut is broadcast with shuffles, so dS never exists in memory.
+// ---------------------------------------------------------------------------
+template <int NC>
+__global__ void __launch_bounds__(256) ln_silu_bwd_reg_kernel(const float* __restrict__ dS, long ldds,
+                                                              const float* __restrict__ dOut, int No,
+                                                              const float* __restrict__ W3,
+                                                              const float* __restrict__ Y, long ldy,
+                                                              const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, float* __restrict__ dY,
+                                                              long lddy, float* __restrict__ dgamma,
+                                                              float* __restrict__ dbeta, float* __restrict__ dbias,
+                                                              int R, int N) {
+    extern __shared__ float sm[];
+    float* acc = sm;          // [3][N]
+    float* w3s = sm + 3 * N;  // [No][N] when fused
+    for (int i = threadIdx.x; i < 3 * N; i += blockDim.x) acc[i] = 0.f;
+    if (W3)
+        for (int i = threadIdx.x; i < No * N; i += blockDim.x) w3s[i] = __ldg(W3 + i);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const float invN = 1.0f / (float)N;
+    float gam[NC], bet[NC], ag[NC], ab[NC], abi[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+        const int n = lane + 32 * j;
+        gam[j] = n < N ? gamma[n] : 0.f;
+        bet[j] = n < N ? beta[n] : 0.f;
+        ag[j] = ab[j] = abi[j] = 0.f;
+    }
+    for (int r = warp; r < R; r += nwarps) {
+        float y[NC], ds[NC];
+        const float* yr = Y + (long)r * ldy;
+#pragma unroll
+        for (int j = 0; j < NC; ++j) y[j] = (lane + 32 * j < N) ? yr[lane + 32 * j] : 0.f;
+        if (W3) {
+#pragma unroll
+            for (int j = 0; j < NC; ++j) ds[j] = 0.f;
+            const float* dor = dOut + (long)r * No;
+            for (int k0 = 0; k0 < No; k0 += 32) {
+                const float mine = (k0 + lane < No) ? dor[k0 + lane] : 0.f;
+                const int kn = min(32, No - k0);
+                for (int k = 0; k < kn; ++k) {
+                    const float d = __shfl_sync(0xffffffffu, mine, k);
+                    const float* wr = w3s + (k0 + k) * N + lane;
+#pragma unroll
+                    for (int j = 0; j < NC; ++j)
+                        if (lane + 32 * j < N) ds[j] = fmaf(d, wr[32 * j], ds[j]);
+                }
+            }
+        } else {
+            const float* dsr = dS + (long)r * ldds;
+#pragma unroll
+            for (int j = 0; j < NC; ++j) ds[j] = (lane + 32 * j < N) ? dsr[lane + 32 * j] : 0.f;
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < NC; ++j) s += y[j];  // padding columns hold 0
+        const float mean = warp_sum(s) * invN;
+        float v = 0.f;
+#pragma unroll
+        for (int j = 0; j < NC; ++j)
+            if (lane + 32 * j < N) { const float d = y[j] - mean; v += d * d; }
+        const float rstd = 1.0f / sqrtf(warp_sum(v) * invN + LN_EPS);
+        float c1 = 0.f, c2 = 0.f, xh[NC], dz[NC];
+#pragma unroll
+        for (int j = 0; j < NC; ++j) {
+            const bool ok = lane + 32 * j < N;
+            xh[j] = ok ? (y[j] - mean) * rstd : 0.f;
+            dz[j] = ok ? ds[j] * silu_grad_(xh[j] * gam[j] + bet[j]) : 0.f;
+            const float dxh = dz[j] * gam[j];
+            c1 += dxh;
+            c2 += dxh * xh[j];
+            ag[j] += dz[j] * xh[j];
+            ab[j] += dz[j];
+        }
+        c1 = warp_sum(c1) * invN;
+        c2 = warp_sum(c2) * invN;
+        float* dy = dY + (long)r * lddy;
+#pragma unroll
+        for (int j = 0; j < NC; ++j)
+            if (lane + 32 * j < N) {
+                const float g = rstd * (dz[j] * gam[j] - c1 - xh[j] * c2);
+                dy[lane + 32 * j] = g;
+                abi[j] += g;
+            }
+    }
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+        const int n = lane + 32 * j;
+        if (n < N) {
+            atomicAdd(&acc[n], ag[j]);
+            atomicAdd(&acc[N + n], ab[j]);
+            atomicAdd(&acc[2 * N + n], abi[j]);
+        }
+    }
+    __syncthreads();
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        if (dgamma) atomicAdd(&dgamma[n], acc[n]);
+        if (dbeta) atomicAdd(&dbeta[n], acc[N + n]);
+        if (dbias) atomicAdd(&dbias[n], acc[2 * N + n]);
+    }
+}
+
+template <int NC>
+static int launch_ln_bwd_reg(const float* dS, long ldds, const float* dOut, int No, const float* W3, const float* Y,
+                             long ldy, const float* gamma, const float* beta, float* dY, long lddy, float* dgamma,
+                             float* dbeta, float* dbias, int R, int N, cudaStream_t s) {
+    const size_t smem = sizeof(float) * ((size_t)3 * N + (W3 ? (size_t)No * N : 0));
+    MARLC_CHECK(smem <= 200 * 1024, "ln_silu_bwd: %zu B of shared memory (No=%d, N=%d)", smem, No, N);
+    static size_t attr = 0;
+    if (smem > 48 * 1024 && smem > attr) {
+        MARLC_CUDA(cudaFuncSetAttribute(ln_silu_bwd_reg_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = smem;
+    }
+    // one CTA per SM when the staged weights are large (their staging cost is per CTA), else two
+    const int blocks = max(1, min((R + 7) / 8, MARLC_SMS * (W3 && No * N > 8192 ? 1 : 2)));
+    ln_silu_bwd_reg_kernel<NC><<<blocks, 256, smem, s>>>(dS, ldds, dOut, No, W3, Y, ldy, gamma, beta, dY, lddy, dgamma,
+                                                         dbeta, dbias, R, N);
+    MARLC_LAUNCH_CHECK();
+    return 0;
+}
+
+// dS given (W3 == nullptr), or fused dS = dOut[R,No] . W3[No,N]
+int ln_silu_bwd_fused(const float* dS, long ldds, const float* dOut, int No, const float* W3, const float* Y, long ldy,
+                      const float* gamma, const float* beta, float* dY, long lddy, float* dgamma, float* dbeta,
+                      float* dbias, int R, int N, cudaStream_t s) {
+    if (R <= 0) return 0;
+#define MARLC_LNB(NC) \
+    return launch_ln_bwd_reg<NC>(dS, ldds, dOut, No, W3, Y, ldy, gamma, beta, dY, lddy, dgamma, dbeta, dbias, R, N, s)
+    if (N <= 32) MARLC_LNB(1);
+    if (N <= 64) MARLC_LNB(2);
+    if (N <= 128) MARLC_LNB(4);
+    if (N <= 256) MARLC_LNB(8);
+    if (N <= 384) MARLC_LNB(12);
+    if (N <= 512) MARLC_LNB(16);
+    if (N <= 1024) MARLC_LNB(32);
+#undef MARLC_LNB
+    MARLC_FAIL("ln_silu_bwd_fused: N=%d too wide", N);
+}
+
 int ln_silu_bwd(const float* dS, long ldds, const float* Y, long ldy, const float* gamma, const float* beta, float* dY,
                 long lddy, float* dgamma, float* dbeta, float* dbias, int R, int N, cudaStream_t s) {
     if (R <= 0) return 0;
+    if (N <= 1024)
+        return ln_silu_bwd_fused(dS, ldds, nullptr, 0, nullptr, Y, ldy, gamma, beta, dY, lddy, dgamma, dbeta, dbias, R, N, s);
     MARLC_CHECK(3 * N * sizeof(float) <= 48 * 1024, "ln_silu_bwd: N=%d too wide", N);
     int blocks = max(1, min((R + 7) / 8, MARLC_SMS * 2));
     ln_silu_bwd_kernel<<<blocks, 256, 3 * N * sizeof(float), s>>>(dS, ldds, Y, ldy, gamma, beta, dY, lddy, dgamma,
