@@ -17,7 +17,7 @@ constexpr float GN_EPS2 = 1e-5f;
 
 struct CnnBwdLayerKernelArgs {
     CnnBwdLayerArgs a;
-    int total, npos, npn, per_warp;  // per_warp: floats of smem per warp (3 * total rounded)
+    int total, npos, npn, per_warp;  // per_warp: floats of smem per warp (3 * total rounded + staged dCol block)
 };
 
 __global__ void __launch_bounds__(256) cnn_bwd_layer_kernel(const CnnBwdLayerKernelArgs ka) {
@@ -25,8 +25,14 @@ __global__ void __launch_bounds__(256) cnn_bwd_layer_kernel(const CnnBwdLayerKer
     const CnnBwdLayerArgs& a = ka.a;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
     const int p = blockIdx.x * wpc + warp;
-    if (p >= a.P) return;
     const int total = ka.total, npos = ka.npos, ho = a.ho, co_n = a.cout;
+    float* cta_acc = sm + (size_t)wpc * ka.per_warp;  // [3][cout]: dgamma, dbeta, dbias of this CTA's windows
+    const bool fold = a.d_gn_w != nullptr;
+    if (fold) {
+        for (int i = threadIdx.x; i < 3 * co_n; i += blockDim.x) cta_acc[i] = 0.f;
+        __syncthreads();
+    }
+    if (p < a.P) {
     float* xh = sm + (size_t)warp * ka.per_warp;  // y, then xhat
     float* dz = xh + total;                       // dA, then dz, then dy
     float* act = dz + total;                      // SiLU(GN(y))
@@ -36,11 +42,27 @@ __global__ void __launch_bounds__(256) cnn_bwd_layer_kernel(const CnnBwdLayerKer
         const float* go = a.dOut + (long)p * a.lddo;
         for (int e = lane; e < total; e += 32) { xh[e] = yg[e]; dz[e] = go[e]; }
     } else {
-        // col2im: dA[c, iy, ix] = sum over taps (ky,kx) with (iy+1-ky, ix+1-kx) even and in range
+        // col2im: dA[c, iy, ix] = sum over taps (ky,kx) with (iy+1-ky, ix+1-kx) even and in range.
+        // The window's dCol block (npn x cout*9 floats, contiguous) is first staged in shared memory
+        // with coalesced 128-bit loads, all in flight together: gathering the taps straight from
+        // global memory serialised ~9 dependent L2 round trips per element.
         const int hon = a.ho_next, npn = ka.npn, kk = co_n * 9;
-        const float* dc = a.dColNext + (long)p * npn * kk;
+        float* dc = xh + 3 * ((total + 3) & ~3);  // 16-byte aligned: per_warp and the rounded sizes are multiples of 4
+        {
+            const float* src = a.dColNext + (long)p * npn * kk;
+            const int n = npn * kk;
+            if ((n & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+                const float4* s4 = reinterpret_cast<const float4*>(src);
+                float4* d4 = reinterpret_cast<float4*>(dc);
+#pragma unroll 4
+                for (int i = lane; i < (n >> 2); i += 32) d4[i] = __ldg(s4 + i);
+            } else {
+                for (int i = lane; i < n; i += 32) dc[i] = __ldg(src + i);
+            }
+        }
+        for (int e = lane; e < total; e += 32) xh[e] = yg[e];
+        __syncwarp();
         for (int e = lane; e < total; e += 32) {
-            xh[e] = yg[e];
             const int c = e / npos, pos = e - c * npos, iy = pos / ho, ix = pos - iy * ho;
             float acc = 0.f;
 #pragma unroll
@@ -51,7 +73,7 @@ __global__ void __launch_bounds__(256) cnn_bwd_layer_kernel(const CnnBwdLayerKer
                 for (int kx = 0; kx < 3; ++kx) {
                     const int tx = ix + 1 - kx;
                     if (tx < 0 || (tx & 1) || (tx >> 1) >= hon) continue;
-                    acc += dc[(long)((ty >> 1) * hon + (tx >> 1)) * kk + c * 9 + ky * 3 + kx];
+                    acc += dc[((ty >> 1) * hon + (tx >> 1)) * kk + c * 9 + ky * 3 + kx];
                 }
             }
             dz[e] = acc;
@@ -88,17 +110,30 @@ __global__ void __launch_bounds__(256) cnn_bwd_layer_kernel(const CnnBwdLayerKer
         s2 = warp_sum(s2) * inv;
         __syncwarp();
         // per-channel partials for dgamma / dbeta (lanes over the group's channels)
-        float* gp = a.gnpart + (long)p * 2 * co_n;
         for (int cc = lane; cc < cpg; cc += 32) {
             float t1 = 0.f, t2 = 0.f;
             for (int q = 0; q < npos; ++q) { const float d = dg[cc * npos + q]; t1 += d * xg[cc * npos + q]; t2 += d; }
-            gp[g * cpg + cc] = t1;
-            gp[co_n + g * cpg + cc] = t2;
+            if (fold) {
+                atomicAdd(&cta_acc[g * cpg + cc], t1);
+                atomicAdd(&cta_acc[co_n + g * cpg + cc], t2);
+            } else {
+                float* gp = a.gnpart + (long)p * 2 * co_n;
+                gp[g * cpg + cc] = t1;
+                gp[co_n + g * cpg + cc] = t2;
+            }
         }
         __syncwarp();
         for (int e = lane; e < ng; e += 32) {
             const int c = g * cpg + e / npos;
             dg[e] = rstd * (dg[e] * a.gn_w[c] - s1 - xg[e] * s2);
+        }
+        if (fold) {  // conv bias gradient: sum of dY over the positions of each channel
+            __syncwarp();
+            for (int cc = lane; cc < cpg; cc += 32) {
+                float t3 = 0.f;
+                for (int q = 0; q < npos; ++q) t3 += dg[cc * npos + q];
+                atomicAdd(&cta_acc[2 * co_n + g * cpg + cc], t3);
+            }
         }
     }
     __syncwarp();
@@ -120,6 +155,15 @@ __global__ void __launch_bounds__(256) cnn_bwd_layer_kernel(const CnnBwdLayerKer
             cg[e] = (iy >= 0 && iy < ho && ix >= 0 && ix < ho) ? act[c * npos + iy * ho + ix] : 0.f;
         }
     }
+    }  // p < P
+    if (fold) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < co_n; i += blockDim.x) {
+            atomicAdd(a.d_gn_w + i, cta_acc[i]);
+            atomicAdd(a.d_gn_b + i, cta_acc[co_n + i]);
+            atomicAdd(a.d_conv_b + i, cta_acc[2 * co_n + i]);
+        }
+    }
 }
 
 int cnn_bwd_layer(const CnnBwdLayerArgs& a, cudaStream_t s) {
@@ -129,10 +173,13 @@ int cnn_bwd_layer(const CnnBwdLayerArgs& a, cudaStream_t s) {
     ka.npos = a.ho * a.ho;
     ka.total = a.cout * ka.npos;
     ka.npn = a.ho_next * a.ho_next;
-    ka.per_warp = 3 * ((ka.total + 3) & ~3);
+    ka.per_warp = 3 * ((ka.total + 3) & ~3) + (a.dOut ? 0 : ((ka.npn * a.cout * 9 + 3) & ~3));
     int wpc = 8;
     while (wpc > 1 && (size_t)wpc * ka.per_warp * sizeof(float) > 160 * 1024) wpc >>= 1;
-    const size_t smem = (size_t)wpc * ka.per_warp * sizeof(float);
+    MARLC_CHECK((a.d_gn_w != nullptr) == (a.d_gn_b != nullptr) && (a.d_gn_w != nullptr) == (a.d_conv_b != nullptr) &&
+                    (a.d_gn_w != nullptr || a.gnpart != nullptr),
+                "cnn_bwd_layer: give either gnpart or all three accumulation targets");
+    const size_t smem = ((size_t)wpc * ka.per_warp + 3 * a.cout) * sizeof(float);
     MARLC_CHECK(smem <= 200 * 1024, "cnn_bwd_layer: layer too large for shared memory (%zu B)", smem);
     static size_t attr = 0;
     if (smem > 48 * 1024 && smem > attr) {

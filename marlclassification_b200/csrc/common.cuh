@@ -173,6 +173,7 @@ int ln_silu_bwd_fused(const float* dS, long ldds, const float* dOut, int No, con
 int ln_silu_bwd(const float* dS, long ldds, const float* Y, long ldy, const float* gamma, const float* beta, float* dY,
                 long lddy, float* dgamma, float* dbeta, float* dbias, int R, int N, cudaStream_t s);
 int colsum_add(const float* X, long ldx, float* out, int R, int N, cudaStream_t s);
+int colsum_add2(const float* X, long ldx, float* out, float* out2, int R, int N, cudaStream_t s);
 int msg_mean(const float* msg, float* coll, int Na, int Nb, int n, cudaStream_t s);  // also its own adjoint
 int pos_features_fwd(const float* npos, const float* W, const float* b, const float* gamma, const float* beta,
                      float* y_pre, float* out, long ldo, int R, int nd, cudaStream_t s);

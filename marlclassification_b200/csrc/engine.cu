@@ -60,6 +60,11 @@ struct marlc_engine {
     int debug_stop = 0;
     // fork/join plumbing for independent branches (works eagerly and under stream capture)
     cudaStream_t side[2] = {nullptr, nullptr};
+    cudaStream_t hp = nullptr;  // highest priority: the latency-bound BPTT sweep, while batched gradients fill the GPU
+    // time-step chunks of the batched gradients; chunks > 1 overlap the sweep (MARLC_BWD_CHUNKS).  Measured at C2:
+    // 1, 2 and 4 chunks take the same time (the overlapped launches delay the sweep as much as they save), 8 is
+    // slower, so the default is one chunk after the sweep.
+    int bwd_chunks = 1;
     cudaEvent_t ev[64];
     int n_ev = 0, ev_i = 0;
     cudaEvent_t next_event() { cudaEvent_t x = ev[ev_i]; ev_i = (ev_i + 1) % n_ev; return x; }
@@ -304,6 +309,7 @@ extern "C" void marlc_engine_destroy(marlc_engine* e) {
     for (int i = 0; i < e->n_ev; ++i) cudaEventDestroy(e->ev[i]);
     for (int i = 0; i < 2; ++i)
         if (e->side[i]) cudaStreamDestroy(e->side[i]);
+    if (e->hp) cudaStreamDestroy(e->hp);
     delete e;
 }
 extern "C" int marlc_engine_param_count(const marlc_engine* e) { return (int)e->params.size(); }
@@ -338,6 +344,10 @@ extern "C" int marlc_engine_bind(marlc_engine* e, void* workspace, float* params
     e->G = grads;
     if (e->n_ev == 0) {
         for (int i = 0; i < 2; ++i) MARLC_CUDA(cudaStreamCreateWithFlags(&e->side[i], cudaStreamNonBlocking));
+        int least = 0, greatest = 0;
+        MARLC_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        MARLC_CUDA(cudaStreamCreateWithPriority(&e->hp, cudaStreamNonBlocking, greatest));
+        if (const char* env = getenv("MARLC_BWD_CHUNKS")) e->bwd_chunks = std::max(1, atoi(env));
         for (int i = 0; i < 64; ++i) {
             MARLC_CUDA(cudaEventCreateWithFlags(&e->ev[i], cudaEventDisableTiming));
             e->n_ev = i + 1;
@@ -442,6 +452,25 @@ static int G_tn(const marlc_engine* e, const float* dY, long lddy, const float* 
     return gemm_tn(dY, lddy, X, ldx, dW, lddw, R, N, K, 1, s);
 }
 
+
+// several dW[N,K] += dY[R,N]^T X[R,K] products in one grouped tensor-core launch (<= 3), falling back to
+// one launch each when any of them is not TMA-addressable / worth a tensor-core tile
+struct TnProblem { const float* dY; long lddy; const float* X; long ldx; float* dW; long lddw; int R, N, K; };
+static int G_tn_group(const marlc_engine* e, const TnProblem* p, int count, cudaStream_t s) {
+    bool ok = e->cfg.use_tc != 0 && count <= 3;
+    TcGemmArgs g[3];
+    for (int i = 0; ok && i < count; ++i) {
+        TcGemmArgs& a = g[i];
+        a.A = tc_op(p[i].dY, p[i].lddy, true); a.B = tc_op(p[i].X, p[i].ldx, true); a.K = p[i].R;
+        a.C = p[i].dW; a.ldc = p[i].lddw; a.M = p[i].N; a.N = p[i].K; a.accumulate = 1;
+        a.x3 = x3_of(e); a.allow_split = 1;
+        ok = tc_worth(p[i].N, p[i].K, p[i].R) && p[i].K >= 16 && tc_operand_ok(a.A) && tc_operand_ok(a.B);
+    }
+    if (ok) return tc_gemm_group(g, count, s);
+    for (int i = 0; i < count; ++i)
+        MARLC_TRY(G_tn(e, p[i].dY, p[i].lddy, p[i].X, p[i].ldx, p[i].dW, p[i].lddw, p[i].R, p[i].N, p[i].K, s));
+    return 0;
+}
 
 static ChainLin chain_lin(const marlc_engine* e, const std::string& name, int i, int n_in, int n_out, bool norm) {
     const std::string a = name + "." + std::to_string(i), b = name + "." + std::to_string(i + 1);
@@ -888,6 +917,118 @@ extern "C" int marlc_episode_backward(marlc_engine* e, const float* img, int acc
         return 0;
     };
     if (e->debug_stop == 1) { MARLC_TRY(join_sides()); e->last_launches = g_launch_count - start; return 0; }
+    // ---- weight gradients of steps [t0, t1), batched over their (t1-t0)*M rows (the reduction
+    //      dimension).  Three independent branches on three streams: LSTM (sL) | encoder / decoder /
+    //      position features (s1) | feature extractor (s0).  Nothing here feeds the sweep, so with the
+    //      fused chains the sweep runs on the high-priority stream and these launches fill the GPU
+    //      underneath it, one chunk of time steps behind.
+    const bool par = c.use_chains != 0;
+    auto batched = [&](int t0, int t1, cudaStream_t sL, cudaStream_t s1, cudaStream_t s0) -> int {
+        const size_t r0 = (size_t)t0 * M;       // first row of the chunk
+        const int R = (t1 - t0) * M;            // rows in the chunk
+        if (R <= 0) return 0;
+        {
+            const float* dgb = e->buf("dgates_b") + r0 * 4 * c.n_b;
+            const float* dga = e->buf("dgates_a") + r0 * 4 * c.n_a;
+            const float* Ur = e->buf("U") + r0 * Kin;
+            const std::string pb = LSTM_B, pa = LSTM_A;
+            const TnProblem ih[2] = {{dgb, 4L * c.n_b, Ur, Kin, e->grd(pb + "weight_ih"), Kin, R, 4 * c.n_b, Kin},
+                                     {dga, 4L * c.n_a, Ur, Kin, e->grd(pa + "weight_ih"), Kin, R, 4 * c.n_a, Kin}};
+            const TnProblem hh[2] = {{dgb, 4L * c.n_b, H + r0 * c.n_b, c.n_b, e->grd(pb + "weight_hh"), c.n_b, R, 4 * c.n_b, c.n_b},
+                                     {dga, 4L * c.n_a, Hc + r0 * c.n_a, c.n_a, e->grd(pa + "weight_hh"), c.n_a, R, 4 * c.n_a, c.n_a}};
+            MARLC_TRY(G_tn_group(e, ih, 2, sL));
+            MARLC_TRY(G_tn_group(e, hh, 2, sL));
+            MARLC_TRY(colsum_add2(dgb, 4 * c.n_b, e->grd(pb + "bias_ih"), e->grd(pb + "bias_hh"), R, 4 * c.n_b, sL));
+            MARLC_TRY(colsum_add2(dga, 4 * c.n_a, e->grd(pa + "bias_ih"), e->grd(pa + "bias_hh"), R, 4 * c.n_a, sL));
+        }
+        {
+            const int Re = (std::min(t1, T - 1) - t0) * M;  // the last message is never consumed
+            const TnProblem enc[2] = {
+                {e->buf("d_enc_y2") + r0 * c.n_m, c.n_m, e->buf("enc_s1") + r0 * 2 * c.n_m, 2L * c.n_m,
+                 e->grd("encode_msg.3.weight"), 2L * c.n_m, Re, c.n_m, 2 * c.n_m},
+                {e->buf("d_enc_y1") + r0 * 2 * c.n_m, 2L * c.n_m, H + (r0 + M) * c.n_b, c.n_b,
+                 e->grd("encode_msg.0.weight"), c.n_b, Re, 2 * c.n_m, c.n_b}};
+            if (Re > 0) MARLC_TRY(G_tn_group(e, enc, 2, s1));
+            const TnProblem dec[2] = {
+                {e->buf("d_dec_y2") + r0 * c.n_m_o, c.n_m_o, e->buf("dec_s1") + r0 * 2 * c.n_m, 2L * c.n_m,
+                 e->grd("decode_msg.3.weight"), 2L * c.n_m, R, c.n_m_o, 2 * c.n_m},
+                {e->buf("d_dec_y1") + r0 * 2 * c.n_m, 2L * c.n_m, e->buf("coll") + r0 * c.n_m, c.n_m,
+                 e->grd("decode_msg.0.weight"), c.n_m, R, 2 * c.n_m, c.n_m}};
+            MARLC_TRY(G_tn_group(e, dec, 2, s1));
+        }
+        // position features (state.py:13-17)
+        MARLC_TRY(block_bwd_norm(e, "map_pos", 0, dU + r0 * Kin + F + c.n_m_o, Kin, e->buf("pos_y") + r0 * c.n_d, R, c.n_d,
+                                 e->buf("d_pos_y") + r0 * c.n_d, s1));
+        MARLC_TRY(G_tn(e, e->buf("d_pos_y") + r0 * c.n_d, c.n_d, e->buf("npos") + r0 * 2, 2, e->grd("map_pos.0.weight"), 2,
+                       R, c.n_d, 2, s1));
+        // feature extractor: layer-wise, batched over the chunk's windows (cnn_bwd2.cu); every conv product
+        // (input gradient dCol_l = dY_l W_l, weight gradient dW_l = dY_l^T col_l) is a tensor-core GEMM
+        const CnnDesc& d = e->cnn;
+        const float* ysave[MAX_CNN_LAYERS];
+        CnnBwdBuffers bb;
+        float* dcol[MAX_CNN_LAYERS] = {nullptr};
+        for (int l = 0; l < e->L; ++l) {
+            const size_t npos = (size_t)d.hout[l] * d.hout[l];
+            ysave[l] = e->buf("cnn_y" + std::to_string(l)) + (par ? r0 * e->cnn_sz[l] : 0);
+            bb.dY[l] = e->buf("cnn_dY" + std::to_string(l)) + (par ? r0 * npos * d.cout[l] : 0);
+            bb.col[l] = e->buf("cnn_col" + std::to_string(l)) + (par ? r0 * npos * d.cin[l] * 9 : 0);
+            bb.gnpart[l] = e->buf("cnn_gnpart" + std::to_string(l)) + (par ? r0 * 2 * d.cout[l] : 0);
+            if (l > 0) dcol[l] = e->buf("cnn_dcol" + std::to_string(l)) + (par ? r0 * npos * d.cin[l] * 9 : 0);
+        }
+        auto conv_weight_grad = [&](int l, cudaStream_t st) -> int {
+            const int npos = d.hout[l] * d.hout[l], kk = d.cin[l] * 9, co = d.cout[l];
+            return G_tn(e, bb.dY[l], co, bb.col[l], kk, e->grd(CNN_PREFIX + std::to_string(3 * l) + ".weight"), kk,
+                        R * npos, co, kk, st);
+        };
+        if (!par) {  // unfused reference path: one whole-episode call of the per-window kernel
+            MARLC_TRY(cnn_bwd(e->cnn, img, e->buf<int>("pos_hist"), c.nb, c.H, c.W, M, 0, TM, ysave, dU, Kin, bb, s0));
+            for (int l = 0; l < e->L; ++l) {
+                const int npos = d.hout[l] * d.hout[l], co = d.cout[l];
+                const std::string cw = CNN_PREFIX + std::to_string(3 * l), gn = CNN_PREFIX + std::to_string(3 * l + 1);
+                MARLC_TRY(conv_weight_grad(l, s0));
+                MARLC_TRY(colsum_add(bb.dY[l], co, e->grd(cw + ".bias"), R * npos, co, s0));
+                MARLC_TRY(colsum_add(bb.gnpart[l], 2 * co, e->grd(gn + ".weight"), R, co, s0));
+                MARLC_TRY(colsum_add(bb.gnpart[l] + co, 2 * co, e->grd(gn + ".bias"), R, co, s0));
+            }
+            return 0;
+        }
+        // The serial chain is only layer kernel -> input-gradient GEMM -> next layer kernel; the im2col
+        // of the input windows is independent of it (stream s1), and the weight-gradient GEMMs wait at
+        // the end and fan out over the three streams.  GroupNorm-affine and conv-bias gradients are
+        // accumulated inside the layer kernel.
+        MARLC_TRY(cnn_im2col_input(img, e->buf<int>("pos_hist") + r0 * 2, bb.col[0], R, M, c.nb, c.C, d.cin[0], c.H, c.W,
+                                   c.f, d.hout[0], s1));
+        for (int l = e->L - 1; l >= 0; --l) {
+            CnnBwdLayerArgs la;
+            memset(&la, 0, sizeof(la));
+            la.cout = d.cout[l]; la.ho = d.hout[l]; la.groups = d.groups[l]; la.P = R;
+            la.Y = ysave[l]; la.gn_w = d.gn_w[l]; la.gn_b = d.gn_b[l];
+            const bool top = (l == e->L - 1);
+            la.dOut = top ? dU + r0 * Kin : nullptr; la.lddo = Kin;
+            la.dColNext = top ? nullptr : dcol[l + 1];
+            la.ho_next = top ? 1 : d.hout[l + 1];
+            la.dY = bb.dY[l]; la.gnpart = nullptr;
+            la.d_gn_w = e->grd(CNN_PREFIX + std::to_string(3 * l + 1) + ".weight");
+            la.d_gn_b = e->grd(CNN_PREFIX + std::to_string(3 * l + 1) + ".bias");
+            la.d_conv_b = e->grd(CNN_PREFIX + std::to_string(3 * l) + ".bias");
+            la.colNext = top ? nullptr : bb.col[l + 1];
+            MARLC_TRY(cnn_bwd_layer(la, s0));
+            if (l > 0) {
+                const int npos = d.hout[l] * d.hout[l], kk = d.cin[l] * 9;
+                MARLC_TRY(G_nn_on(e, bb.dY[l], d.cout[l], d.w[l], kk, dcol[l], kk, R * npos, d.cout[l], kk, s0));
+            }
+        }
+        {
+            cudaStream_t fan[3] = {s0, s1, sL};
+            cudaEvent_t done = e->next_event();
+            MARLC_CUDA(cudaEventRecord(done, s0));
+            if (s1 != s0) MARLC_CUDA(cudaStreamWaitEvent(s1, done, 0));
+            if (sL != s0) MARLC_CUDA(cudaStreamWaitEvent(sL, done, 0));
+            // layer 0 reads the im2col of the input windows, produced on s1: it stays on s1
+            for (int l = e->L - 1, i = 0; l >= 0; --l, ++i) MARLC_TRY(conv_weight_grad(l, l == 0 ? s1 : fan[(i & 1) ? 2 : 0]));
+        }
+        return 0;
+    };
     // ---- BPTT sweep
     float* dh = e->buf("dh");
     float* dhc = e->buf("dhc");
@@ -908,6 +1049,12 @@ extern "C" int marlc_episode_backward(marlc_engine* e, const float* img, int acc
         MARLC_CUDA(cudaMemsetAsync(dU, 0, sizeof(float) * (size_t)TM * Kin, s));
         MARLC_CUDA(cudaMemsetAsync(dh_hist, 0, sizeof(float) * (size_t)TM * c.n_b, s));
         MARLC_CUDA(cudaMemsetAsync(dhc_hist, 0, sizeof(float) * (size_t)TM * c.n_a, s));
+        // the sweep moves to the high-priority stream; the caller's stream becomes the LSTM branch
+        const bool profiling_stop = e->debug_stop == 2 || e->debug_stop == 21 || e->debug_stop == 22;
+        const int nch = profiling_stop ? 0 : std::max(1, std::min(e->bwd_chunks, T));
+        cudaStream_t sw = e->hp, s0 = e->side[0], s1 = e->side[1];
+        MARLC_TRY(e->chain(s, sw));
+        int chunk_hi = T, next_chunk = nch - 1;  // chunk k covers steps [k*T/nch, (k+1)*T/nch)
         for (int t = T - 1; t >= 0; --t) {
             float* dgb = e->buf("dgates_b") + (size_t)t * M * 4 * c.n_b;
             float* dga = e->buf("dgates_a") + (size_t)t * M * 4 * c.n_a;
@@ -940,7 +1087,7 @@ extern "C" int marlc_episode_backward(marlc_engine* e, const float* img, int acc
             bp.dc_prev[0] = dc[cur ^ 1]; bp.dc_prev[1] = dcc[cur ^ 1];
             bp.n[0] = c.n_b; bp.n[1] = c.n_a;
             bp.Na = c.na; bp.Nb = c.nb; bp.M = M; bp.n_m = c.n_m;
-            MARLC_TRY(bwd_pre(bp, s));
+            MARLC_TRY(bwd_pre(bp, sw));
             cur ^= 1;
             if (e->debug_stop == 21) continue;
             // input gradients: du = dg_b Wih_b + dg_a Wih_a ; dh = dg_b Whh_b ; dh^ = dg_a Whh_a  (ONE grouped launch)
@@ -964,7 +1111,7 @@ extern "C" int marlc_episode_backward(marlc_engine* e, const float* img, int acc
                 }
                 ok = ok && tc_operand_ok(g[0].A2) && tc_operand_ok(g[0].B2);
                 if (ok) {
-                    MARLC_TRY(tc_gemm_group(g, t > 0 ? 3 : 1, s));  // at t == 0 nothing consumes dh / dh^
+                    MARLC_TRY(tc_gemm_group(g, t > 0 ? 3 : 1, sw));  // at t == 0 nothing consumes dh / dh^
                     tc_dx = true;
                 }
             }
@@ -995,7 +1142,7 @@ extern "C" int marlc_episode_backward(marlc_engine* e, const float* img, int acc
                     p.C = dhc_t; p.ldc = c.n_a;
                     p.M = M; p.N = c.n_a; p.K = 4 * c.n_a;
                 }
-                MARLC_TRY(gemm_group(gg, s));
+                MARLC_TRY(gemm_group(gg, sw));
             }
             // fused decoder backward (models.py:97-98) -> dcoll for step t-1
             if (e->debug_stop == 22) continue;
@@ -1010,8 +1157,19 @@ extern "C" int marlc_episode_backward(marlc_engine* e, const float* img, int acc
             bq.d_dec_y2 = e->buf("d_dec_y2") + (size_t)t * M * c.n_m_o;
             bq.dcoll = t > 0 ? dcoll : nullptr;
             bq.M = M; bq.n_m = c.n_m; bq.n_m_o = c.n_m_o;
-            MARLC_TRY(bwd_post(bq, s));
+            MARLC_TRY(bwd_post(bq, sw));
+            if (next_chunk >= 0 && t == (int)((long)next_chunk * T / nch)) {  // steps [t, chunk_hi) are final
+                cudaEvent_t done = e->next_event();
+                MARLC_CUDA(cudaEventRecord(done, sw));
+                MARLC_CUDA(cudaStreamWaitEvent(s, done, 0));
+                MARLC_CUDA(cudaStreamWaitEvent(s0, done, 0));
+                MARLC_CUDA(cudaStreamWaitEvent(s1, done, 0));
+                MARLC_TRY(batched(t, chunk_hi, s, s1, s0));
+                chunk_hi = t;
+                --next_chunk;
+            }
         }
+        MARLC_TRY(e->chain(sw, s));
     } else
     for (int t = T - 1; t >= 0; --t) {
         if (t < T - 1) {
@@ -1108,90 +1266,8 @@ extern "C" int marlc_episode_backward(marlc_engine* e, const float* img, int acc
         e->last_launches = g_launch_count - start;
         return 0;
     }
-    // ---- weight gradients, batched over all T*M rows (reduction dim T*M).  Three independent
-    //      branches: LSTM (main stream) | encoder / decoder / position features (side 1) |
-    //      feature extractor (side 0, after its per-step backward chunks)
-    const bool par = c.use_chains != 0;
-    cudaStream_t s1 = par ? e->side[1] : s, s0 = par ? e->side[0] : s;
-    if (par) MARLC_TRY(e->chain(s, s1));
-    for (int k = 0; k < 2; ++k) {
-        const std::string pre = k ? LSTM_A : LSTM_B;
-        const int n = k ? c.n_a : c.n_b;
-        const float* dg = e->buf(k ? "dgates_a" : "dgates_b");
-        MARLC_TRY(G_tn(e, dg, 4 * n, e->buf("U"), Kin, e->grd(pre + "weight_ih"), Kin, TM, 4 * n, Kin, s));
-        MARLC_TRY(G_tn(e, dg, 4 * n, k ? Hc : H, n, e->grd(pre + "weight_hh"), n, TM, 4 * n, n, s));
-        MARLC_TRY(colsum_add(dg, 4 * n, e->grd(pre + "bias_ih"), TM, 4 * n, s));
-        MARLC_TRY(colsum_add(dg, 4 * n, e->grd(pre + "bias_hh"), TM, 4 * n, s));
-    }
-    if (T > 1) {
-        const int R = (T - 1) * M;  // the last message is never consumed
-        MARLC_TRY(G_tn(e, e->buf("d_enc_y2"), c.n_m, e->buf("enc_s1"), 2 * c.n_m, e->grd("encode_msg.3.weight"),
-                       2 * c.n_m, R, c.n_m, 2 * c.n_m, s1));
-        MARLC_TRY(G_tn(e, e->buf("d_enc_y1"), 2 * c.n_m, H + (size_t)M * c.n_b, c.n_b, e->grd("encode_msg.0.weight"),
-                       c.n_b, R, 2 * c.n_m, c.n_b, s1));
-    }
-    MARLC_TRY(G_tn(e, e->buf("d_dec_y2"), c.n_m_o, e->buf("dec_s1"), 2 * c.n_m, e->grd("decode_msg.3.weight"),
-                   2 * c.n_m, TM, c.n_m_o, 2 * c.n_m, s1));
-    MARLC_TRY(G_tn(e, e->buf("d_dec_y1"), 2 * c.n_m, e->buf("coll"), c.n_m, e->grd("decode_msg.0.weight"), c.n_m, TM,
-                   2 * c.n_m, c.n_m, s1));
-    // position features (state.py:13-17)
-    MARLC_TRY(block_bwd_norm(e, "map_pos", 0, dU + F + c.n_m_o, Kin, e->buf("pos_y"), TM, c.n_d, e->buf("d_pos_y"), s1));
-    MARLC_TRY(G_tn(e, e->buf("d_pos_y"), c.n_d, e->buf("npos"), 2, e->grd("map_pos.0.weight"), 2, TM, c.n_d, 2, s1));
-    // feature extractor: layer-wise, batched over all T*M windows (cnn_bwd2.cu); every conv product
-    // (input gradient dCol_l = dY_l W_l, weight gradient dW_l = dY_l^T col_l) is a tensor-core GEMM
-    {
-        const CnnDesc& d = e->cnn;
-        const float* ysave[MAX_CNN_LAYERS];
-        CnnBwdBuffers bb;
-        float* dcol[MAX_CNN_LAYERS] = {nullptr};
-        for (int l = 0; l < e->L; ++l) {
-            ysave[l] = e->buf("cnn_y" + std::to_string(l));
-            bb.dY[l] = e->buf("cnn_dY" + std::to_string(l));
-            bb.col[l] = e->buf("cnn_col" + std::to_string(l));
-            bb.gnpart[l] = e->buf("cnn_gnpart" + std::to_string(l));
-            if (l > 0) dcol[l] = e->buf("cnn_dcol" + std::to_string(l));
-        }
-        auto weight_grads = [&](int l) -> int {
-            const int npos = d.hout[l] * d.hout[l], kk = d.cin[l] * 9, co = d.cout[l];
-            const std::string cw = CNN_PREFIX + std::to_string(3 * l), gn = CNN_PREFIX + std::to_string(3 * l + 1);
-            MARLC_TRY(G_tn(e, bb.dY[l], co, bb.col[l], kk, e->grd(cw + ".weight"), kk, TM * npos, co, kk, s0));
-            MARLC_TRY(colsum_add(bb.dY[l], co, e->grd(cw + ".bias"), TM * npos, co, s0));
-            MARLC_TRY(colsum_add(bb.gnpart[l], 2 * co, e->grd(gn + ".weight"), TM, co, s0));
-            MARLC_TRY(colsum_add(bb.gnpart[l] + co, 2 * co, e->grd(gn + ".bias"), TM, co, s0));
-            return 0;
-        };
-        if (!par) {
-            MARLC_TRY(cnn_bwd(e->cnn, img, e->buf<int>("pos_hist"), c.nb, c.H, c.W, M, 0, TM, ysave, dU, Kin, bb, s0));
-            for (int l = 0; l < e->L; ++l) MARLC_TRY(weight_grads(l));
-        } else {
-            MARLC_TRY(e->chain(s, s0));
-            for (int l = e->L - 1; l >= 0; --l) {
-                CnnBwdLayerArgs la;
-                memset(&la, 0, sizeof(la));
-                la.cout = d.cout[l]; la.ho = d.hout[l]; la.groups = d.groups[l]; la.P = TM;
-                la.Y = ysave[l]; la.gn_w = d.gn_w[l]; la.gn_b = d.gn_b[l];
-                const bool top = (l == e->L - 1);
-                la.dOut = top ? dU : nullptr; la.lddo = Kin;
-                la.dColNext = top ? nullptr : dcol[l + 1];
-                la.ho_next = top ? 1 : d.hout[l + 1];
-                la.dY = bb.dY[l]; la.gnpart = bb.gnpart[l];
-                la.colNext = top ? nullptr : bb.col[l + 1];
-                MARLC_TRY(cnn_bwd_layer(la, s0));
-                if (!top) MARLC_TRY(weight_grads(l + 1));  // col_{l+1} is now available
-                if (l > 0) {
-                    const int npos = d.hout[l] * d.hout[l], kk = d.cin[l] * 9;
-                    MARLC_TRY(G_nn_on(e, bb.dY[l], d.cout[l], d.w[l], kk, dcol[l], kk, TM * npos, d.cout[l], kk, s0));
-                }
-            }
-            MARLC_TRY(cnn_im2col_input(img, e->buf<int>("pos_hist"), bb.col[0], TM, M, c.nb, c.C, d.cin[0], c.H, c.W,
-                                       c.f, d.hout[0], s0));
-            MARLC_TRY(weight_grads(0));
-        }
-    }
-    if (par) {  // join
-        MARLC_TRY(e->chain(s0, s));
-        MARLC_TRY(e->chain(s1, s));
-    }
+    if (!par) MARLC_TRY(batched(0, T, s, s, s));
+    if (par) MARLC_TRY(join_sides());
     e->last_launches = g_launch_count - start;
     return 0;
 }

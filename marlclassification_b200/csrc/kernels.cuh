@@ -89,7 +89,11 @@ struct CnnBwdLayerArgs {
     const float* dColNext;  // other layers: dCol of layer l+1, [P*ho_next^2, cout*9]
     int ho_next;
     float* dY;              // out [P*ho*ho, cout]
-    float* gnpart;          // out [P, 2*cout]
+    float* gnpart;          // out [P, 2*cout] per-window GroupNorm affine partials, or nullptr when the
+                            // three gradients below are accumulated by the kernel itself
+    float* d_gn_w;          // += sum over windows (atomicAdd, one per channel per CTA)
+    float* d_gn_b;
+    float* d_conv_b;        // += sum over windows and positions of dY
     float* colNext;         // out im2col of this layer's activation for layer l+1 (nullptr for the top layer)
 };
 int cnn_bwd_layer(const CnnBwdLayerArgs& a, cudaStream_t s);

@@ -270,8 +270,8 @@ int ln_silu_bwd(const float* dS, long ldds, const float* Y, long ldy, const floa
 // ---------------------------------------------------------------------------
 // out[n] += sum_r X[r,n]   (bias gradients)
 // ---------------------------------------------------------------------------
-__global__ void colsum_kernel(const float* __restrict__ X, long ldx, float* __restrict__ out, int R, int N,
-                              int rows_per_block) {
+__global__ void colsum_kernel(const float* __restrict__ X, long ldx, float* __restrict__ out, float* __restrict__ out2,
+                              int R, int N, int rows_per_block) {
     __shared__ float red[8][33];
     const int n = blockIdx.x * 32 + threadIdx.x;
     const int r0 = blockIdx.y * rows_per_block, r1 = min(R, r0 + rows_per_block);
@@ -285,15 +285,19 @@ __global__ void colsum_kernel(const float* __restrict__ X, long ldx, float* __re
 #pragma unroll
         for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
         atomicAdd(&out[n], t);
+        if (out2) atomicAdd(&out2[n], t);  // e.g. bias_ih and bias_hh of an LSTM cell share their gradient
     }
 }
 
 int colsum_add(const float* X, long ldx, float* out, int R, int N, cudaStream_t s) {
+    return colsum_add2(X, ldx, out, nullptr, R, N, s);
+}
+int colsum_add2(const float* X, long ldx, float* out, float* out2, int R, int N, cudaStream_t s) {
     if (R <= 0 || N <= 0) return 0;
     int gy = max(1, min((R + 63) / 64, 128));
     int rpb = (R + gy - 1) / gy;
     dim3 grid((N + 31) / 32, gy);
-    colsum_kernel<<<grid, dim3(32, 8), 0, s>>>(X, ldx, out, R, N, rpb);
+    colsum_kernel<<<grid, dim3(32, 8), 0, s>>>(X, ldx, out, out2, R, N, rpb);
     MARLC_LAUNCH_CHECK();
     return 0;
 }

