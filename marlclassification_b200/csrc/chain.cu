@@ -360,31 +360,89 @@ int step_pre(const StepPreArgs& a, cudaStream_t s) {
 // ---------------------------------------------------------------------------------
 constexpr int MAX_ACT = 16;
 
-__device__ void policy_tail_row(const StepPostArgs& a, const int m, float* srow /* smem [nl] */) {
+// One warp per row.  Every global operand of the row (pre-norm activations, LayerNorm affine, the
+// nb_action rows of the final Linear) is requested up front into registers, so the row pays ONE
+// exposed memory round trip instead of one per pass (measured: the serial version spent 40 % of
+// its samples waiting on these loads).  NCOL = ceil(nl / 32) columns per lane, <= 16.
+template <int NCOL>
+__device__ __forceinline__ void policy_logits_regs(const StepPostArgs& a, const int m, float* logit) {
     const PolicyActArgs& p = a.act;
     const int lane = threadIdx.x & 31, nl = p.nl;
     const float* y = a.pol_y1 + (long)m * nl;
+    float yv[NCOL], gv[NCOL], bv[NCOL];
+#pragma unroll
+    for (int i = 0; i < NCOL; ++i) {
+        const int k = lane + 32 * i;
+        const bool ok = k < nl;
+        yv[i] = ok ? y[k] : 0.f;
+        gv[i] = ok ? a.pol_g[k] : 0.f;
+        bv[i] = ok ? a.pol_be[k] : 0.f;
+    }
     const float inv = 1.0f / (float)nl;
     float s = 0.f;
-    for (int k = lane; k < nl; k += 32) s += y[k];
+#pragma unroll
+    for (int i = 0; i < NCOL; ++i) s += yv[i];
     const float mean = warp_sum(s) * inv;
     float v = 0.f;
-    for (int k = lane; k < nl; k += 32) { const float d = y[k] - mean; v += d * d; }
+#pragma unroll
+    for (int i = 0; i < NCOL; ++i)
+        if (lane + 32 * i < nl) { const float d = yv[i] - mean; v += d * d; }
     const float rstd = 1.0f / sqrtf(warp_sum(v) * inv + LN_EPS_C);
     float* s1 = const_cast<float*>(p.s1) + (long)m * nl;
-    for (int k = lane; k < nl; k += 32) {
-        const float o = siluf_((y[k] - mean) * rstd * a.pol_g[k] + a.pol_be[k]);
-        s1[k] = o;      // saved for the batched weight gradient of policy.3
-        srow[k] = o;
+#pragma unroll
+    for (int i = 0; i < NCOL; ++i) {
+        const int k = lane + 32 * i;
+        yv[i] = (k < nl) ? siluf_((yv[i] - mean) * rstd * gv[i] + bv[i]) : 0.f;
+        if (k < nl) s1[k] = yv[i];  // saved for the batched weight gradient of policy.3
     }
-    __syncwarp();
+    for (int j0 = 0; j0 < p.nA; j0 += 4) {  // four rows of W3 in flight at a time
+        float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            if (j0 + jj < p.nA) {
+                const float* w = p.W3 + (long)(j0 + jj) * nl;
+#pragma unroll
+                for (int i = 0; i < NCOL; ++i)
+                    if (lane + 32 * i < nl) d[jj] = fmaf(yv[i], __ldg(w + lane + 32 * i), d[jj]);
+            }
+        }
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+            if (j0 + jj < p.nA) logit[j0 + jj] = warp_sum(d[jj]) + p.b3[j0 + jj];
+    }
+}
+
+__device__ void policy_tail_row(const StepPostArgs& a, const int m, float* srow /* smem [nl] */) {
+    const PolicyActArgs& p = a.act;
+    const int lane = threadIdx.x & 31, nl = p.nl;
     float logit[MAX_ACT];
+    if (nl <= 128) policy_logits_regs<4>(a, m, logit);
+    else if (nl <= 256) policy_logits_regs<8>(a, m, logit);
+    else if (nl <= 384) policy_logits_regs<12>(a, m, logit);
+    else if (nl <= 512) policy_logits_regs<16>(a, m, logit);
+    else {
+        const float* y = a.pol_y1 + (long)m * nl;
+        const float inv = 1.0f / (float)nl;
+        float s = 0.f;
+        for (int k = lane; k < nl; k += 32) s += y[k];
+        const float mean = warp_sum(s) * inv;
+        float v = 0.f;
+        for (int k = lane; k < nl; k += 32) { const float d = y[k] - mean; v += d * d; }
+        const float rstd = 1.0f / sqrtf(warp_sum(v) * inv + LN_EPS_C);
+        float* s1 = const_cast<float*>(p.s1) + (long)m * nl;
+        for (int k = lane; k < nl; k += 32) {
+            const float o = siluf_((y[k] - mean) * rstd * a.pol_g[k] + a.pol_be[k]);
+            s1[k] = o;      // saved for the batched weight gradient of policy.3
+            srow[k] = o;
+        }
+        __syncwarp();
 #pragma unroll 1
-    for (int j = 0; j < p.nA; ++j) {
-        const float* w = p.W3 + (long)j * nl;
-        float d = 0.f;
-        for (int k = lane; k < nl; k += 32) d = fmaf(srow[k], w[k], d);
-        logit[j] = warp_sum(d) + p.b3[j];
+        for (int j = 0; j < p.nA; ++j) {
+            const float* w = p.W3 + (long)j * nl;
+            float d = 0.f;
+            for (int k = lane; k < nl; k += 32) d = fmaf(srow[k], w[k], d);
+            logit[j] = warp_sum(d) + p.b3[j];
+        }
     }
     float mx = -INFINITY;
     for (int j = 0; j < p.nA; ++j) mx = fmaxf(mx, logit[j]);

@@ -66,6 +66,21 @@ static int make_map(CUtensorMap* m, const float* ptr, long inner, long rows, lon
     return 0;
 }
 
+// 2-D map over C[M][N] (row stride ldc) for the epilogue's TMA store / reduce-add: box 32 cols x 32 rows
+// (one TMEM lane quarter x one 128-byte swizzle row); out-of-range rows / columns are clipped by TMA
+static int make_map_c(CUtensorMap* m, float* C, long M, long N, long ldc) {
+    EncodeTiledFn enc = get_encode();
+    MARLC_CHECK(enc, "cuTensorMapEncodeTiled not available");
+    cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M};
+    cuuint64_t strides[1] = {(cuuint64_t)ldc * 4};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)C, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MARLC_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (C) failed (%d): ptr=%p M=%ld N=%ld ldc=%ld", (int)r, (void*)C, M, N, ldc);
+    return 0;
+}
+
 bool tc_operand_ok(const TcOperand& o) {
     return o.ptr && (((uintptr_t)o.ptr & 15) == 0) && (o.ld % 4 == 0) && (o.slab_stride % 4 == 0);
 }
@@ -124,6 +139,17 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), \
                    "=r"(r[7])                                                                         \
                  : "r"(addr))
+#define TMEM_LD32(addr, r)                                                                                  \
+    asm volatile(                                                                                          \
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                          \
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"                                          \
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"                         \
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),  \
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),         \
+          "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),       \
+          "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),       \
+          "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                                                            \
+        : "r"(addr))
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // MUFU-based activations for the tensor-core epilogue (abs error ~1e-7, far below TF32's)
@@ -149,6 +175,8 @@ struct TcKernelParams {
     // fetched by TMA into the lo ring, so no CTA has to split them (at small M every CTA of a
     // launch would otherwise re-split the same A tiles)
     CUtensorMap a1l, b1l, a2l, b2l;
+    CUtensorMap cmap;            // EPI_STORE: C as [M rows][N cols], box 32 x 32, 128B swizzle (TMA store / reduce)
+    int c_tma;                   // 1: cmap is valid (C 16-byte aligned, ldc % 4 == 0)
     int a_lo_g, b_lo_g;          // 1: the lo part of A / B comes from global memory
     int nk1, nk2;                // K blocks of each pair
     int slab_a1, slab_b1, slab_a2, slab_b2;
@@ -211,9 +239,18 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
     __shared__ __align__(8) uint64_t split_bar[STAGES];
     __shared__ __align__(8) uint64_t tmem_full_bar;
     __shared__ uint32_t tmem_base_smem;
+    __shared__ float s_bias[4][BN];  // per epilogue warp: bias (+ bias2) of this tile's columns
 
     const TcKernelParams& p = pp.p[PI];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef MARLC_TC_TRACE  // in-kernel timeline of CTA (0,0,0): cycles since entry at each pipeline event
+    __shared__ long long trace[8];
+    const bool tr = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+    const long long t_entry = clock64();
+#define TC_TRACE(i) do { if (tr) trace[i] = clock64() - t_entry; } while (0)
+#else
+#define TC_TRACE(i) do { } while (0)
+#endif
     const int m0 = blockIdx.y * BM;
     const int n_tile = blockIdx.x;
     if (m0 >= p.M || n_tile * BN >= p.N) return;  // grid is sized for the largest problem of the group
@@ -228,7 +265,15 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
     const int my_kb = max(0, kb_end - kb_begin);
     constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
 
-    if (threadIdx.x == 0) {
+    if (warp == 0 && lane == 0) {  // descriptor fetch overlaps barrier init / TMEM allocation
+        auto pf = [](const CUtensorMap* m) { asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)m) : "memory"); };
+        pf(&p.a1); pf(&p.b1);
+        if (p.nk2 > 0) { pf(&p.a2); pf(&p.b2); }
+        if (X3 && p.a_lo_g) { pf(&p.a1l); if (p.nk2 > 0) pf(&p.a2l); }
+        if (X3 && p.b_lo_g) { pf(&p.b1l); if (p.nk2 > 0) pf(&p.b2l); }
+        if (EPI == EPI_STORE && p.c_tma) pf(&p.cmap);
+    }
+    if (threadIdx.x == 32) {
         for (int s = 0; s < stages; ++s) {
             mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1);
             mbar_init(&split_bar[s], TC_SPLITTERS / 2);  // one of the two splitter groups
@@ -245,6 +290,7 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
+    if (threadIdx.x == 0) TC_TRACE(0);  // setup done (barriers, TMEM)
 
     if (warp == 0) {
         // ============================ TMA producer ============================
@@ -287,6 +333,7 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
                     }
                 }
                 }
+                if (i == 0) TC_TRACE(1);  // first stage's TMA issued
             }
         }
     } else if (warp == 1) {
@@ -298,6 +345,7 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
                 const int s = i % stages, ph = (i / stages) & 1;
                 mbar_wait((X3 && !(p.a_lo_g && p.b_lo_g)) ? &split_bar[s] : &full_bar[s], ph);
                 tc_fence_after();
+                if (i == 0) TC_TRACE(2);  // first stage landed (and split)
 #pragma unroll
                 for (int sub = 0; sub < KS; ++sub) {
                 const uint32_t a_addr = smem_u32(sA + s * S::A_BYTES + sub * S::A_SUB);
@@ -320,11 +368,47 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
                 umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs retire
             }
             umma_commit(&tmem_full_bar);
+            TC_TRACE(3);  // last MMA issued
         }
     } else {
         // ============================ epilogue (warps 2..5) ============================
         const int q = warp & 3;  // TMEM lane quarter this warp may touch
         const int m = m0 + 32 * q + lane;
+        // Everything the epilogue needs from global memory is requested BEFORE the main loop ends:
+        // the tile's bias values go to shared memory (one copy per warp, so a __syncwarp suffices) and
+        // the LSTM cell's c_prev to registers.  Loading them after the accumulator wait cost one
+        // exposed L2 round trip per 8-column chunk (~2 us of a 4.7 us launch, in-kernel trace).
+        float cp_pref[8];
+        if (warp < 6) {
+            float* sb = s_bias[q];
+            if (EPI == EPI_STORE) {
+                const bool first_split0 = (p.splits <= 1) || (split == 0);
+                for (int j = lane; j < BN; j += 32) {
+                    const int n = n_tile * BN + j;
+                    float b = 0.f;
+                    if (first_split0 && n < p.N) {
+                        if (p.bias) b += __ldg(p.bias + n);
+                        if (p.bias2) b += __ldg(p.bias2 + n);
+                    }
+                    sb[j] = b;
+                }
+            } else {
+                constexpr int HU = BN / 4;
+                const int n = p.n_hidden, j0 = n_tile * HU;
+                for (int j = lane; j < BN; j += 32) {
+                    const int g = j / HU, col = g * n + j0 + (j - g * HU);
+                    sb[j] = __ldg(p.bias + col) + __ldg(p.bias2 + col);
+                }
+                if (m < p.M) {
+                    const long off = (long)m * n + j0;
+                    const float4 c0 = *reinterpret_cast<const float4*>(p.c_prev + off);
+                    const float4 c1 = *reinterpret_cast<const float4*>(p.c_prev + off + 4);
+                    cp_pref[0] = c0.x; cp_pref[1] = c0.y; cp_pref[2] = c0.z; cp_pref[3] = c0.w;
+                    cp_pref[4] = c1.x; cp_pref[5] = c1.y; cp_pref[6] = c1.z; cp_pref[7] = c1.w;
+                }
+            }
+            __syncwarp();
+        }
         if (X3) {
             // ---- operand splitter: lo = x - trunc_tf32(x) for every landed stage
             // two groups of 4 warps take alternate K blocks, so one group's barrier wake-up / proxy
@@ -355,55 +439,139 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
             }
         }
         if (warp < 6) {  // warps 2..5 own the four TMEM lane quarters
+        // Epilogue parameters are pulled into registers NOW (and made opaque to the compiler, which
+        // would otherwise re-read them from the constant bank inside the store loop: the SASS had four
+        // dependent LDCU -> compare -> branch chains per row, ~250 cycles per iteration in the trace).
+        int e_M = p.M, e_N = p.N, e_mode = p.splits > 1 ? 2 : (p.accumulate ? 1 : 0);
+        long e_ldc = p.ldc;
+        float* e_C = p.C;
+        asm volatile("" : "+r"(e_M), "+r"(e_N), "+r"(e_mode), "+l"(e_ldc), "+l"(e_C));
         mbar_wait(&tmem_full_bar, 0);
         tc_fence_after();
+        if (warp == 2 && lane == 0) TC_TRACE(4);  // accumulators complete
         const uint32_t trow = tmem_base + ((uint32_t)(32 * q) << 16);
         if (EPI == EPI_STORE) {
+            // Accumulator tile -> shared memory (row per lane) -> global memory with ROW-coalesced 128-bit
+            // accesses.  Writing straight from the TMEM registers makes every store instruction touch 32
+            // different rows (one 16-byte piece each): the in-kernel trace showed 3700 cycles for a
+            // 128 x 64 tile, ~40 % of a small launch.  The pipeline ring is dead by now (every MMA has
+            // retired), so the staging tile reuses it.
+            constexpr int PITCH = BN + 4;  // 16-byte aligned rows, conflict-free for 128-bit accesses
+            static_assert(4 * 32 * PITCH * 4 <= S::BYTES - 1024, "epilogue staging tile does not fit in the ring");
+            float* stg = reinterpret_cast<float*>(smem) + q * 32 * PITCH;
             const int nbase = n_tile * BN;
-            const bool vec = ((p.ldc & 3) == 0) && (((uintptr_t)p.C & 15) == 0);
-            const bool first_split = (p.splits <= 1) || (split == 0);
-            // 8 columns per tcgen05.ld + wait: the stores of one chunk overlap the TMEM read of the
-            // next (a 32-column variant with one wait per 4 loads measured 3 us SLOWER per launch)
+            const bool vec = ((e_ldc & 3) == 0) && (((uintptr_t)e_C & 15) == 0);
+            if (p.c_tma) {
+                // TMA epilogue: the warp's 32 x BN accumulator slab goes to shared memory as BN/32 boxes of
+                // 32 rows x 128 bytes in the 128B-swizzled layout (conflict-free 128-bit stores: 16-byte
+                // chunk c of row r lands at chunk c ^ (r & 7)), and ONE elected lane hands each box to the
+                // TMA unit: a plain tensor store, or an f32 reduce-add when the launch accumulates into C
+                // or is one of several K splits.  Row / column tails are clipped by the TMA unit.  The
+                // per-row store loop below (kept for unaligned C) costs ~230 cycles per row per warp with
+                // one warp per scheduler (in-kernel trace): 3700-4200 cycles for a 128 x 64 tile.
+                constexpr int BOXES = BN / 32;
+                const uint32_t box0 = smem_u32(smem) + (uint32_t)(q * BOXES) * 4096u;
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 8) {
-                uint32_t r[8];
-                if (my_kb > 0) { TMEM_LD8(trow + c0, r); tmem_ld_wait(); }
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t r[32];
+                    if (my_kb > 0) { TMEM_LD32(trow + c0, r); tmem_ld_wait(); }
+                    else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) r[j] = 0u;
+                    }
+                    const float* sb = s_bias[q] + c0;
+                    const uint32_t rowb = box0 + (uint32_t)(c0 >> 5) * 4096u + (uint32_t)lane * 128u;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const uint32_t dst = rowb + (uint32_t)(((j >> 2) ^ (lane & 7)) << 4);
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst),
+                                     "f"(__uint_as_float(r[j]) + sb[j]), "f"(__uint_as_float(r[j + 1]) + sb[j + 1]),
+                                     "f"(__uint_as_float(r[j + 2]) + sb[j + 2]), "f"(__uint_as_float(r[j + 3]) + sb[j + 3])
+                                     : "memory");
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> TMA reads
+                __syncwarp();
+                if (warp == 2 && lane == 0) TC_TRACE(6);
+                if (lane == 0 && m0 + 32 * q < e_M) {
+#pragma unroll 1
+                    for (int b = 0; b < BOXES; ++b) {
+                        const int cn = nbase + 32 * b;
+                        if (cn >= e_N) break;
+                        const uint32_t src = box0 + (uint32_t)b * 4096u;
+                        if (e_mode == 0)
+                            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                                             (uint64_t)&p.cmap), "r"(src), "r"(cn), "r"(m0 + 32 * q) : "memory");
+                        else
+                            asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                                             (uint64_t)&p.cmap), "r"(src), "r"(cn), "r"(m0 + 32 * q) : "memory");
+                    }
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem must outlive the reads
+                }
+            } else {
+            const uint32_t stg_s = smem_u32(stg);  // explicit shared-space accesses (generic ones are slower)
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t r[32];
+                if (my_kb > 0) { TMEM_LD32(trow + c0, r); tmem_ld_wait(); }
                 else {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) r[j] = 0u;
+                    for (int j = 0; j < 32; ++j) r[j] = 0u;
                 }
-                if (m < p.M) {
-                    float v[8];
+                const float* sb = s_bias[q] + c0;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int n = nbase + c0 + j;
-                        v[j] = __uint_as_float(r[j]);
-                        if (first_split && n < p.N) {
-                            if (p.bias) v[j] += p.bias[n];
-                            if (p.bias2) v[j] += p.bias2[n];
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 v = make_float4(__uint_as_float(r[j]) + sb[j], __uint_as_float(r[j + 1]) + sb[j + 1],
+                                                 __uint_as_float(r[j + 2]) + sb[j + 2], __uint_as_float(r[j + 3]) + sb[j + 3]);
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg_s + (uint32_t)(lane * PITCH + c0 + j) * 4),
+                                 "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+                }
+            }
+            __syncwarp();
+            constexpr int LPR = BN / 4;    // lanes per row (one float4 each)
+            constexpr int RPI = 32 / LPR;  // rows per warp-wide instruction
+            const int rr = lane / LPR, c4 = (lane % LPR) * 4;
+            const int n = nbase + c4;
+            const bool full4 = vec && n + 4 <= e_N;
+            if (n < e_N) {
+#pragma unroll 1  // executed once per launch: keep the loop body short
+                for (int r0 = 0; r0 < 32; r0 += RPI) {
+                    const int row = r0 + rr, mrow = m0 + 32 * q + row;
+                    if (mrow >= e_M) break;  // rows grow with r0
+                    float4 v;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                                 : "r"(stg_s + (uint32_t)(row * PITCH + c4) * 4));
+                    float* crow = e_C + (long)mrow * e_ldc + n;
+#ifdef MARLC_TC_NOSTORE
+                    if (v.x == 123.456f) crow[0] = v.y;
+                    continue;
+#endif
+#ifdef MARLC_TC_TRACE
+                    if (warp == 2 && lane == 0 && r0 == RPI * 2) TC_TRACE(7);
+#endif
+                    if (full4) {
+                        if (e_mode == 2) {
+                            atomicAdd(reinterpret_cast<float4*>(crow), v);
+                        } else {
+                            if (e_mode == 1) {
+                                const float4 o = *reinterpret_cast<const float4*>(crow);
+                                v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+                            }
+                            *reinterpret_cast<float4*>(crow) = v;
                         }
-                    }
-                    float* crow = p.C + (long)m * p.ldc + nbase + c0;
-                    if (p.splits > 1) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            if (nbase + c0 + j < p.N) atomicAdd(crow + j, v[j]);
-                    } else if (vec && nbase + c0 + 8 <= p.N) {
-                        float4 lo = make_float4(v[0], v[1], v[2], v[3]), hi = make_float4(v[4], v[5], v[6], v[7]);
-                        if (p.accumulate) {
-                            const float4 o0 = *reinterpret_cast<float4*>(crow), o1 = *reinterpret_cast<float4*>(crow + 4);
-                            lo.x += o0.x; lo.y += o0.y; lo.z += o0.z; lo.w += o0.w;
-                            hi.x += o1.x; hi.y += o1.y; hi.z += o1.z; hi.w += o1.w;
-                        }
-                        *reinterpret_cast<float4*>(crow) = lo;
-                        *reinterpret_cast<float4*>(crow + 4) = hi;
                     } else {
+                        const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            if (nbase + c0 + j < p.N) crow[j] = p.accumulate ? crow[j] + v[j] : v[j];
+                        for (int j = 0; j < 4; ++j) {
+                            if (n + j >= e_N) break;
+                            if (e_mode == 2) atomicAdd(crow + j, vv[j]);
+                            else crow[j] = e_mode == 1 ? crow[j] + vv[j] : vv[j];
+                        }
                     }
                 }
             }
+            }  // !c_tma
         } else {
             // fused LSTM cell (recurrent.py:30): columns [g*HU + j] hold gate g of hidden unit j0 + j
             constexpr int HU = BN / 4;
@@ -418,17 +586,24 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
                 tmem_ld_wait();
                 if (m < p.M) {
                     const long off = (long)m * n + j0 + jb;
-                    const float4 cp0 = *reinterpret_cast<const float4*>(p.c_prev + off);
-                    const float4 cp1 = *reinterpret_cast<const float4*>(p.c_prev + off + 4);
-                    const float cp[8] = {cp0.x, cp0.y, cp0.z, cp0.w, cp1.x, cp1.y, cp1.z, cp1.w};
+                    float cp[8];
+                    if (jb == 0) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) cp[j] = cp_pref[j];
+                    } else {
+                        const float4 cp0 = *reinterpret_cast<const float4*>(p.c_prev + off);
+                        const float4 cp1 = *reinterpret_cast<const float4*>(p.c_prev + off + 4);
+                        cp[0] = cp0.x; cp[1] = cp0.y; cp[2] = cp0.z; cp[3] = cp0.w;
+                        cp[4] = cp1.x; cp[5] = cp1.y; cp[6] = cp1.z; cp[7] = cp1.w;
+                    }
+                    const float* sb = s_bias[q];
                     float gi[8], gf[8], gc[8], go[8], cn[8], hn[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const int col = j0 + jb + j;
-                        gi[j] = fast_sigmoid(__uint_as_float(ri[j]) + __ldg(p.bias + col) + __ldg(p.bias2 + col));
-                        gf[j] = fast_sigmoid(__uint_as_float(rf[j]) + __ldg(p.bias + n + col) + __ldg(p.bias2 + n + col));
-                        gc[j] = fast_tanh(__uint_as_float(rg[j]) + __ldg(p.bias + 2 * n + col) + __ldg(p.bias2 + 2 * n + col));
-                        go[j] = fast_sigmoid(__uint_as_float(ro[j]) + __ldg(p.bias + 3 * n + col) + __ldg(p.bias2 + 3 * n + col));
+                        gi[j] = fast_sigmoid(__uint_as_float(ri[j]) + sb[0 * HU + jb + j]);
+                        gf[j] = fast_sigmoid(__uint_as_float(rf[j]) + sb[1 * HU + jb + j]);
+                        gc[j] = fast_tanh(__uint_as_float(rg[j]) + sb[2 * HU + jb + j]);
+                        go[j] = fast_sigmoid(__uint_as_float(ro[j]) + sb[3 * HU + jb + j]);
                         cn[j] = gf[j] * cp[j] + gi[j] * gc[j];
                         hn[j] = go[j] * fast_tanh(cn[j]);
                     }
@@ -451,8 +626,15 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
         }
         }  // warp < 6
     }
+    if (warp == 2 && lane == 0) TC_TRACE(5);  // epilogue of warp 2 done
     tc_fence_before();
     __syncthreads();
+#ifdef MARLC_TC_TRACE
+    if (tr && threadIdx.x == 0)
+        printf("tc trace BN=%d X3=%d KS=%d EPI=%d kb=%d: setup %lld | tma0 %lld | full0 %lld | mma_issued %lld | acc_done %lld | epi_done %lld | end %lld\n",
+               BN, (int)X3, KS, EPI, my_kb, trace[0], trace[1], trace[2], trace[3], trace[4], trace[5], clock64() - t_entry);
+    if (tr && threadIdx.x == 0 && EPI == EPI_STORE) printf("   staged at %lld, third store iteration at %lld\n", trace[6], trace[7]);
+#endif
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
@@ -548,6 +730,8 @@ int tc_gemm_group(const TcGemmArgs* args, int count, cudaStream_t s) {
         }
         p.M = a.M; p.N = a.N; p.C = a.C; p.ldc = a.ldc; p.bias = a.bias; p.bias2 = a.bias2;
         p.accumulate = a.accumulate;
+        p.c_tma = ((a.ldc & 3) == 0 && ((uintptr_t)a.C & 15) == 0) ? 1 : 0;
+        if (p.c_tma) MARLC_TRY(make_map_c(&p.cmap, a.C, a.M, a.N, a.ldc));
         const int mt = (a.M + BM - 1) / BM, nt = (a.N + BN - 1) / BN, nkb = p.nk1 + p.nk2;
         int splits = 1;
         if (a.allow_split && ctas < MARLC_SMS) {
