@@ -91,6 +91,22 @@ def lstm_pair(M: int, Kin: int, n: int, dev, reps: int = 200, x3: int = 1) -> di
     def run():
         _lib.check(L.marlc_tc_lstm_pair(*args, _lib.stream_ptr(dev)))
 
+    if x3:
+        # what the episode engine launches per step: operands pre-split (weights once per forward,
+        # activations by their producer), so the kernel only streams tiles and issues 3 MMAs per K step
+        def lo_of(t):
+            out = torch.empty_like(t)
+            _lib.check(L.marlc_split_lo(t.data_ptr(), out.data_ptr(), t.numel(), _lib.stream_ptr(dev)))
+            return out
+
+        u_lo, hp_lo, wih_lo, whh_lo = lo_of(u), [lo_of(t) for t in hp], [lo_of(t) for t in wih], [lo_of(t) for t in whh]
+        hn_lo = [torch.empty(M, n, device=dev) for _ in range(2)]
+        pargs = (u.data_ptr(), u_lo.data_ptr(), M, Kin, n, arr(hp), arr(hp_lo), arr(cp), arr(wih), arr(wih_lo), arr(whh),
+                 arr(whh_lo), arr(bih), arr(bhh), arr(cn), arr(hn), arr(hn_lo), arr(gates))
+
+        def run():  # noqa: F811
+            _lib.check(L.marlc_tc_lstm_pair_presplit(*pargs, _lib.stream_ptr(dev)))
+
     t = _time(run, reps)
     flops = 2.0 * M * (Kin + n) * 4 * n * 2  # both cells (lstm = 2(K_in+n)4n per row per cell)
     bytes_min = 4.0 * (M * Kin + 2 * M * n * 2 + 2 * 4 * n * (Kin + n) + 2 * M * 6 * n)

@@ -77,6 +77,17 @@ int marlc_tc_lstm_pair(const float* u, int M, int Kin, int n, const float* const
                        const float* const* b_hh, float* const* c_new, float* const* h_new, float* const* gates,
                        int x3, void* stream);
 
+/* Error-compensated 3xTF32 with PRE-SPLIT operands (what the episode engine runs per step): every
+ * operand comes with its low-order part lo = x - trunc_tf32(x) in a second array of the same
+ * layout, produced by marlc_split_lo (weights, once per forward) or by the kernel that wrote the
+ * operand (h_new_lo here).  The tensor core then needs no in-kernel splitting pass. */
+int marlc_split_lo(const float* x, float* lo, int64_t n, void* stream);
+int marlc_tc_lstm_pair_presplit(const float* u, const float* u_lo, int M, int Kin, int n, const float* const* h_prev,
+                                const float* const* h_prev_lo, const float* const* c_prev, const float* const* w_ih,
+                                const float* const* w_ih_lo, const float* const* w_hh, const float* const* w_hh_lo,
+                                const float* const* b_ih, const float* const* b_hh, float* const* c_new,
+                                float* const* h_new, float* const* h_new_lo, float* const* gates, void* stream);
+
 /* _Generic2dCnnModule.forward, vision.py:47-49: k x [conv3x3 s2 p1 -> GroupNorm ->
  * SiLU] -> flatten on N stand-alone windows patch f32[N,img_c,f,f] (the first
  * cin[0] channels are read) -> out f32[N, cout[k-1]*h_k^2].  w/b/gn_w/gn_b are

@@ -44,6 +44,8 @@ _SIGS = {
     "marlc_tc_gemm": (C.c_int, [_P, C.c_int64, C.c_int, _P, C.c_int64, C.c_int, _P, C.c_int64, _P, C.c_int64, C.c_int, _P,
                                 _P, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "marlc_tc_lstm_pair": (C.c_int, [_P, C.c_int, C.c_int, C.c_int] + [C.POINTER(_P)] * 9 + [C.c_int, _P]),
+    "marlc_split_lo": (C.c_int, [_P, _P, C.c_int64, _P]),
+    "marlc_tc_lstm_pair_presplit": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int] + [C.POINTER(_P)] * 13 + [_P]),
     "marlc_cnn_forward": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.c_int,
                                     C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), _P, _P, C.c_int, _P]),
     "marlc_engine_create": (C.c_int, [C.POINTER(MarlcConfig), C.POINTER(_P)]),

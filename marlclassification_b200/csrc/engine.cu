@@ -104,6 +104,10 @@ struct marlc_engine {
     // activations next to where they are produced.  lo_of(p) is the lo twin of a pointer into the
     // parameter block / H / Hc / U / dgates history, or nullptr (the GEMM then splits in-kernel).
     bool lo_on = false;
+    // H_lo / Hc_lo are written by the fused tensor-core LSTM epilogue only; when a step falls back to
+    // the FFMA gate GEMMs + point-wise cell (n_a != n_b, shapes TMA cannot address) they are NOT
+    // maintained and must not be offered as operands (a stale lo silently degrades 3xTF32 to TF32)
+    bool h_lo_ok = false;
     const float* lo_of(const float* p) const {
         if (!lo_on || !p) return nullptr;
         struct R { const float* base; size_t n; const float* lo; };
@@ -112,8 +116,11 @@ struct marlc_engine {
                        {buf("H"), T1 * Ms * cfg.n_b, buf("H_lo")},
                        {buf("Hc"), T1 * Ms * cfg.n_a, buf("Hc_lo")}
                        };
-        for (const R& q : r)
+        for (int i = 0; i < 3; ++i) {
+            const R& q = r[i];
+            if (i > 0 && !h_lo_ok) break;
             if (q.lo && p >= q.base && p < q.base + q.n) return q.lo + (p - q.base);
+        }
         return nullptr;
     }
     TcOperand op(const float* p, long ld, bool mn = false) const {
@@ -398,8 +405,9 @@ static int refresh_lo(marlc_engine* e, const float* h0, const float* hc0, cudaSt
     if (!e->lo_on) return 0;
     SplitLoArgs a;
     a.src[0] = e->P; a.dst[0] = e->buf("params_lo"); a.n[0] = e->param_floats;  // slots are multiples of 64 floats
-    a.src[1] = h0; a.dst[1] = const_cast<float*>(e->lo_of(h0)); a.n[1] = (h0 && a.dst[1]) ? (long)e->M * e->cfg.n_b : 0;
-    a.src[2] = hc0; a.dst[2] = const_cast<float*>(e->lo_of(hc0)); a.n[2] = (hc0 && a.dst[2]) ? (long)e->M * e->cfg.n_a : 0;
+    // (slot 0 of the histories: always refreshed, whether or not the LSTM launch ends up consuming it)
+    a.src[1] = h0; a.dst[1] = h0 ? e->buf("H_lo") + (h0 - e->buf("H")) : nullptr; a.n[1] = h0 ? (long)e->M * e->cfg.n_b : 0;
+    a.src[2] = hc0; a.dst[2] = hc0 ? e->buf("Hc_lo") + (hc0 - e->buf("Hc")) : nullptr; a.n[2] = hc0 ? (long)e->M * e->cfg.n_a : 0;
     split_lo_kernel<<<dim3(296, 3), 256, 0, s>>>(a);
     MARLC_LAUNCH_CHECK();
     return 0;
@@ -557,24 +565,30 @@ static int step_networks(marlc_engine* e, int t, const float* img, const int* po
             const int n = k ? c.n_a : c.n_b;
             TcLstmArgs& a = la[k];
             a.U = tc_op(Ut, Kin);
-            a.U.lo = (e->lo_on && c.use_chains) ? e->buf("U_lo") : nullptr;
-            a.Hprev = e->op(k ? hc_in : h_in, n);
+            a.Hprev = tc_op(k ? hc_in : h_in, n);
             a.Wih = e->prm(pre + "weight_ih"); a.Whh = e->prm(pre + "weight_hh");
-            a.Wih_lo = e->lo_of(a.Wih); a.Whh_lo = e->lo_of(a.Whh);
             a.bih = e->prm(pre + "bias_ih"); a.bhh = e->prm(pre + "bias_hh");
             a.c_prev = k ? cc_in : c_in;
             a.c_new = (k ? Cc : Cb) + (size_t)(t + 1) * M * n;
             a.h_new = (k ? Hc : H) + (size_t)(t + 1) * M * n;
-            a.h_new_lo = const_cast<float*>(e->lo_of(a.h_new));
             a.gates = k ? ga : gb;
             a.M = M; a.Kin = Kin; a.n = n;
             a.x3 = x3_of(e);
         }
-        if (tc_lstm_supported(la[0]) && tc_lstm_supported(la[1])) {
+        fused = tc_lstm_supported(la[0]) && tc_lstm_supported(la[1]);
+        e->h_lo_ok = fused && e->lo_on;  // decided BEFORE the lo twins below are looked up
+        if (fused) {
+            for (int k = 0; k < 2; ++k) {  // pre-split low-order operands (3xTF32 without an in-kernel split)
+                TcLstmArgs& a = la[k];
+                a.U.lo = e->lo_on ? e->buf("U_lo") : nullptr;
+                a.Hprev.lo = e->lo_of(a.Hprev.ptr);
+                a.Wih_lo = e->lo_of(a.Wih); a.Whh_lo = e->lo_of(a.Whh);
+                a.h_new_lo = const_cast<float*>(e->lo_of(a.h_new));
+            }
             MARLC_TRY(tc_lstm_pair(la[0], la[1], s));
-            fused = true;
         }
     }
+    if (!fused) e->h_lo_ok = false;
     if (!fused) {
         GemmGroup gg;
         memset(&gg, 0, sizeof(gg));
@@ -1348,6 +1362,39 @@ extern "C" int marlc_tc_lstm_pair(const float* u, int M, int Kin, int n, const f
         a.Wih = w_ih[k]; a.Whh = w_hh[k]; a.bih = b_ih[k]; a.bhh = b_hh[k];
         a.c_prev = c_prev[k]; a.c_new = c_new[k]; a.h_new = h_new[k]; a.gates = gates[k];
         a.M = M; a.Kin = Kin; a.n = n; a.x3 = x3;
+    }
+    return tc_lstm_pair(la[0], la[1], (cudaStream_t)stream);
+}
+
+extern "C" int marlc_split_lo(const float* x, float* lo, int64_t n, void* stream) {
+    MARLC_CHECK(x && lo && n >= 0, "split_lo: bad argument");
+    if (n == 0) return 0;
+    SplitLoArgs a;
+    memset(&a, 0, sizeof(a));
+    a.src[0] = x; a.dst[0] = lo; a.n[0] = n;
+    MARLC_CHECK((((uintptr_t)x | (uintptr_t)lo) & 15) == 0, "split_lo: buffers must be 16-byte aligned");
+    split_lo_kernel<<<dim3((unsigned)std::max<int64_t>(1, std::min<int64_t>(296, (n / 4 + 255) / 256)), 1), 256, 0, (cudaStream_t)stream>>>(a);
+    MARLC_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int marlc_tc_lstm_pair_presplit(const float* u, const float* u_lo, int M, int Kin, int n,
+                                           const float* const* h_prev, const float* const* h_prev_lo,
+                                           const float* const* c_prev, const float* const* w_ih,
+                                           const float* const* w_ih_lo, const float* const* w_hh,
+                                           const float* const* w_hh_lo, const float* const* b_ih,
+                                           const float* const* b_hh, float* const* c_new, float* const* h_new,
+                                           float* const* h_new_lo, float* const* gates, void* stream) {
+    TcLstmArgs la[2];
+    for (int k = 0; k < 2; ++k) {
+        TcLstmArgs& a = la[k];
+        a.U = tc_op(u, Kin); a.U.lo = u_lo;
+        a.Hprev = tc_op(h_prev[k], n); a.Hprev.lo = h_prev_lo[k];
+        a.Wih = w_ih[k]; a.Whh = w_hh[k]; a.Wih_lo = w_ih_lo[k]; a.Whh_lo = w_hh_lo[k];
+        a.bih = b_ih[k]; a.bhh = b_hh[k];
+        a.c_prev = c_prev[k]; a.c_new = c_new[k]; a.h_new = h_new[k]; a.h_new_lo = h_new_lo ? h_new_lo[k] : nullptr;
+        a.gates = gates[k];
+        a.M = M; a.Kin = Kin; a.n = n; a.x3 = 1;
     }
     return tc_lstm_pair(la[0], la[1], (cudaStream_t)stream);
 }

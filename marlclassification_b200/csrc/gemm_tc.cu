@@ -49,12 +49,12 @@ static EncodeTiledFn get_encode() {
 // mn_major operands use the 32B-atom variant of the 128B swizzle: the only shared-memory
 // layout tcgen05 accepts for MN-major TF32 (UMMA layout type SWIZZLE_128B_BASE32B)
 static int make_map(CUtensorMap* m, const float* ptr, long inner, long rows, long slabs, long ld, long slab_stride,
-                    int box_rows, bool mn_major = false) {
+                    int box_rows, bool mn_major = false, int box_slabs = 1) {
     EncodeTiledFn enc = get_encode();
     MARLC_CHECK(enc, "cuTensorMapEncodeTiled not available");
     cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)slabs};
     cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)(slabs > 1 ? slab_stride : rows * ld) * 4};
-    cuuint32_t box[3] = {32, (cuuint32_t)box_rows, 1};
+    cuuint32_t box[3] = {32, (cuuint32_t)box_rows, (cuuint32_t)box_slabs};
     cuuint32_t es[3] = {1, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)ptr, dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -322,9 +322,9 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
                     if (!do_b) continue;
                     if (EPI == EPI_LSTM) {
                         // gather the 4 gate row-blocks of HU hidden units: rows g*n + j0 .. +HU
+                        // one box {32 floats of K, HU units, 4 gates} of the [gate][unit][K] weight view
                         constexpr int HU = BN / 4;
-                        for (int g = 0; g < 4; ++g)
-                            tma_load_3d(b_dst + g * HU * 128, mb, &full_bar[s], k0, g * p.n_hidden + n_tile * HU, zb);
+                        tma_load_3d(b_dst, mb, &full_bar[s], k0, n_tile * HU, 0);
                     } else if (!B_MN) {
                         tma_load_3d(b_dst, mb, &full_bar[s], k0, n_tile * BN, zb);
                     } else {
@@ -822,9 +822,11 @@ int tc_lstm_pair(const TcLstmArgs& c0, const TcLstmArgs& c1, cudaStream_t s) {
         const TcLstmArgs& c = *cs[k];
         TcKernelParams& p = kp.p[k];
         MARLC_TRY(make_map(&p.a1, c.U.ptr, c.Kin, c.M, c.U.slabs, c.U.ld, c.U.slab_stride, BM));
-        MARLC_TRY(make_map(&p.b1, c.Wih, c.Kin, 4 * c.n, 1, c.Kin, 0, HU));
+        // weights viewed as [gate][unit][K]: ONE box of HU units x 4 gates per K sub-block (the producer
+        // thread is issue-bound: 4 separate gate boxes per sub-block made 20 TMA instructions per stage)
+        MARLC_TRY(make_map(&p.b1, c.Wih, c.Kin, c.n, 4, c.Kin, (long)c.n * c.Kin, HU, false, 4));
         MARLC_TRY(make_map(&p.a2, c.Hprev.ptr, c.n, c.M, c.Hprev.slabs, c.Hprev.ld, c.Hprev.slab_stride, BM));
-        MARLC_TRY(make_map(&p.b2, c.Whh, c.n, 4 * c.n, 1, c.n, 0, HU));
+        MARLC_TRY(make_map(&p.b2, c.Whh, c.n, c.n, 4, c.n, (long)c.n * c.n, HU, false, 4));
         p.nk1 = (c.Kin + BKS - 1) / BKS;
         p.nk2 = (c.n + BKS - 1) / BKS;
         p.a_lo_g = (c.x3 && c.U.lo && c.Hprev.lo) ? 1 : 0;
@@ -834,8 +836,8 @@ int tc_lstm_pair(const TcLstmArgs& c0, const TcLstmArgs& c1, cudaStream_t s) {
             MARLC_TRY(make_map(&p.a2l, c.Hprev.lo, c.n, c.M, c.Hprev.slabs, c.Hprev.ld, c.Hprev.slab_stride, BM));
         }
         if (p.b_lo_g) {
-            MARLC_TRY(make_map(&p.b1l, c.Wih_lo, c.Kin, 4 * c.n, 1, c.Kin, 0, HU));
-            MARLC_TRY(make_map(&p.b2l, c.Whh_lo, c.n, 4 * c.n, 1, c.n, 0, HU));
+            MARLC_TRY(make_map(&p.b1l, c.Wih_lo, c.Kin, c.n, 4, c.Kin, (long)c.n * c.Kin, HU, false, 4));
+            MARLC_TRY(make_map(&p.b2l, c.Whh_lo, c.n, c.n, 4, c.n, (long)c.n * c.n, HU, false, 4));
         }
         p.h_new_lo = c.h_new_lo;
         p.slab_a1 = c.U.slab; p.slab_a2 = c.Hprev.slab;

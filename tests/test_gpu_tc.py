@@ -148,7 +148,11 @@ def test_tf32_engine_vs_reference(name, precision):
     model.attach_grads()
     worst = max(rel_l2(p.grad.cpu(), fx["grads"][k]) for k, p in model.named_parameters() if fx["grads"][k].norm() > 0)
     print(f"{name} {precision}: preds/logp/values rel-L2 = {e[0]:.1e}/{e[1]:.1e}/{e[2]:.1e}, worst grad = {worst:.1e}")
-    fwd_tol, grad_tol = (TF32_FWD_TOL, TF32_GRAD_TOL) if precision == "tf32" else (X3_TOL, X3_TOL)
+    # 3xTF32 is held here to what it actually delivers (fp32-class: measured <= 6e-6 forward, <= 4e-5 on the
+    # worst parameter gradient), far inside the 1e-3 north-star bound, so that a path that silently loses
+    # its low-order correction (TF32-class error, ~1e-4..1e-3) fails instead of hiding under the bound
+    fwd_tol, grad_tol = (TF32_FWD_TOL, TF32_GRAD_TOL) if precision == "tf32" else (3e-5, 2e-4)
+    assert fwd_tol <= X3_TOL or precision == "tf32"
     assert max(e) < fwd_tol
     assert abs(loss_out[0].item() - fx["logged"]["loss"]) <= fwd_tol * abs(fx["logged"]["loss"])
     assert worst < grad_tol
@@ -188,3 +192,59 @@ def test_tf32_full_c2_vs_fp32_mode():
         eg = rel_l2(res[key][3].cpu(), res[False][3].cpu())
         print(f"c2 {'tf32x3' if key is True else key} vs fp32: preds {ep:.1e}, values {ev:.1e}, flat grads {eg:.1e}")
         assert ep < ftol and ev < ftol and eg < gtol
+
+
+# ---- fused LSTM pair (recurrent.py:7-35: both cells share u_t) as one tensor-core launch ----------
+def _lstm_ref64(u, h, c, wih, whh, bih, bhh):
+    g = u.double() @ wih.double().t() + bih.double() + h.double() @ whh.double().t() + bhh.double()
+    i, f, gg, o = g.chunk(4, dim=1)
+    i, f, gg, o = torch.sigmoid(i), torch.sigmoid(f), torch.tanh(gg), torch.sigmoid(o)
+    cn = f * c.double() + i * gg
+    return torch.cat([i, f, gg, o], 1), cn, o * torch.tanh(cn)
+
+
+@pytest.mark.parametrize("M,Kin,n", [(128, 368, 256), (96, 96, 64), (4096, 368, 256), (20, 624, 256), (130, 100, 32)])
+@pytest.mark.parametrize("mode", ["tf32", "tf32x3", "presplit"])
+def test_tc_lstm_pair_vs_fp64(M, Kin, n, mode):
+    import ctypes as ct
+
+    from marlclassification_b200 import _lib
+
+    L = _lib.lib()
+    g = torch.Generator(device=DEV).manual_seed(M + Kin + n)
+    rnd = lambda *s: torch.randn(*s, device=DEV, generator=g)  # noqa: E731
+    u = rnd(M, Kin)
+    hp, cp = [rnd(M, n), rnd(M, n)], [rnd(M, n), rnd(M, n)]
+    wih, whh = [rnd(4 * n, Kin) * 0.05 for _ in range(2)], [rnd(4 * n, n) * 0.05 for _ in range(2)]
+    bih, bhh = [rnd(4 * n) * 0.1 for _ in range(2)], [rnd(4 * n) * 0.1 for _ in range(2)]
+    cn = [torch.zeros(M, n, device=DEV) for _ in range(2)]
+    hn = [torch.zeros(M, n, device=DEV) for _ in range(2)]
+    hn_lo = [torch.zeros(M, n, device=DEV) for _ in range(2)]
+    gates = [torch.zeros(M, 4 * n, device=DEV) for _ in range(2)]
+    arr = lambda ts: (ct.c_void_p * 2)(*[t.data_ptr() for t in ts])  # noqa: E731
+    if mode == "presplit":
+        def lo_of(t):
+            out = torch.empty_like(t)
+            _lib.check(L.marlc_split_lo(t.data_ptr(), out.data_ptr(), t.numel(), _lib.stream_ptr()))
+            return out
+
+        # the split is exact: hi + lo == x bit for bit, hi has at most 10 mantissa bits
+        lo = lo_of(u)
+        assert torch.equal((u - lo) + lo, u) and torch.equal(tf32_round(u - lo), u - lo)
+        hp_lo, wih_lo, whh_lo = [lo_of(t) for t in hp], [lo_of(t) for t in wih], [lo_of(t) for t in whh]  # keep alive
+        _lib.check(L.marlc_tc_lstm_pair_presplit(
+            u.data_ptr(), lo.data_ptr(), M, Kin, n, arr(hp), arr(hp_lo), arr(cp), arr(wih), arr(wih_lo), arr(whh),
+            arr(whh_lo), arr(bih), arr(bhh), arr(cn), arr(hn), arr(hn_lo), arr(gates), _lib.stream_ptr()))
+    else:
+        _lib.check(L.marlc_tc_lstm_pair(u.data_ptr(), M, Kin, n, arr(hp), arr(cp), arr(wih), arr(whh), arr(bih), arr(bhh),
+                                        arr(cn), arr(hn), arr(gates), 1 if mode == "tf32x3" else 0, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    tol = 5e-3 if mode == "tf32" else 2e-5
+    for k in range(2):
+        g_ref, c_ref, h_ref = _lstm_ref64(u, hp[k], cp[k], wih[k], whh[k], bih[k], bhh[k])
+        assert rel_l2(gates[k].double().cpu(), g_ref.cpu()) < tol
+        assert rel_l2(cn[k].double().cpu(), c_ref.cpu()) < tol
+        assert rel_l2(hn[k].double().cpu(), h_ref.cpu()) < tol
+        if mode == "presplit":  # the kernel also emits the low-order part of h for the next step's operand
+            hi = tf32_round(hn[k])
+            assert torch.equal(hn_lo[k], hn[k] - hi)
