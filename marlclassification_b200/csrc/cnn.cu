@@ -34,6 +34,35 @@ int cnn_fwd(const CnnDesc& d, const float* img, const int* pos, const float* pat
 }
 
 // ---------------------------------------------------------------------------
+// Transposed copies of the conv weights, wT_l[(ci*9 + tap)][co] (output channel contiguous), used
+// by the register-tiled forward block: a thread computing 4 consecutive output channels reads the
+// 4 weights of a tap with one 128-bit load, and a whole layer is one contiguous bulk copy.
+// Refreshed once per forward (the parameters may have been updated by the optimiser).
+// ---------------------------------------------------------------------------
+struct CnnTransposeArgs { const float* w[MAX_CNN_LAYERS]; float* wT[MAX_CNN_LAYERS]; int co[MAX_CNN_LAYERS], wrow[MAX_CNN_LAYERS]; int L; };
+__global__ void __launch_bounds__(256) cnn_transpose_kernel(const CnnTransposeArgs a) {
+    for (int l = 0; l < a.L; ++l) {
+        const int n = a.co[l] * a.wrow[l];
+        for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+            const int k = e / a.co[l], c = e - k * a.co[l];  // coalesced writes
+            a.wT[l][e] = __ldg(a.w[l] + (long)c * a.wrow[l] + k);
+        }
+    }
+}
+int cnn_weights_transpose(const CnnDesc& d, float* const* wT, cudaStream_t s) {
+    CnnTransposeArgs a;
+    a.L = d.L;
+    int mx = 0;
+    for (int l = 0; l < d.L; ++l) {
+        a.w[l] = d.w[l]; a.wT[l] = wT[l]; a.co[l] = d.cout[l]; a.wrow[l] = d.cin[l] * 9;
+        mx = max(mx, d.cout[l] * d.cin[l] * 9);
+    }
+    cnn_transpose_kernel<<<max(1, min(148, (mx + 255) / 256)), 256, 0, s>>>(a);
+    MARLC_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
 // Backward.  One CTA per window p (p = t*M + m).  Re-gathers the input window,
 // rebuilds the activations from the saved pre-norm outputs, then walks the
 // layers backwards.  It does NOT reduce weight gradients itself: it emits, per

@@ -292,6 +292,9 @@ extern "C" int marlc_engine_create(const marlc_config* c, marlc_engine** out) {
     e->add_buf("dhc", M * c->n_a * F4);
     e->add_buf("dcc0", M * c->n_a * F4);
     e->add_buf("dcc1", M * c->n_a * F4);
+    if (e->cfg.use_chains)
+        for (int l = 0; l < e->L; ++l)  // transposed conv weights for the register-tiled forward block
+            e->add_buf("cnn_wT" + std::to_string(l), (size_t)d.cout[l] * d.cin[l] * 9 * F4);
     if (e->lo_on) {
         e->add_buf("params_lo", (size_t)e->param_floats * F4);
         e->add_buf("U_lo", M * e->Kin * F4);  // one step at a time: only the per-step LSTM GEMM reads it
@@ -365,6 +368,7 @@ extern "C" int marlc_engine_bind(marlc_engine* e, void* workspace, float* params
         e->cnn.b[l] = e->prm(CNN_PREFIX + std::to_string(3 * l) + ".bias");
         e->cnn.gn_w[l] = e->prm(CNN_PREFIX + std::to_string(3 * l + 1) + ".weight");
         e->cnn.gn_b[l] = e->prm(CNN_PREFIX + std::to_string(3 * l + 1) + ".bias");
+        e->cnn.wT[l] = e->cfg.use_chains ? e->buf("cnn_wT" + std::to_string(l)) : nullptr;
     }
     return 0;
 }
@@ -402,6 +406,11 @@ __global__ void __launch_bounds__(256) split_lo_kernel(const SplitLoArgs a) {
 }
 // h0 / hc0: the first step's recurrent inputs (nullptr: skip; only the parameters are refreshed)
 static int refresh_lo(marlc_engine* e, const float* h0, const float* hc0, cudaStream_t s) {
+    if (e->cfg.use_chains) {  // derived copies of the parameters, once per forward
+        float* wT[MAX_CNN_LAYERS];
+        for (int l = 0; l < e->L; ++l) wT[l] = const_cast<float*>(e->cnn.wT[l]);
+        MARLC_TRY(cnn_weights_transpose(e->cnn, wT, s));
+    }
     if (!e->lo_on) return 0;
     SplitLoArgs a;
     a.src[0] = e->P; a.dst[0] = e->buf("params_lo"); a.n[0] = e->param_floats;  // slots are multiples of 64 floats

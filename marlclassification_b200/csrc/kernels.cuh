@@ -59,6 +59,9 @@ struct CnnDesc {
     const float* b[MAX_CNN_LAYERS];
     const float* gn_w[MAX_CNN_LAYERS];
     const float* gn_b[MAX_CNN_LAYERS];
+    // optional: conv weights transposed to [cin*9][cout] (output channel contiguous), refreshed by the
+    // engine once per forward; enables the register-tiled forward block (cnn_device.cuh)
+    const float* wT[MAX_CNN_LAYERS];
 };
 // Fused gather + CNN forward for M windows.  If `patch` is non-null the windows
 // are read from it ([M, img_c, f, f]) instead of gathered from `img` by `pos`.
@@ -76,6 +79,8 @@ struct CnnBwdBuffers {
 // dY / col / gnpart rows of those windows.  All buffer pointers are for window 0.
 int cnn_bwd(const CnnDesc& d, const float* img, const int* pos_hist, int B, int H, int W, int M, int p0, int P,
             const float* const* y_save, const float* dOut, long lddo, const CnnBwdBuffers& buf, cudaStream_t s);
+
+int cnn_weights_transpose(const CnnDesc& d, float* const* wT, cudaStream_t s);
 
 // ---- cnn_bwd2.cu: layer-wise, batched backward (conv products on the tensor cores) ------------
 struct CnnBwdLayerArgs {
