@@ -243,7 +243,14 @@ __device__ __forceinline__ float other_agents_mean(const float* __restrict__ x, 
     const float* base = x + (long)b * n + j;
     const long stride = (long)Nb * n;
     float s = 0.f;
-    for (int a = 0; a < Na; ++a) s += base[a * stride];
+    int a = 0;
+    for (; a + 8 <= Na; a += 8) {  // 8 loads in flight, then the adds
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = base[(a + i) * stride];
+        s += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+    }
+    for (; a < Na; ++a) s += base[a * stride];
     return (s - x[(long)m * n + j]) / (float)(Na - 1);
 }
 
@@ -582,7 +589,71 @@ __device__ __forceinline__ void cell_bwd_rows(const int row0, const int rows_val
     }
 }
 
+// The same cell backward split in two, for n <= CT (one column j = threadIdx.x per thread): the loads
+// are issued at kernel entry for BOTH cells, so their global-memory latency overlaps the encoder
+// chain instead of being exposed twice (in-kernel trace of the serial version: 4000 cycles for the
+// action cell at entry and 5700 for the belief cell at the end, of 31 000).
+// (no arithmetic in the load phase: an add right after two loads would make the in-order thread wait
+// for them before it can issue the next loads)
+struct CellIn { float gi[RB], gf[RB], gg[RB], go[RB], dh[RB], dhc[RB], dcn[RB], cp[RB], cn[RB]; };
+__device__ __forceinline__ void cell_bwd_load(CellIn& c, const int row0, const int rows_valid, const int n,
+                                              const float* __restrict__ gates, const float* __restrict__ dh_heads,
+                                              const float* __restrict__ dh_carry, const float* __restrict__ dc_next,
+                                              const float* __restrict__ c_prev, const float* __restrict__ c_new) {
+    const int j = threadIdx.x;
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+        c.gi[r] = c.gf[r] = c.gg[r] = c.go[r] = c.dh[r] = c.dhc[r] = c.dcn[r] = c.cp[r] = c.cn[r] = 0.f;
+        if (j < n && r < rows_valid) {
+            const long m = row0 + r, idx = m * n + j;
+            const float* g = gates + m * 4 * n;
+            c.gi[r] = g[j]; c.gf[r] = g[n + j]; c.gg[r] = g[2 * n + j]; c.go[r] = g[3 * n + j];
+            c.dh[r] = dh_heads[idx];
+            if (dh_carry) c.dhc[r] = dh_carry[idx];
+            if (dc_next) c.dcn[r] = dc_next[idx];
+            c.cp[r] = c_prev[idx]; c.cn[r] = c_new[idx];
+        }
+    }
+}
+__device__ __forceinline__ void cell_bwd_compute(const CellIn& c, const int row0, const int rows_valid, const int n,
+                                                 const float* dhx, const int ldx, float* __restrict__ dgates,
+                                                 float* __restrict__ dgates_lo, float* __restrict__ dc_prev) {
+    const int j = threadIdx.x;
+    if (j >= n) return;
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+        if (r < rows_valid) {
+            const long m = row0 + r, idx = m * n + j;
+            const float dhv = c.dh[r] + c.dhc[r] + (dhx ? dhx[r * ldx + j] : 0.f);
+            const float tc = tanhf(c.cn[r]);
+            const float dc = c.dcn[r] + dhv * c.go[r] * (1.f - tc * tc);
+            float* dg = dgates + m * 4 * n;
+            const float d_i = dc * c.gg[r] * c.gi[r] * (1.f - c.gi[r]);
+            const float d_f = dc * c.cp[r] * c.gf[r] * (1.f - c.gf[r]);
+            const float d_g = dc * c.gi[r] * (1.f - c.gg[r] * c.gg[r]);
+            const float d_o = dhv * tc * c.go[r] * (1.f - c.go[r]);
+            dg[j] = d_i; dg[n + j] = d_f; dg[2 * n + j] = d_g; dg[3 * n + j] = d_o;
+            if (dgates_lo) {
+                float* dl = dgates_lo + m * 4 * n;
+                dl[j] = tf32_lo(d_i); dl[n + j] = tf32_lo(d_f); dl[2 * n + j] = tf32_lo(d_g); dl[3 * n + j] = tf32_lo(d_o);
+            }
+            dc_prev[idx] = dc * c.gf[r];
+        }
+    }
+}
+
 struct BwdPreKernelArgs { BwdPreArgs a; int maxw; int staged; };
+
+#ifdef MARLC_CHAIN_TRACE  // timeline of CTA 0 (cycles since entry), printed by thread 0
+#define CHAIN_TRACE_DECL() __shared__ long long ch_tr[24]; const long long ch_t0 = clock64(); int ch_i = 0
+#define CHAIN_TRACE() do { if (blockIdx.x == 0 && threadIdx.x == 0 && ch_i < 24) ch_tr[ch_i] = clock64() - ch_t0; ++ch_i; } while (0)
+#define CHAIN_TRACE_PRINT(name) do { if (blockIdx.x == 0 && threadIdx.x == 0) { printf("%s trace:", name); \
+    for (int i_ = 0; i_ < ch_i && i_ < 24; ++i_) printf(" %lld", ch_tr[i_]); printf(" | end %lld\n", clock64() - ch_t0); } } while (0)
+#else
+#define CHAIN_TRACE_DECL() do { } while (0)
+#define CHAIN_TRACE() do { } while (0)
+#define CHAIN_TRACE_PRINT(name) do { } while (0)
+#endif
 
 __global__ void __launch_bounds__(CT) bwd_pre_kernel(const BwdPreKernelArgs ka) {
     extern __shared__ __align__(16) float sm[];
@@ -594,13 +665,97 @@ __global__ void __launch_bounds__(CT) bwd_pre_kernel(const BwdPreKernelArgs ka) 
     float* W3s = S.wres;             // encode_msg.3 weight [n_m][n1]
     float* W0s = W3s + n_m * n1;     // encode_msg.0 weight [n1][nb]
     const bool enc = a.dcoll != nullptr;
-    if (enc && ka.staged) {  // asynchronous: overlaps the action cell and the first encoder phases
+    CHAIN_TRACE_DECL();
+    // ---- fast path: every global operand of the CTA is requested up front (cell inputs and encoder
+    //      activations to registers, LayerNorm affines to shared memory), and only THEN the 164 KB of
+    //      weights (cp.async): the load/store unit is in order, and with the weight copies queued
+    //      first the ~95 operand loads per thread took 9200 cycles just to issue (in-kernel trace).
+    const bool fast = ka.staged && a.n[0] <= CT && a.n[1] <= CT && RB * n_m <= CT && RB * n1 <= 2 * CT &&
+                      2 * (n_m + n1) + RB * mw <= CT * WT_P;
+    if (!fast && enc && ka.staged) {  // asynchronous: overlaps the action cell and the first encoder phases
         stage_w_async(W3s, a.e3.W, n_m, n1);
         stage_w_async(W0s, a.e0.W, n1, nb);
+    }
+    CHAIN_TRACE();  // 0
+    if (fast) {
+        float* sG3 = S.wt;            // encode_msg.4 affine
+        float* sB3 = sG3 + n_m;
+        float* sG0 = sB3 + n_m;       // encode_msg.1 affine
+        float* sB0 = sG0 + n1;
+        float* Y1S = sB0 + n1;        // [RB][mw] pre-norm activations of block 0
+        CellIn ca, cb;
+        cell_bwd_load(ca, row0, rows_valid, a.n[1], a.gates[1], a.dh_heads[1], a.dh_carry[1], a.dc_next[1], a.c_prev[1], a.c_new[1]);
+        cell_bwd_load(cb, row0, rows_valid, a.n[0], a.gates[0], a.dh_heads[0], a.dh_carry[0], a.dc_next[0], a.c_prev[0], a.c_new[0]);
+        float meanv = 0.f, y2v = 0.f, y1v[2] = {0.f, 0.f};
+        const int tid = threadIdx.x;
+        if (enc) {
+            if (tid < RB * n_m) {
+                const int r = tid / n_m, j = tid - r * n_m;
+                if (r < rows_valid) {
+                    meanv = other_agents_mean(a.dcoll, row0 + r, j, a.Na, a.Nb, n_m);
+                    y2v = a.enc_y2[(long)(row0 + r) * n_m + j];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int e = tid + i * CT;
+                if (e < RB * n1) {
+                    const int r = e / n1, k = e - r * n1;
+                    if (r < rows_valid) y1v[i] = a.enc_y1[(long)(row0 + r) * n1 + k];
+                }
+            }
+            if (tid < n_m) { sG3[tid] = a.e3.g[tid]; sB3[tid] = a.e3.be[tid]; }
+            if (tid < n1) { sG0[tid] = a.e0.g[tid]; sB0[tid] = a.e0.be[tid]; }
+            stage_w_async(W3s, a.e3.W, n_m, n1);
+            stage_w_async(W0s, a.e0.W, n1, nb);
+        }
+        CHAIN_TRACE();  // loads issued
+#ifdef MARLC_CHAIN_TRACE
+        if (ca.gi[0] == 1234.5f) printf("x");
+        CHAIN_TRACE();  // first cell operand arrived
+        if (cb.cn[RB - 1] == 1234.5f) printf("x");
+        CHAIN_TRACE();  // last cell operand arrived
+        if (y1v[1] == 1234.5f || meanv == 1234.5f) printf("x");
+        CHAIN_TRACE();  // encoder operands arrived
+#endif
+        cell_bwd_compute(ca, row0, rows_valid, a.n[1], nullptr, 0, a.dgates[1], a.dgates_lo[1], a.dc_prev[1]);
+        CHAIN_TRACE();  // 1: loads issued + action cell
+        if (enc) {
+            if (tid < RB * n_m) {
+                const int r = tid / n_m, j = tid - r * n_m;
+                S.bufA[r * mw + j] = meanv;
+                S.bufB[r * mw + j] = y2v;
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int e = tid + i * CT;
+                if (e < RB * n1) { const int r = e / n1, k = e - r * n1; Y1S[r * mw + k] = y1v[i]; }
+            }
+            __syncthreads();
+            CHAIN_TRACE();  // 2: operands in shared memory
+            rb_ln_silu_bwd(S.bufA, S.bufB, mw, n_m, sG3, sB3, rows_valid, row0, dhx, S.bufT, a.d_enc_y2, n_m,
+                           a.e3.dg, a.e3.dbe, a.e3.db);
+            CHAIN_TRACE();  // 3: LN backward (block 3)
+            stage_wait_all();
+            __syncthreads();
+            CHAIN_TRACE();  // 4: weights landed
+            rb_dx_s(S.bufT, W3s, n1, S.bufA, mw, n_m, n1);  // ds1 [RB][2n_m]
+            CHAIN_TRACE();  // 5: dx through W3
+            rb_ln_silu_bwd(S.bufA, Y1S, mw, n1, sG0, sB0, rows_valid, row0, dhx, S.bufT, a.d_enc_y1, n1,
+                           a.e0.dg, a.e0.dbe, a.e0.db);
+            CHAIN_TRACE();  // 6: LN backward (block 0)
+            rb_dx_s(S.bufT, W0s, nb, dhx, mw, n1, nb);      // dh contribution [RB][n_b]
+            CHAIN_TRACE();  // 7: dx through W0
+        }
+        cell_bwd_compute(cb, row0, rows_valid, a.n[0], enc ? dhx : nullptr, mw, a.dgates[0], a.dgates_lo[0], a.dc_prev[0]);
+        CHAIN_TRACE();  // 8: belief cell
+        CHAIN_TRACE_PRINT("bwd_pre");
+        return;
     }
     // the action cell does not depend on the encoder chain: do it while the weights stream in
     cell_bwd_rows(row0, rows_valid, a.n[1], a.gates[1], a.dh_heads[1], a.dh_carry[1], a.dc_next[1], a.c_prev[1],
                   a.c_new[1], nullptr, 0, a.dgates[1], a.dgates_lo[1], a.dc_prev[1]);
+    CHAIN_TRACE();  // 1: action cell
     if (enc) {
         // gradient of the message produced at step t = adjoint mean of dcoll(t+1); encoder block 3 backward
         for (int e = threadIdx.x; e < RB * n_m; e += CT) {
@@ -610,11 +765,15 @@ __global__ void __launch_bounds__(CT) bwd_pre_kernel(const BwdPreKernelArgs ka) 
             S.bufB[r * mw + j] = ok ? a.enc_y2[(long)(row0 + r) * n_m + j] : 0.f;
         }
         __syncthreads();
+        CHAIN_TRACE();  // 2: adjoint mean + y2 loaded
         rb_ln_silu_bwd(S.bufA, S.bufB, mw, n_m, a.e3.g, a.e3.be, rows_valid, row0, dhx, S.bufT, a.d_enc_y2, n_m,
                        a.e3.dg, a.e3.dbe, a.e3.db);
+        CHAIN_TRACE();  // 3: LN backward (block 3)
         if (ka.staged) { stage_wait_all(); __syncthreads(); }
+        CHAIN_TRACE();  // 4: weights landed
         if (ka.staged) rb_dx_s(S.bufT, W3s, n1, S.bufA, mw, n_m, n1);  // ds1 [RB][2n_m]
         else rb_dx(S.bufT, a.e3.W, S.bufA, mw, n_m, n1);
+        CHAIN_TRACE();  // 5: dx through W3
         for (int e = threadIdx.x; e < RB * n1; e += CT) {
             const int r = e / n1, k = e % n1;
             S.bufB[r * mw + k] = r < rows_valid ? a.enc_y1[(long)(row0 + r) * n1 + k] : 0.f;
@@ -622,11 +781,15 @@ __global__ void __launch_bounds__(CT) bwd_pre_kernel(const BwdPreKernelArgs ka) 
         __syncthreads();
         rb_ln_silu_bwd(S.bufA, S.bufB, mw, n1, a.e0.g, a.e0.be, rows_valid, row0, dhx, S.bufT, a.d_enc_y1, n1,
                        a.e0.dg, a.e0.dbe, a.e0.db);
+        CHAIN_TRACE();  // 6: y1 load + LN backward (block 0)
         if (ka.staged) rb_dx_s(S.bufT, W0s, nb, dhx, mw, n1, nb);      // dh contribution [RB][n_b]
         else rb_dx(S.bufT, a.e0.W, dhx, mw, n1, nb);
+        CHAIN_TRACE();  // 7: dx through W0
     }
     cell_bwd_rows(row0, rows_valid, a.n[0], a.gates[0], a.dh_heads[0], a.dh_carry[0], a.dc_next[0], a.c_prev[0],
                   a.c_new[0], enc ? dhx : nullptr, mw, a.dgates[0], a.dgates_lo[0], a.dc_prev[0]);
+    CHAIN_TRACE();  // 8: belief cell
+    CHAIN_TRACE_PRINT("bwd_pre");
 }
 
 int bwd_pre(const BwdPreArgs& a, cudaStream_t s) {
