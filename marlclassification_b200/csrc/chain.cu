@@ -293,6 +293,35 @@ __global__ void __launch_bounds__(CT) step_pre_kernel(const StepPreKernelArgs ka
     const int P0 = odd_pitch(n_m), P3 = odd_pitch(n1);
     float* W0s = S.wres;
     float* W3s = W0s + n1 * P0;
+    if (ka.staged && RB * n_m <= CT && n1 <= CT && n2 <= CT && 2 * (n1 + n2) <= CT * WT_P) {
+        // every global operand requested up front, grouped ahead of any use (see bwd_pre): the message
+        // mean and the LayerNorm affines first, then the (synchronously staged) weights
+        float* sG0 = S.wt;
+        float* sB0 = sG0 + n1;
+        float* sG3 = sB0 + n1;
+        float* sB3 = sG3 + n2;
+        const int tid = threadIdx.x;
+        float mv = 0.f;
+        const int r = tid / n_m, j = tid - r * n_m;
+        if (tid < RB * n_m && r < rows_valid) mv = other_agents_mean(a.msg_in, row0 + r, j, a.Na, a.Nb, n_m);
+        float g0 = 0.f, b0 = 0.f, g3 = 0.f, b3 = 0.f;
+        if (tid < n1) { g0 = a.d0.g[tid]; b0 = a.d0.be[tid]; }
+        if (tid < n2) { g3 = a.d3.g[tid]; b3 = a.d3.be[tid]; }
+        stage_w(W0s, a.d0.W, n1, n_m, P0);
+        stage_w(W3s, a.d3.W, n2, n1, P3);
+        if (tid < n1) { sG0[tid] = g0; sB0[tid] = b0; }
+        if (tid < n2) { sG3[tid] = g3; sB3[tid] = b3; }
+        if (tid < RB * n_m) {
+            if (r < rows_valid) a.coll[(long)(row0 + r) * n_m + j] = mv;
+            S.bufT[j * RB + r] = mv;
+        }
+        __syncthreads();
+        rb_linear_s(S.bufT, W0s, P0, a.d0.b, S.bufA, ka.maxw, n1, n_m);
+        rb_ln_silu(S.bufA, ka.maxw, n1, sG0, sB0, rows_valid, row0, a.dec_y1, n1, a.dec_s1, n1, S.bufT);
+        rb_linear_s(S.bufT, W3s, P3, a.d3.b, S.bufA, ka.maxw, n2, n1);
+        rb_ln_silu(S.bufA, ka.maxw, n2, sG3, sB3, rows_valid, row0, a.dec_y2, n2, a.U + a.F, a.ldu, nullptr,
+                   a.U_lo ? a.U_lo + a.F : nullptr);
+    } else {
     if (ka.staged) { stage_w(W0s, a.d0.W, n1, n_m, P0); stage_w(W3s, a.d3.W, n2, n1, P3); }
     // collected message (mean of the other agents)                      message.py:5-17
     for (int e = threadIdx.x; e < RB * n_m; e += CT) {
@@ -313,6 +342,7 @@ __global__ void __launch_bounds__(CT) step_pre_kernel(const StepPreKernelArgs ka
     else rb_linear(S.bufT, a.d3.W, a.d3.b, S.bufA, ka.maxw, n2, n1, S.wt);
     rb_ln_silu(S.bufA, ka.maxw, n2, a.d3.g, a.d3.be, rows_valid, row0, a.dec_y2, n2, a.U + a.F, a.ldu, nullptr,
                a.U_lo ? a.U_lo + a.F : nullptr);
+    }
     // position features                                                  state.py:7-17
     {
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nd = a.pos.n_out;
@@ -507,6 +537,35 @@ __global__ void __launch_bounds__(CT) step_post_kernel(const StepPostKernelArgs 
     const int n1 = a.e3.n_in, n2 = a.e3.n_out;
     ChainSmem S(sm, ka.maxw);
     const int P3 = odd_pitch(n1);
+    if (ka.staged && RB * n1 <= 2 * CT && n1 <= CT && n2 <= CT && 2 * (n1 + n2) <= CT * WT_P) {
+        // every global operand requested up front, grouped ahead of any use (see bwd_pre)
+        float* sG1 = S.wt;
+        float* sB1 = sG1 + n1;
+        float* sG3 = sB1 + n1;
+        float* sB3 = sG3 + n2;
+        const int tid = threadIdx.x;
+        float y1v[2] = {0.f, 0.f};
+        int r1[2], k1[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) { const int e = tid + i * CT; r1[i] = e / n1; k1[i] = e - r1[i] * n1; }
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+            if (r1[i] < rows_valid) y1v[i] = a.enc_y1[(long)(row0 + r1[i]) * n1 + k1[i]];
+        float g1 = 0.f, b1 = 0.f, g3 = 0.f, b3 = 0.f;
+        if (tid < n1) { g1 = a.enc_g[tid]; b1 = a.enc_be[tid]; }
+        if (tid < n2) { g3 = a.e3.g[tid]; b3 = a.e3.be[tid]; }
+        stage_w(S.wres, a.e3.W, n2, n1, P3);
+        if (tid < n1) { sG1[tid] = g1; sB1[tid] = b1; }
+        if (tid < n2) { sG3[tid] = g3; sB3[tid] = b3; }
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+            if (r1[i] < RB) S.bufA[r1[i] * ka.maxw + k1[i]] = y1v[i];
+        __syncthreads();
+        rb_ln_silu(S.bufA, ka.maxw, n1, sG1, sB1, rows_valid, row0, nullptr, 0, a.enc_s1, n1, S.bufT);
+        rb_linear_s(S.bufT, S.wres, P3, a.e3.b, S.bufA, ka.maxw, n2, n1);
+        rb_ln_silu(S.bufA, ka.maxw, n2, sG3, sB3, rows_valid, row0, a.enc_y2, n2, a.msg_out, n2, nullptr);
+        return;
+    }
     if (ka.staged) stage_w(S.wres, a.e3.W, n2, n1, P3);
     for (int e = threadIdx.x; e < RB * n1; e += CT) {
         const int r = e / n1, k = e % n1;
@@ -824,6 +883,62 @@ __global__ void __launch_bounds__(CT) bwd_post_kernel(const BwdPostKernelArgs ka
     const int n_m = a.n_m, n1 = a.d0.n_out, n2 = a.n_m_o;
     float* W3s = S.wres;           // decode_msg.3 weight [n2][n1]
     float* W0s = W3s + n2 * n1;    // decode_msg.0 weight [n1][n_m]
+    // ---- fast path (as in bwd_pre): every global operand is requested up front, loads grouped ahead of
+    //      any use, LayerNorm affines and the block-0 activations parked in the unused tile scratch
+    const bool fast = ka.staged && RB * n2 <= 2 * CT && RB * n1 <= 2 * CT && n1 <= CT && n2 <= CT &&
+                      2 * (n1 + n2) + RB * mw <= CT * WT_P;
+    if (fast) {
+        float* sG3 = S.wt;
+        float* sB3 = sG3 + n2;
+        float* sG0 = sB3 + n2;
+        float* sB0 = sG0 + n1;
+        float* Y1S = sB0 + n1;  // [RB][mw]
+        const int tid = threadIdx.x;
+        float du[2] = {0.f, 0.f}, y2v[2] = {0.f, 0.f}, y1v[2] = {0.f, 0.f};
+        int r2[2], j2[2], r1[2], k1[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int e = tid + i * CT;
+            r2[i] = e / n2; j2[i] = e - r2[i] * n2;
+            r1[i] = e / n1; k1[i] = e - r1[i] * n1;
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            if (r2[i] < rows_valid) {
+                du[i] = a.dU[(long)(row0 + r2[i]) * a.ldu + a.F + j2[i]];
+                y2v[i] = a.dec_y2[(long)(row0 + r2[i]) * n2 + j2[i]];
+            }
+            if (r1[i] < rows_valid) y1v[i] = a.dec_y1[(long)(row0 + r1[i]) * n1 + k1[i]];
+        }
+        float g3 = 0.f, b3 = 0.f, g0 = 0.f, b0 = 0.f;
+        if (tid < n2) { g3 = a.d3.g[tid]; b3 = a.d3.be[tid]; }
+        if (tid < n1) { g0 = a.d0.g[tid]; b0 = a.d0.be[tid]; }
+        stage_w_async(W3s, a.d3.W, n2, n1);
+        if (a.dcoll) stage_w_async(W0s, a.d0.W, n1, n_m);
+        if (tid < n2) { sG3[tid] = g3; sB3[tid] = b3; }
+        if (tid < n1) { sG0[tid] = g0; sB0[tid] = b0; }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            if (r2[i] < RB) { S.bufA[r2[i] * mw + j2[i]] = du[i]; S.bufB[r2[i] * mw + j2[i]] = y2v[i]; }
+            if (r1[i] < RB) Y1S[r1[i] * mw + k1[i]] = y1v[i];
+        }
+        __syncthreads();
+        rb_ln_silu_bwd(S.bufA, S.bufB, mw, n2, sG3, sB3, rows_valid, row0, S.bufC, S.bufT, a.d_dec_y2, n2, a.d3.dg,
+                       a.d3.dbe, a.d3.db);
+        stage_wait_all();
+        __syncthreads();
+        rb_dx_s(S.bufT, W3s, n1, S.bufA, mw, n2, n1);
+        rb_ln_silu_bwd(S.bufA, Y1S, mw, n1, sG0, sB0, rows_valid, row0, S.bufC, S.bufT, a.d_dec_y1, n1, a.d0.dg,
+                       a.d0.dbe, a.d0.db);
+        if (a.dcoll) {
+            rb_dx_s(S.bufT, W0s, n_m, S.bufA, mw, n1, n_m);
+            for (int e = tid; e < rows_valid * n_m; e += CT) {
+                const int r = e / n_m, j = e % n_m;
+                a.dcoll[(long)(row0 + r) * n_m + j] = S.bufA[r * mw + j];
+            }
+        }
+        return;
+    }
     if (ka.staged) { stage_w_async(W3s, a.d3.W, n2, n1); if (a.dcoll) stage_w_async(W0s, a.d0.W, n1, n_m); }
     for (int e = threadIdx.x; e < RB * n2; e += CT) {
         const int r = e / n2, j = e % n2;
