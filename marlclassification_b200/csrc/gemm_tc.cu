@@ -117,6 +117,26 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
         ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                               uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
@@ -177,6 +197,10 @@ struct TcKernelParams {
     CUtensorMap a1l, b1l, a2l, b2l;
     CUtensorMap cmap;            // EPI_STORE: C as [M rows][N cols], box 32 x 32, 128B swizzle (TMA store / reduce)
     int c_tma;                   // 1: cmap is valid (C 16-byte aligned, ldc % 4 == 0)
+    int cluster;                 // EPI_LSTM: CTAs along x that share the A tile through TMA multicast (1 = off);
+                                 // the A maps then have box rows BM / cluster
+    int ksplit;                  // EPI_LSTM: 2 = a pair of CTAs (cluster of 2 along x) splits K; the odd CTA ships its
+                                 // partial accumulators into the even CTA's shared memory (DSMEM) before the cell
     int a_lo_g, b_lo_g;          // 1: the lo part of A / B comes from global memory
     int nk1, nk2;                // K blocks of each pair
     int slab_a1, slab_b1, slab_a2, slab_b2;
@@ -243,6 +267,9 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
 
     const TcKernelParams& p = pp.p[PI];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cl = (EPI == EPI_LSTM && p.cluster > 1) ? p.cluster : 1;
+    const uint16_t cl_mask = (uint16_t)((1u << cl) - 1u);
+    const uint32_t cl_rank = cl > 1 ? cluster_rank() : 0u;
 #ifdef MARLC_TC_TRACE  // in-kernel timeline of CTA (0,0,0): cycles since entry at each pipeline event
     __shared__ long long trace[8];
     const bool tr = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
@@ -252,7 +279,9 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
 #define TC_TRACE(i) do { } while (0)
 #endif
     const int m0 = blockIdx.y * BM;
-    const int n_tile = blockIdx.x;
+    const int ksp = (EPI == EPI_LSTM && p.ksplit > 1) ? p.ksplit : 1;
+    const int n_tile = ksp > 1 ? blockIdx.x / ksp : blockIdx.x;
+    const int kslice = ksp > 1 ? blockIdx.x % ksp : 0;  // = rank in the cluster of ksp CTAs
     if (m0 >= p.M || n_tile * BN >= p.N) return;  // grid is sized for the largest problem of the group
     // K-block range of this CTA (split-K over the concatenated list of both pairs)
     const int nkb = p.nk1 + p.nk2;
@@ -260,6 +289,11 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
     if (EPI == EPI_STORE && p.splits > 1) {
         const int per = (nkb + p.splits - 1) / p.splits;
         kb_begin = split * per;
+        kb_end = min(nkb, kb_begin + per);
+    }
+    if (ksp > 1) {
+        const int per = (nkb + ksp - 1) / ksp;
+        kb_begin = kslice * per;
         kb_end = min(nkb, kb_begin + per);
     }
     const int my_kb = max(0, kb_end - kb_begin);
@@ -275,7 +309,9 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
     }
     if (threadIdx.x == 32) {
         for (int s = 0; s < stages; ++s) {
-            mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1);
+            // with A multicast a slot is refilled by every CTA of the cluster, so it is free only when
+            // ALL of them have consumed it: every MMA warp arrives on every CTA's empty barrier
+            mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], cl);
             mbar_init(&split_bar[s], TC_SPLITTERS / 2);  // one of the two splitter groups
         }
         mbar_init(&tmem_full_bar, 1);
@@ -288,6 +324,7 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
     }
     tc_fence_before();
     __syncthreads();
+    if (cl > 1) cluster_sync_all();  // every CTA's barriers exist before any peer multicasts into them
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
     if (threadIdx.x == 0) TC_TRACE(0);  // setup done (barriers, TMEM)
@@ -315,7 +352,10 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
                     uint8_t* a_dst = sA + s * S::A_BYTES + sub * S::A_SUB + hl * LO_OFF;
                     uint8_t* b_dst = sB + s * S::B_BYTES + sub * S::B_SUB + hl * LO_OFF;
                     if (do_a) {
-                        if (!A_MN) tma_load_3d(a_dst, ma, &full_bar[s], k0, m0, za);
+                        if (!A_MN && cl > 1) {  // this CTA fetches rows [rank*BM/cl, +BM/cl) for the whole cluster
+                            const int rows = BM / cl;
+                            tma_load_3d_mc(a_dst + cl_rank * rows * 128, ma, &full_bar[s], k0, m0 + (int)cl_rank * rows, za, cl_mask);
+                        } else if (!A_MN) tma_load_3d(a_dst, ma, &full_bar[s], k0, m0, za);
                         else
                             for (int j = 0; j < BM / 32; ++j) tma_load_3d(a_dst + j * 4096, ma, &full_bar[s], m0 + 32 * j, k0, za);
                     }
@@ -365,7 +405,8 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
                     }
                 }
                 }
-                umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs retire
+                if (cl > 1) umma_commit_mc(&empty_bar[s], cl_mask);
+                else umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs retire
             }
             umma_commit(&tmem_full_bar);
             TC_TRACE(3);  // last MMA issued
@@ -576,6 +617,35 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
             // fused LSTM cell (recurrent.py:30): columns [g*HU + j] hold gate g of hidden unit j0 + j
             constexpr int HU = BN / 4;
             const int n = p.n_hidden, j0 = n_tile * HU;
+            // K split over a CTA pair: each SM streams only half of the A tile (the main loop is bound by
+            // per-SM TMA ingest).  The odd CTA writes its partial gate sums into the even CTA's shared
+            // memory (distributed shared memory), one cluster barrier, the even CTA adds them.
+            constexpr int PPITCH = BN + 4;
+            float* part = reinterpret_cast<float*>(smem + (S::BYTES - 1024));  // [BM][PPITCH], after the ring
+            if (ksp > 1 && kslice != 0) {
+                uint32_t remote;
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(part)), "r"(0));
+                const uint32_t rrow = remote + (uint32_t)((32 * q + lane) * PPITCH) * 4u;
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 8) {
+                    uint32_t r[8];
+                    if (my_kb > 0) { TMEM_LD8(trow + c0, r); tmem_ld_wait(); }
+                    else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) r[j] = 0u;
+                    }
+                    asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rrow + (uint32_t)c0 * 4u), "r"(r[0]),
+                                 "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+                    asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rrow + (uint32_t)c0 * 4u + 16u), "r"(r[4]),
+                                 "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+                }
+            }
+            if (ksp > 1) {
+                asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+                asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+            }
+            const float* prow = part + (32 * q + lane) * PPITCH;
+            if (ksp == 1 || kslice == 0) {
 #pragma unroll 1
             for (int jb = 0; jb < HU; jb += 8) {
                 uint32_t ri[8], rf[8], rg[8], ro[8];
@@ -584,6 +654,15 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
                 TMEM_LD8(trow + 2 * HU + jb, rg);
                 TMEM_LD8(trow + 3 * HU + jb, ro);
                 tmem_ld_wait();
+                if (ksp > 1) {  // add the partner's half of K
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        ri[j] = __float_as_uint(__uint_as_float(ri[j]) + prow[0 * HU + jb + j]);
+                        rf[j] = __float_as_uint(__uint_as_float(rf[j]) + prow[1 * HU + jb + j]);
+                        rg[j] = __float_as_uint(__uint_as_float(rg[j]) + prow[2 * HU + jb + j]);
+                        ro[j] = __float_as_uint(__uint_as_float(ro[j]) + prow[3 * HU + jb + j]);
+                    }
+                }
                 if (m < p.M) {
                     const long off = (long)m * n + j0 + jb;
                     float cp[8];
@@ -623,8 +702,13 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
                     }
                 }
             }
+            }  // receiving / only CTA
         }
         }  // warp < 6
+    }
+    if (ksp > 1 && !(warp >= 2 && warp < 6)) {  // every thread of the pair takes part in the cluster barrier
+        asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
     }
     if (warp == 2 && lane == 0) TC_TRACE(5);  // epilogue of warp 2 done
     tc_fence_before();
@@ -639,6 +723,7 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
     }
+    if (cl > 1) cluster_sync_all();  // no CTA may exit while a peer can still signal its barriers
 }
 
 template <int BN, bool A_MN, bool B_MN, int EPI, int STAGES, bool X3, int KS>
@@ -789,6 +874,30 @@ static int launch_lstm(TcKernelGroup& kp, int gx, int gy, int nkb, cudaStream_t 
         MARLC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES));
         attr_done = true;
     }
+    const int ksp = kp.p[0].ksplit > 1 ? kp.p[0].ksplit : 1;
+    const int cl = ksp > 1 ? ksp : kp.p[0].cluster;
+    const size_t smem_bytes = S::BYTES + (ksp > 1 ? (size_t)BM * (BN + 4) * 4 : 0);
+    MARLC_CHECK(smem_bytes <= 227 * 1024, "tc_lstm_pair: K-split staging does not fit in shared memory");
+    static size_t attr_sz = 0;
+    if (smem_bytes > attr_sz) {
+        MARLC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        attr_sz = smem_bytes;
+    }
+    if (cl > 1) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(gx * ksp, gy, 2);
+        cfg.blockDim = dim3(X3 ? TC_THREADS_X3 : TC_THREADS);
+        cfg.dynamicSmemBytes = smem_bytes;
+        cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        MARLC_CUDA(cudaLaunchKernelEx(&cfg, kern, kp));
+        ++g_launch_count;
+        return 0;
+    }
     kern<<<dim3(gx, gy, 2), X3 ? TC_THREADS_X3 : TC_THREADS, S::BYTES, s>>>(kp);
     MARLC_LAUNCH_CHECK();
     return 0;
@@ -817,23 +926,39 @@ int tc_lstm_pair(const TcLstmArgs& c0, const TcLstmArgs& c1, cudaStream_t s) {
     const int KSv = !fat ? 1 : (c0.x3 ? 2 : (HU == 8 ? 4 : 2));
     const int BKS = BK * KSv;
     const TcLstmArgs* cs[2] = {&c0, &c1};
+    // A-tile multicast: the n/HU CTAs of one M tile all read the same 128 x K activations; in a cluster
+    // of `cl` of them each CTA requests 1/cl of every A tile and the TMA unit delivers it to all
+    // (the main loop is bound by what one SM's TMA engine can request, ~40-50 B/clk measured)
+    // (measured: no gain at M=128 - 14.4 vs 14.1 us - and slightly slower at M=4096: what binds is the
+    // bytes ARRIVING in each SM, not the requests its TMA engine issues; off unless MARLC_LSTM_CLUSTER)
+    int cl = 1;
+    if (const char* env = getenv("MARLC_LSTM_CLUSTER")) cl = atoi(env);
+    while (cl > 1 && ((c0.n / HU) % cl != 0 || (BM / cl) % 8 != 0)) cl >>= 1;
+    if (cl < 1) cl = 1;
+    // K split over CTA pairs (DSMEM reduction): halves the bytes each SM streams; used when the launch is
+    // small enough that twice the CTAs still fit in one wave
+    int ksplit = (fat && HU == 8 && cl == 1 && 2 * 2 * mt * (c0.n / HU) <= MARLC_SMS) ? 2 : 1;
+    if (const char* env = getenv("MARLC_LSTM_KSPLIT")) ksplit = (atoi(env) == 2 && fat && HU == 8 && cl == 1) ? 2 : 1;
+    const int abox = BM / cl;
     int gx = 0;
     for (int k = 0; k < 2; ++k) {
         const TcLstmArgs& c = *cs[k];
         TcKernelParams& p = kp.p[k];
-        MARLC_TRY(make_map(&p.a1, c.U.ptr, c.Kin, c.M, c.U.slabs, c.U.ld, c.U.slab_stride, BM));
+        p.cluster = cl;
+        p.ksplit = ksplit;
+        MARLC_TRY(make_map(&p.a1, c.U.ptr, c.Kin, c.M, c.U.slabs, c.U.ld, c.U.slab_stride, abox));
         // weights viewed as [gate][unit][K]: ONE box of HU units x 4 gates per K sub-block (the producer
         // thread is issue-bound: 4 separate gate boxes per sub-block made 20 TMA instructions per stage)
         MARLC_TRY(make_map(&p.b1, c.Wih, c.Kin, c.n, 4, c.Kin, (long)c.n * c.Kin, HU, false, 4));
-        MARLC_TRY(make_map(&p.a2, c.Hprev.ptr, c.n, c.M, c.Hprev.slabs, c.Hprev.ld, c.Hprev.slab_stride, BM));
+        MARLC_TRY(make_map(&p.a2, c.Hprev.ptr, c.n, c.M, c.Hprev.slabs, c.Hprev.ld, c.Hprev.slab_stride, abox));
         MARLC_TRY(make_map(&p.b2, c.Whh, c.n, c.n, 4, c.n, (long)c.n * c.n, HU, false, 4));
         p.nk1 = (c.Kin + BKS - 1) / BKS;
         p.nk2 = (c.n + BKS - 1) / BKS;
         p.a_lo_g = (c.x3 && c.U.lo && c.Hprev.lo) ? 1 : 0;
         p.b_lo_g = (c.x3 && c.Wih_lo && c.Whh_lo) ? 1 : 0;
         if (p.a_lo_g) {
-            MARLC_TRY(make_map(&p.a1l, c.U.lo, c.Kin, c.M, c.U.slabs, c.U.ld, c.U.slab_stride, BM));
-            MARLC_TRY(make_map(&p.a2l, c.Hprev.lo, c.n, c.M, c.Hprev.slabs, c.Hprev.ld, c.Hprev.slab_stride, BM));
+            MARLC_TRY(make_map(&p.a1l, c.U.lo, c.Kin, c.M, c.U.slabs, c.U.ld, c.U.slab_stride, abox));
+            MARLC_TRY(make_map(&p.a2l, c.Hprev.lo, c.n, c.M, c.Hprev.slabs, c.Hprev.ld, c.Hprev.slab_stride, abox));
         }
         if (p.b_lo_g) {
             MARLC_TRY(make_map(&p.b1l, c.Wih_lo, c.Kin, c.n, 4, c.Kin, (long)c.n * c.Kin, HU, false, 4));
