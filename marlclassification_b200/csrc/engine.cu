@@ -633,6 +633,11 @@ static int step_networks(marlc_engine* e, int t, const float* img, const int* po
             g[1].A = e->op(pol_x, c.n_a); g[1].B = e->op(e->prm("policy.0.weight"), c.n_a); g[1].K = c.n_a;
             g[1].C = pol_y1; g[1].ldc = c.nl_a; g[1].M = M; g[1].N = c.nl_a; g[1].bias = e->prm("policy.0.bias");
             g[0].x3 = g[1].x3 = x3_of(e);
+            // 8 CTAs would each stream the whole K (the loop is bound by per-SM ingest): split K down to one
+            // stage per CTA; the outputs are zeroed once per episode, the first split adds the bias and the
+            // epilogue is a TMA reduce-add
+            g[0].allow_split = g[1].allow_split = 2;
+            g[0].c_zeroed = g[1].c_zeroed = 1;
             if (tc_operand_ok(g[0].A) && tc_operand_ok(g[0].B) && tc_operand_ok(g[1].A) && tc_operand_ok(g[1].B)) {
                 MARLC_TRY(tc_gemm_group(g, 2, s));
                 grouped = true;
@@ -747,6 +752,10 @@ extern "C" int marlc_episode_forward(marlc_engine* e, const float* img, const in
     ia.M = M; ia.n_m = c.n_m; ia.H = c.H; ia.W = c.W; ia.f = c.f;
     MARLC_TRY(episode_init(ia, s));
     MARLC_TRY(refresh_lo(e, H, Hc, s));
+    if (c.use_chains && c.use_tc) {  // split-K targets of the per-step block-0 GEMMs
+        MARLC_CUDA(cudaMemsetAsync(e->buf("enc_y1"), 0, sizeof(float) * (size_t)e->TM * 2 * c.n_m, s));
+        MARLC_CUDA(cudaMemsetAsync(e->buf("pol_y1"), 0, sizeof(float) * (size_t)e->TM * c.nl_a, s));
+    }
 
     for (int t = 0; t < T; ++t) {
         MARLC_TRY(step_networks(e, t, img, pos_hist + (size_t)t * M * 2, nullptr, msg + (size_t)t * M * c.n_m,
@@ -775,6 +784,10 @@ extern "C" int marlc_model_step(marlc_engine* e, const float* patch, const float
     cudaStream_t s = (cudaStream_t)stream;
     const int start = g_launch_count;
     MARLC_TRY(refresh_lo(e, nullptr, nullptr, s));
+    if (e->cfg.use_chains && e->cfg.use_tc) {
+        MARLC_CUDA(cudaMemsetAsync(e->buf("enc_y1"), 0, sizeof(float) * (size_t)e->M * 2 * e->cfg.n_m, s));
+        MARLC_CUDA(cudaMemsetAsync(e->buf("pol_y1"), 0, sizeof(float) * (size_t)e->M * e->cfg.nl_a, s));
+    }
     MARLC_TRY(step_networks(e, 0, nullptr, nullptr, patch, msg, npos, hidden[0], hidden[1], hidden[2], hidden[3], s));
     // the tail also needs an action to form log p[a]; use the all-zero index buffer
     // (only probs are read back by ModelsWrapper.forward)

@@ -820,7 +820,8 @@ int tc_gemm_group(const TcGemmArgs* args, int count, cudaStream_t s) {
         const int mt = (a.M + BM - 1) / BM, nt = (a.N + BN - 1) / BN, nkb = p.nk1 + p.nk2;
         int splits = 1;
         if (a.allow_split && ctas < MARLC_SMS) {
-            splits = min(max(1, nkb * KS / 4), max(1, (2 * MARLC_SMS) / ctas));
+            // allow_split == 2: latency-bound per-step launch, split down to ONE stage per CTA
+            splits = min(a.allow_split >= 2 ? nkb : max(1, nkb * KS / 4), max(1, (2 * MARLC_SMS) / ctas));
             splits = min(splits, nkb);
             // every split must own at least one K block
             while (splits > 1 && ((nkb + splits - 1) / splits) * (splits - 1) >= nkb) --splits;

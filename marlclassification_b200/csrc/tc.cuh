@@ -38,7 +38,7 @@ struct TcGemmArgs {
     const float* bias = nullptr;
     const float* bias2 = nullptr;
     int accumulate = 0;
-    int allow_split = 0;  // split-K with an atomicAdd epilogue when the grid would be small
+    int allow_split = 0;  // 1: split-K (TMA reduce-add epilogue) when the grid would be small; 2: down to one stage per CTA
     int c_zeroed = 0;     // C is known to be zero already: skip the memset a split-K launch needs
     int x3 = 0;           // error-compensated 3xTF32 (fp32-class accuracy)
 };
