@@ -332,23 +332,29 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
     if (warp == 0) {
         // ============================ TMA producer ============================
         if (lane == 0) {
+            // loop-invariant parameters in registers (a single thread issues every copy of the CTA: constant-
+            // bank reads and their dependent branches inside this loop delayed the first stage by ~500 cycles)
+            int q_nk1 = p.nk1, q_alo = X3 ? p.a_lo_g : 0, q_blo = X3 ? p.b_lo_g : 0;
+            int q_za1 = p.slab_a1, q_za2 = p.slab_a2, q_zb1 = p.slab_b1, q_zb2 = p.slab_b2, q_nh = p.n_hidden;
+            asm volatile("" : "+r"(q_nk1), "+r"(q_alo), "+r"(q_blo), "+r"(q_za1), "+r"(q_za2), "+r"(q_zb1), "+r"(q_zb2), "+r"(q_nh));
+            const uint32_t tx_bytes = S::A_BYTES + S::B_BYTES + (q_alo ? S::A_BYTES : 0) + (q_blo ? S::B_BYTES : 0);
+            (void)q_nh;
             for (int i = 0; i < my_kb; ++i) {
                 const int s = i % stages, ph = (i / stages) & 1;
                 mbar_wait(&empty_bar[s], ph ^ 1);
-                mbar_expect_tx(&full_bar[s], S::A_BYTES + S::B_BYTES + ((X3 && p.a_lo_g) ? S::A_BYTES : 0) +
-                                                 ((X3 && p.b_lo_g) ? S::B_BYTES : 0));
+                mbar_expect_tx(&full_bar[s], tx_bytes);
                 const int kb = kb_begin + i;
-                const bool second = kb >= p.nk1;
-                const int za = second ? p.slab_a2 : p.slab_a1, zb = second ? p.slab_b2 : p.slab_b1;
+                const bool second = kb >= q_nk1;
+                const int za = second ? q_za2 : q_za1, zb = second ? q_zb2 : q_zb1;
                 const int nlo = X3 ? 2 : 1;
                 for (int hl = 0; hl < nlo; ++hl) {  // hl == 1: the pre-split lo tiles (when provided)
-                if (hl == 1 && !p.a_lo_g && !p.b_lo_g) break;
+                if (hl == 1 && !q_alo && !q_blo) break;
                 const CUtensorMap* ma = hl ? (second ? &p.a2l : &p.a1l) : (second ? &p.a2 : &p.a1);
                 const CUtensorMap* mb = hl ? (second ? &p.b2l : &p.b1l) : (second ? &p.b2 : &p.b1);
-                const bool do_a = hl == 0 || p.a_lo_g, do_b = hl == 0 || p.b_lo_g;
+                const bool do_a = hl == 0 || q_alo, do_b = hl == 0 || q_blo;
 #pragma unroll
                 for (int sub = 0; sub < KS; ++sub) {  // sub-blocks past the end of K are zero-filled by TMA
-                    const int k0 = ((second ? kb - p.nk1 : kb) * KS + sub) * BK;
+                    const int k0 = ((second ? kb - q_nk1 : kb) * KS + sub) * BK;
                     uint8_t* a_dst = sA + s * S::A_BYTES + sub * S::A_SUB + hl * LO_OFF;
                     uint8_t* b_dst = sB + s * S::B_BYTES + sub * S::B_SUB + hl * LO_OFF;
                     if (do_a) {
@@ -381,9 +387,11 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) |
                                    ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            int wait_split = (X3 && !(p.a_lo_g && p.b_lo_g)) ? 1 : 0;
+            asm volatile("" : "+r"(wait_split));
             for (int i = 0; i < my_kb; ++i) {
                 const int s = i % stages, ph = (i / stages) & 1;
-                mbar_wait((X3 && !(p.a_lo_g && p.b_lo_g)) ? &split_bar[s] : &full_bar[s], ph);
+                mbar_wait(wait_split ? &split_bar[s] : &full_bar[s], ph);
                 tc_fence_after();
                 if (i == 0) TC_TRACE(2);  // first stage landed (and split)
 #pragma unroll
