@@ -91,3 +91,53 @@ def test_confusion_meter():
     for v in (1.0, 2.0, 3.0):
         lm.add(v)
     assert lm.loss() == 2.5
+
+
+def test_input_pipeline_has_no_cpu_path():
+    """Device-side ToTensor and the prefetcher refuse host tensors / a CPU device loudly."""
+    import pytest
+    import torch
+
+    from marlclassification_b200.input_pipeline import DevicePrefetcher, images_u8_to_f32
+
+    with pytest.raises(RuntimeError):
+        images_u8_to_f32(torch.zeros(1, 4, 4, 3, dtype=torch.uint8))
+    with pytest.raises(RuntimeError):
+        DevicePrefetcher([], "cpu")
+
+
+def test_to_tensor_restatement_matches_torchvision():
+    """oracle.to_tensor_batch == torchvision ToTensor (what registry.py:56-57 composes) on PIL images,
+    checked live when torchvision / PIL are importable (the recorded fixture covers the other case)."""
+    import pytest
+    import torch
+
+    tv = pytest.importorskip("torchvision.transforms")
+    Image = pytest.importorskip("PIL.Image")
+    from oracle import marl_oracle as O
+
+    g = torch.Generator().manual_seed(11)
+    u8 = torch.randint(0, 256, (3, 13, 10, 3), dtype=torch.uint8, generator=g)
+    ref = torch.stack([tv.ToTensor()(Image.fromarray(u8[i].numpy())) for i in range(3)])
+    assert torch.equal(O.to_tensor_batch(u8), ref)
+
+
+def test_bench_reference_arm_runs_without_a_gpu():
+    """`bench.py --impl reference` times the CPU port and prints the contract's JSON line; every
+    other rank of a multi-process launch exits 0 without output."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "c1", "--steps", "1", "--warmup", "1"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "image_episodes_per_sec" and line["value"] > 0
+    assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    other = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=root, env=env)
+    assert other.returncode == 0 and other.stdout.strip() == ""
