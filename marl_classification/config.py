@@ -1,1 +1,1 @@
-from marlclassification_b200.config import ModelConfig  # noqa: F401
+from marlclassification_b200.config import EvalConfig, InferConfig, MainConfig, ModelConfig, TrainConfig  # noqa: F401

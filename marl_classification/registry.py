@@ -1,1 +1,1 @@
-from marlclassification_b200.registry import DATASET_REGISTRY, DatasetSpec, get_dataset_spec  # noqa: F401
+from marlclassification_b200.registry import DATASET_REGISTRY, DatasetSpec, default_image_pipeline, get_dataset_spec  # noqa: F401

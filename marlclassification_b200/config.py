@@ -1,5 +1,6 @@
 """Model configuration with the reference's ``marl.json`` schema (config.py:18-104)
-so reference run directories load unchanged."""
+so reference run directories load unchanged, plus the CLI option groups (config.py:11-15,
+107-131)."""
 from __future__ import annotations
 
 import json
@@ -16,6 +17,13 @@ _FIELDS = (
     "hidden_size_msg_output", "hidden_size_state", "state_dim", "actions", "nb_class",
     "hidden_size_linear_belief", "hidden_size_linear_action",
 )
+
+
+class MainConfig(BaseModel):
+    step: int
+    run_id: str
+    cuda: bool
+    nb_agent: int
 
 
 class ModelConfig(BaseModel):
@@ -57,3 +65,30 @@ class ModelConfig(BaseModel):
     def build_marl(self, nb_agents: int) -> tuple[ModelsWrapper, MultiAgent, Environment]:
         networks = self.build_networks()
         return networks, MultiAgent(nb_agents, networks), self.build_environment()
+
+
+class TrainConfig(BaseModel):
+    img_size: int
+    nb_epoch: int
+    learning_rate: float
+    batch_size: int
+    resources_dir: str
+    output_dir: str
+    gamma: float
+
+
+class EvalConfig(BaseModel):
+    img_size: int
+    state_dict_path: str
+    batch_size: int
+    json_path: str
+    dataset_path: str
+    output_dir: str
+
+
+class InferConfig(BaseModel):
+    state_dict_path: str
+    json_path: str
+    images_path: list[str]
+    output_dir: str
+    class_to_idx: str

@@ -1,6 +1,8 @@
 // Environment kernels: patch gather, integer position transition, normalised
 // positions, episode initial state, and the fused policy-head -> sample ->
 // log-prob -> transition step (reference: core/environment.py, core/agent.py).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -17,10 +19,19 @@ namespace marlc {
 // elements = 32/f source row segments (coalesced within a segment).  All iterations' loads are
 // issued before the first store (UNROLL independent requests per lane) so a window costs about
 // one memory round trip.  Measured 2.4 -> see profiles/README.md for the achieved GB/s.
-template <typename PosT, int UNROLL>
+// Division by a launch-constant d as one multiply-high: q = (n * ceil(2^32 / d)) >> 32 is exact for
+// n * d < 2^32 (the host checks the largest n).  The kernel needs three divisions per element
+// (e -> c, i, j); as runtime `/` they were ~60 of the ~75 instructions per element.
+struct FastDiv {
+    unsigned d, m;
+    __host__ explicit FastDiv(unsigned d_) : d(d_), m((unsigned)((0x100000000ull + d_ - 1) / d_)) {}  // d >= 2
+    __device__ __forceinline__ int div(int n) const { return (int)__umulhi((unsigned)n, m); }
+};
+
+template <typename PosT, int UNROLL, bool FAST>
 __global__ void __launch_bounds__(256)
 patch_gather_kernel(const float* __restrict__ img, const PosT* __restrict__ pos, float* __restrict__ obs, int Na, int B,
-                    int C, int H, int W, int f) {
+                    int C, int H, int W, int f, FastDiv dff, FastDiv df) {
     const int lane = threadIdx.x & 31;
     // consecutive warps take the agents of ONE image (b-major): an image is then read in a burst
     // while its DRAM pages are open / its sectors are in L2, instead of once per agent row
@@ -29,25 +40,30 @@ patch_gather_kernel(const float* __restrict__ img, const PosT* __restrict__ pos,
     const int b = g / Na, m = (g - b * Na) * B + b;  // output row m = a*B + b
     const int py = (int)pos[2 * (long)m], px = (int)pos[2 * (long)m + 1];
     const int ff = f * f, total = C * ff;
-    const float* src = img + (long)b * C * H * W + (long)py * W + px;
+    const int plane = H * W;  // offsets inside one image fit 32 bits (host-checked)
+    const float* src = img + (long)b * C * plane + (py * W + px);
     float* dst = obs + (long)m * total;
-    const long plane = (long)H * W;
     for (int e0 = lane; e0 < total; e0 += 32 * UNROLL) {
         float v[UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-            const int e = e0 + 32 * u;
-            if (e < total) {
-                const int c = e / ff, r = e - c * ff, i = r / f, j = r - i * f;
-                v[u] = __ldg(src + c * plane + (long)i * W + j);
-            }
+            // tail lanes re-read the last element instead of branching around the load
+            const int e = min(e0 + 32 * u, total - 1);
+            const int c = FAST ? dff.div(e) : e / ff;
+            const int r = e - c * ff;
+            const int i = FAST ? df.div(r) : r / f;
+            v[u] = __ldg(src + (c * plane + i * W + (r - i * f)));
         }
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            const int e = e0 + 32 * u;
-            if (e < total) dst[e] = v[u];
-        }
+        for (int u = 0; u < UNROLL; ++u)
+            if (e0 + 32 * u < total) dst[e0 + 32 * u] = v[u];
     }
+}
+
+// MARLC_GATHER_DIV=1 selects the runtime-division body (kept for A/B timing, scripts/gather_ab.py).
+static bool gather_use_div() {
+    const char* e = getenv("MARLC_GATHER_DIV");
+    return e && e[0] == '1';
 }
 
 template <typename PosT>
@@ -57,8 +73,15 @@ static int patch_gather_t(const float* img, const PosT* pos, float* obs, int Na,
     const int M = Na * B;
     if (M <= 0) return 0;
     const int blocks = (M + 7) / 8;  // 8 warps = 8 windows per CTA
-    if (C * f * f <= 32 * 8) patch_gather_kernel<PosT, 8><<<blocks, 256, 0, s>>>(img, pos, obs, Na, B, C, H, W, f);
-    else patch_gather_kernel<PosT, 16><<<blocks, 256, 0, s>>>(img, pos, obs, Na, B, C, H, W, f);
+    const long ff = (long)f * f, total = (long)C * ff;
+    MARLC_CHECK((long)C * H * W < 0x7fffffffl, "patch_gather: one image must hold fewer than 2^31 elements");
+    const bool fast = f >= 2 && total * ff < 0x100000000ll && !gather_use_div();  // FastDiv exactness bound
+    const FastDiv dff((unsigned)max(ff, 2l)), df((unsigned)max(f, 2));
+#define MARLC_GATHER_LAUNCH(U, F) \
+    patch_gather_kernel<PosT, U, F><<<blocks, 256, 0, s>>>(img, pos, obs, Na, B, C, H, W, f, dff, df)
+    if (total <= 32 * 8) { if (fast) MARLC_GATHER_LAUNCH(8, true); else MARLC_GATHER_LAUNCH(8, false); }
+    else { if (fast) MARLC_GATHER_LAUNCH(16, true); else MARLC_GATHER_LAUNCH(16, false); }
+#undef MARLC_GATHER_LAUNCH
     MARLC_LAUNCH_CHECK();
     return 0;
 }

@@ -1,5 +1,5 @@
 """Sliding-window meters used by the Trainer (reference: metrics.py).  Host-side
-bookkeeping only; matplotlib (absent from the image) is imported lazily."""
+bookkeeping only; the confusion-matrix picture is drawn with PIL (no matplotlib needed)."""
 from __future__ import annotations
 
 from typing import Optional
@@ -43,16 +43,17 @@ class ConfusionMeter:
         return th.where(tot != 0, cm.diagonal() / tot.clamp(min=1.0), th.zeros_like(tot))
 
     def save_conf_matrix(self, epoch: int, output_dir: str, stage: str) -> None:
+        """Row-normalised confusion matrix as ``confusion_matrix_epoch_{e}_{stage}.png``
+        (metrics.py:110-129).  Drawn with PIL: matplotlib is not a dependency of this build."""
         import os
 
-        import matplotlib.pyplot as plt  # lazy: not installed in every image
+        from .visualization import heatmap_image
 
-        cm = self.conf_mat().cpu().numpy()
-        fig = plt.figure()
-        plt.matshow(cm, fignum=fig.number)
-        plt.title(f"confusion matrix epoch {epoch} - {stage}")
-        plt.savefig(os.path.join(output_dir, f"confusion_matrix_epoch_{epoch}_{stage}.png"))
-        plt.close(fig)
+        cm = self.conf_mat().to(th.float).cpu()
+        norm = cm / cm.sum(dim=1, keepdim=True).clamp(min=1.0)
+        img = heatmap_image(norm, title=f"confusion matrix epoch {epoch} - {stage}",
+                            xlabel="Predicated Label", ylabel="True Label")
+        img.save(os.path.join(output_dir, f"confusion_matrix_epoch_{epoch}_{stage}.png"))
 
 
 class LossMeter:

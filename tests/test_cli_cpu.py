@@ -1,0 +1,191 @@
+"""CPU checks of the CLI layer (reference: __main__.py, train.py, eval.py, infer.py,
+data/datasets.py, visualization.py): option surface, image-folder dataset against torchvision's
+ImageFolder + ToTensor (what the reference uses), data-parallel batch sampler, tracker and the
+PIL-drawn pictures.  Nothing here runs the episode (that is tests/test_gpu_cli.py)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+from PIL import Image
+
+from marlclassification_b200.__main__ import DEFAULT_ACTIONS, build_parser, main, parse_actions
+from marlclassification_b200.data import (
+    FolderDataset, ShardedBatchSampler, collate_images, default_image_pipeline, u8_image_pipeline,
+)
+from marlclassification_b200.registry import DATASET_REGISTRY, get_dataset_spec
+from tests.clidata import make_image_folder
+
+
+def test_parser_defaults_match_reference_cli():
+    """Defaults of __main__.py:47-219 (agents 3, step 7, f 7, nb 64, na 16, nm 16, nmo 24, nd 4,
+    nlb = nla = 128, batch 8, lr 1e-3, gamma 0.99, 10 epochs, mnist)."""
+    a = build_parser().parse_args(["--run-id", "r", "train", "-o", "out"])
+    assert (a.agents, a.step, a.cuda, a.main_choice) == (3, 7, False, "train")
+    assert (a.f, a.dim, a.n_b, a.n_a, a.n_m, a.n_m_o, a.n_d, a.n_l_b, a.n_l_a) == (7, 2, 64, 16, 16, 24, 4, 128, 128)
+    assert (a.batch_size, a.learning_rate, a.gamma, a.nb_epoch, a.ft_extr_str, a.nb_class, a.img_size) == (
+        8, 1e-3, 0.99, 10, "mnist", 10, 28)
+    assert parse_actions(a.action, a.dim) == [[1, 0], [-1, 0], [0, 1], [0, -1]] and a.action == DEFAULT_ACTIONS
+    t = build_parser().parse_args(["--run-id", "r", "-a", "5", "--step", "9", "--cuda", "test", "--dataset-path", "d",
+                                   "--json-path", "j", "--state-dict-path", "s", "-o", "o"])
+    assert (t.agents, t.step, t.cuda, t.batch_size, t.main_choice) == (5, 9, True, 8, "test")
+    i = build_parser().parse_args(["--run-id", "r", "infer", "--images", "a.png", "b/*.png", "--json-path", "j",
+                                   "--state-dict-path", "s", "--class2idx", "c", "-o", "o"])
+    assert i.infer_images == ["a.png", "b/*.png"] and i.output_image_dir == "o"
+
+
+def test_parser_requires_run_id_mode_and_output():
+    for argv in (["train", "-o", "x"], ["--run-id", "r"], ["--run-id", "r", "train"],
+                 ["--run-id", "r", "train", "-o", "x", "--ft-extr", "imagenet"]):
+        with pytest.raises(SystemExit):
+            build_parser().parse_args(argv)
+
+
+@pytest.mark.parametrize("text", ["[[1,0],[1]]x", "[1,0]", "[[1.5,0]]", "[]", "[[true,0]]", "[[]]"])
+def test_parse_actions_rejects_malformed(text):
+    with pytest.raises(ValueError, match="Wrong action"):
+        parse_actions(text, 2)
+
+
+def test_parse_actions_checks_dimension():
+    assert parse_actions("[[3,0],[-3,0],[0,0]]", 2) == [[3, 0], [-3, 0], [0, 0]]
+    with pytest.raises(AssertionError, match="index 1"):
+        parse_actions("[[1,0],[1,0,0]]", 2)
+
+
+def test_cli_without_cuda_flag_fails_loudly(tmp_path):
+    """The reference falls back to CPU without --cuda; this build must refuse (no CPU path)."""
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        main(["--run-id", "r", "train", "-o", str(tmp_path / "out"), "--res-folder", str(tmp_path)])
+
+
+def test_registry_has_reference_names_and_both_constructors(tmp_path):
+    assert sorted(DATASET_REGISTRY) == ["aid", "kneemri", "mnist", "resisc45", "skin_cancer", "worldstrat"]
+    with pytest.raises(AssertionError, match="Unknown dataset"):
+        get_dataset_spec("cifar")
+    with pytest.raises(NotImplementedError):
+        get_dataset_spec("kneemri").dataset_constructor(str(tmp_path), default_image_pipeline())
+    with pytest.raises(AssertionError, match="does not exist"):
+        get_dataset_spec("aid").dataset_constructor(str(tmp_path), default_image_pipeline())
+    root = make_image_folder(str(tmp_path / "downloaded" / "mnist_png" / "all_png"), classes=3, per_class=2, size=28)
+    ds = get_dataset_spec("mnist").dataset_constructor(str(tmp_path), default_image_pipeline())
+    assert ds.root == root and len(ds) == 6
+
+
+def test_folder_dataset_equals_torchvision_imagefolder(tmp_path):
+    """Same class_to_idx, same sample order, bit-identical pixels as ImageFolder + ToTensor with the
+    reference's RGB loader (datasets.py:16-43, registry.py:56-57), grey-scale PNGs included."""
+    tv = pytest.importorskip("torchvision")
+    root = make_image_folder(str(tmp_path / "imgs"), classes=4, per_class=3, size=20, grey_every=2, nested=True)
+    ours = FolderDataset(root, default_image_pipeline())
+    ref = tv.datasets.ImageFolder(root, transform=tv.transforms.Compose([tv.transforms.ToTensor()]),
+                                  loader=lambda p: Image.open(p).convert("RGB"))
+    assert ours.class_to_idx == ref.class_to_idx
+    assert ours.samples == ref.samples and ours.targets == ref.targets
+    raw = FolderDataset(root, u8_image_pipeline())
+    for k in range(len(ref)):
+        (xo, yo), (xr, yr), (xb, _) = ours[k], ref[k], raw[k]
+        assert yo == yr and xo.dtype == torch.float32 and torch.equal(xo, xr)
+        assert xb.dtype == torch.uint8 and xb.shape == (20, 20, 3)
+        assert torch.equal(xb.permute(2, 0, 1).float().div(255), xr)  # the conversion the device kernel performs
+
+
+def test_folder_dataset_errors(tmp_path):
+    with pytest.raises(AssertionError):
+        FolderDataset(str(tmp_path / "missing"), default_image_pipeline())
+    with pytest.raises(FileNotFoundError):
+        FolderDataset(str(tmp_path), default_image_pipeline())
+    os.makedirs(tmp_path / "c0")
+    (tmp_path / "c0" / "notes.txt").write_text("x")
+    with pytest.raises(FileNotFoundError):
+        FolderDataset(str(tmp_path), default_image_pipeline())
+
+
+def test_collate_images_stacks_bytes_and_labels():
+    items = [(torch.full((5, 4, 3), k, dtype=torch.uint8), k) for k in range(3)]
+    x, y = collate_images(items)
+    assert x.shape == (3, 5, 4, 3) and x.dtype == torch.uint8 and y.dtype == torch.int64 and y.tolist() == [0, 1, 2]
+
+
+@pytest.mark.parametrize("length,batch,world", [(37, 8, 1), (37, 8, 2), (64, 16, 4), (5, 8, 2), (3, 4, 4), (0, 4, 2)])
+def test_sharded_batch_sampler_partitions_each_global_batch(length, batch, world):
+    """Ranks agree on the global batches, take disjoint equal slices of each, and together cover
+    every index except the (< world) images trimmed from a ragged last batch."""
+    samplers = [ShardedBatchSampler(length, batch, r, world, shuffle=True, seed=3) for r in range(world)]
+    per_rank = [list(s) for s in samplers]
+    assert len({len(b) for b in per_rank}) == 1 and all(len(b) == len(samplers[0]) for b in per_rank)
+    seen = []
+    for step in zip(*per_rank):
+        assert len({len(s) for s in step}) == 1  # equal shards -> grad average == global mean
+        merged = [i for s in step for i in s]
+        assert len(merged) <= batch and len(set(merged)) == len(merged)
+        seen += merged
+    assert len(set(seen)) == len(seen) and set(seen) <= set(range(length))
+    full, rest = divmod(length, batch)
+    assert len(seen) == full * batch + rest - rest % world
+    if world == 1:
+        assert sorted(seen) == list(range(length))  # drop_last=False, like the reference's loaders
+
+
+def test_sharded_batch_sampler_epochs_and_validation():
+    s = ShardedBatchSampler(50, 10, 0, 1, shuffle=True, seed=1)
+    e0 = list(s)
+    assert list(s) == e0  # deterministic within an epoch: every rank can rebuild it
+    s.set_epoch(1)
+    assert list(s) != e0 and sorted(i for b in s for i in b) == list(range(50))
+    assert list(ShardedBatchSampler(5, 2, shuffle=False)) == [[0, 1], [2, 3], [4]]
+    with pytest.raises(ValueError):
+        ShardedBatchSampler(10, 6, 0, 4)
+    with pytest.raises(ValueError):
+        ShardedBatchSampler(10, 8, 4, 4)
+
+
+def test_run_tracker_jsonl_backend(tmp_path):
+    from marlclassification_b200.tracking import RunTracker
+
+    tr = RunTracker("MARLClassification", "train_x", str(tmp_path), use_mlflow=False)
+    assert tr.backend == "jsonl"
+    tr.log_param("device", "cuda")
+    tr.log_params({"step": 5, "actions": [[1, 0]]})
+    tr.log_metrics(0, {"loss": 1.5})
+    tr.log_metrics(100, {"loss": 0.5, "train_prec": 0.25})
+    tr.end()
+    params = json.load(open(tmp_path / "params.json"))
+    assert params["run_name"] == "train_x" and params["device"] == "cuda" and params["actions"] == [[1, 0]]
+    rows = [json.loads(line) for line in open(tmp_path / "metrics.jsonl")]
+    assert [r["step"] for r in rows] == [0, 100] and rows[1]["train_prec"] == 0.25
+
+
+def test_confusion_matrix_png_and_visualised_episode(tmp_path):
+    """File names of metrics.py:110-129 and visualization.py:45-99; the episode is a stub (the
+    real one needs the GPU), which pins what visualize_steps consumes: step_preds / step_pos."""
+    from marlclassification_b200.core.episode import EpisodeDetailedOutput
+    from marlclassification_b200.metrics import ConfusionMeter
+    from marlclassification_b200.visualization import visualize_steps
+
+    cm = ConfusionMeter(3)
+    cm.add(torch.eye(3)[[0, 1, 1, 2]], torch.tensor([0, 1, 2, 2]))
+    cm.save_conf_matrix(4, str(tmp_path), "eval")
+    assert Image.open(tmp_path / "confusion_matrix_epoch_4_eval.png").size[0] > 0
+
+    T, Na, f, H, W = 3, 2, 4, 12, 10
+
+    class StubSampler:
+        def run_episode(self, img):
+            assert img.shape == (1, 1, H, W)
+            preds = torch.zeros(T, Na, 1, 3)
+            preds[:, :, :, 2] = 5.0
+            pos = torch.tensor([[[[t, t + a]] for a in range(Na)] for t in range(T)])
+            return EpisodeDetailedOutput(preds, torch.zeros(T, Na, 1), torch.zeros(T, Na, 1), pos)
+
+    img = torch.rand(1, H, W)
+    visualize_steps(StubSampler(), img, img, f, str(tmp_path), {"zero": 0, "one": 1, "two": 2})
+    names = sorted(os.listdir(tmp_path))
+    assert {"pred_original.png", "pred_step_0.png", "pred_step_2.png", "animated_gif.gif"} <= set(names)
+    gif = Image.open(tmp_path / "animated_gif.gif")
+    # PIL folds the five identical "original" frames into one shown 5 x 200 ms
+    assert gif.n_frames == 1 + T and gif.info["duration"] == 1000
+    # the last frame shows exactly the uncovered windows: pixel (0,0) was seen at t=0 by agent 0
+    frame = np.asarray(Image.open(tmp_path / "pred_step_2.png").convert("RGB"))
+    assert frame.shape[0] > H and frame.shape[1] >= W
