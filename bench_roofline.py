@@ -159,6 +159,19 @@ def transition(M: int, H: int, W: int, f: int, dev, reps: int = 100) -> dict:
             "bytes_per_launch": bytes_alg, "gbs": bytes_alg / t / 1e9}
 
 
+def to_tensor_u8(B: int, C: int, H: int, W: int, dev, reps: int = 50) -> dict:
+    """Device-side ToTensor (u8[B,H,W,C] -> f32[B,C,H,W] / 255), the input pipeline's kernel."""
+    from marlclassification_b200.input_pipeline import images_u8_to_f32
+
+    g = torch.Generator(device=dev).manual_seed(0)
+    src = torch.randint(0, 256, (B, H, W, C), device=dev, generator=g, dtype=torch.uint8)
+    out = torch.empty(B, C, H, W, device=dev)
+    t = _time(lambda: images_u8_to_f32(src, out, hwc=True), reps)
+    bytes_alg = 5.0 * B * C * H * W  # 1 byte read + 4 bytes written per element (DESIGN section 4)
+    return {"kernel": "images_u8_to_f32 (HWC)", "shape": {"images": B, "C": C, "image": [H, W]},
+            "us_per_launch": t * 1e6, "bytes_per_launch": bytes_alg, "gbs": bytes_alg / t / 1e9}
+
+
 def roofline_for(model, w: dict, nb: int, dev) -> dict:
     """The `roofline` object of bench.py's JSON line (+ the secondary kernels)."""
     pk, src = peaks()
@@ -172,6 +185,8 @@ def roofline_for(model, w: dict, nb: int, dev) -> dict:
     g_small = gather(w["na"], nb, w["C"], w["H"], w["W"], w["f"], dev)
     g_big = gather(256, 256, w["C"], w["H"], w["W"], w["f"], dev, reps=50)  # 65536 windows: saturating
     tr_big = transition(1 << 24, w["H"], w["W"], w["f"], dev, reps=20)
+    n_img = max(1, (1 << 28) // (w["C"] * w["H"] * w["W"]))  # 268 M elements: 1.3 GB moved, far beyond L2
+    tt_big = to_tensor_u8(n_img, w["C"], w["H"], w["W"], dev, reps=20)
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
@@ -199,6 +214,9 @@ def roofline_for(model, w: dict, nb: int, dev) -> dict:
             {"kernel": "transition_i64_kernel @ 16.8 M agents (saturating)", "bound": "hbm", "achieved": tr_big["gbs"],
              "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": tr_big["gbs"] / pk["hbm_gbs"],
              "launch_us": tr_big["us_per_launch"], "bytes_per_launch": tr_big["bytes_per_launch"]},
+            {"kernel": f"images_u8_to_f32 @ {n_img} images (saturating)", "bound": "hbm", "achieved": tt_big["gbs"],
+             "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": tt_big["gbs"] / pk["hbm_gbs"],
+             "launch_us": tt_big["us_per_launch"], "bytes_per_launch": tt_big["bytes_per_launch"]},
         ],
     }
 
@@ -216,3 +234,5 @@ if __name__ == "__main__":
     print(json.dumps(gather(256, 64, 3, 600, 600, 24, dev, reps=50)))
     for M in (128, 1 << 20, 1 << 24):
         print(json.dumps(transition(M, 256, 256, 12, dev, reps=20)))
+    print(json.dumps(to_tensor_u8(8, 3, 256, 256, dev)))
+    print(json.dumps(to_tensor_u8(1365, 3, 256, 256, dev, reps=20)))

@@ -9,6 +9,11 @@
 //   * GroupNorm + SiLU backward -> dY_l (row layout for the GEMMs) and the per-window
 //     dgamma / dbeta partials,
 //   * im2col of the recomputed activation A_l -> col_{l+1} (operand of dW_{l+1}).
+#include <stdlib.h>
+
+#include <algorithm>
+
+#include "common.cuh"
 #include "kernels.cuh"
 
 namespace marlc {
@@ -18,8 +23,17 @@ constexpr float GN_EPS2 = 1e-5f;
 struct CnnBwdLayerKernelArgs {
     CnnBwdLayerArgs a;
     int total, npos, npn, per_warp;  // per_warp: floats of smem per warp (3 * total rounded + staged dCol block)
+    FastDiv d_npos, d_ho, d_co, d_kk, d_hon;  // index decompositions without runtime division
 };
 
+// MARLC_CNNBWD_DIV=1 selects the runtime-division instantiation (A/B timing only).
+static bool cnn_bwd_use_div() {
+    const char* e = getenv("MARLC_CNNBWD_DIV");
+    return e && e[0] == '1';
+}
+#define MARLC_DIV(n, fd, d) (FAST ? (fd).div(n) : (n) / (d))
+
+template <bool FAST>
 __global__ void __launch_bounds__(256) cnn_bwd_layer_kernel(const CnnBwdLayerKernelArgs ka) {
     extern __shared__ float sm[];
     const CnnBwdLayerArgs& a = ka.a;
@@ -63,7 +77,8 @@ __global__ void __launch_bounds__(256) cnn_bwd_layer_kernel(const CnnBwdLayerKer
         for (int e = lane; e < total; e += 32) xh[e] = yg[e];
         __syncwarp();
         for (int e = lane; e < total; e += 32) {
-            const int c = e / npos, pos = e - c * npos, iy = pos / ho, ix = pos - iy * ho;
+            const int c = MARLC_DIV(e, ka.d_npos, npos), pos = e - c * npos, iy = MARLC_DIV(pos, ka.d_ho, ho),
+                      ix = pos - iy * ho;
             float acc = 0.f;
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky) {
@@ -95,7 +110,7 @@ __global__ void __launch_bounds__(256) cnn_bwd_layer_kernel(const CnnBwdLayerKer
         const float rstd = 1.0f / sqrtf(warp_sum(v) * inv + GN_EPS2);
         float s1 = 0.f, s2 = 0.f;
         for (int e = lane; e < ng; e += 32) {
-            const int c = g * cpg + e / npos;
+            const int c = g * cpg + MARLC_DIV(e, ka.d_npos, npos);
             const float gam = a.gn_w[c];
             const float x = (xg[e] - mean) * rstd, z = x * gam + a.gn_b[c];
             const float sg = sigmoidf_(z);
@@ -124,7 +139,7 @@ __global__ void __launch_bounds__(256) cnn_bwd_layer_kernel(const CnnBwdLayerKer
         }
         __syncwarp();
         for (int e = lane; e < ng; e += 32) {
-            const int c = g * cpg + e / npos;
+            const int c = g * cpg + MARLC_DIV(e, ka.d_npos, npos);
             dg[e] = rstd * (dg[e] * a.gn_w[c] - s1 - xg[e] * s2);
         }
         if (fold) {  // conv bias gradient: sum of dY over the positions of each channel
@@ -141,7 +156,7 @@ __global__ void __launch_bounds__(256) cnn_bwd_layer_kernel(const CnnBwdLayerKer
     {
         float* dyg = a.dY + (long)p * total;
         for (int e = lane; e < total; e += 32) {
-            const int pos = e / co_n, c = e - pos * co_n;
+            const int pos = MARLC_DIV(e, ka.d_co, co_n), c = e - pos * co_n;
             dyg[e] = dz[c * npos + pos];
         }
     }
@@ -150,8 +165,9 @@ __global__ void __launch_bounds__(256) cnn_bwd_layer_kernel(const CnnBwdLayerKer
         const int hon = a.ho_next, npn = ka.npn, kk = co_n * 9;
         float* cg = a.colNext + (long)p * npn * kk;
         for (int e = lane; e < npn * kk; e += 32) {
-            const int o = e / kk, r = e - o * kk, c = r / 9, q = r - c * 9, ky = q / 3, kx = q - ky * 3;
-            const int iy = 2 * (o / hon) - 1 + ky, ix = 2 * (o % hon) - 1 + kx;
+            const int o = MARLC_DIV(e, ka.d_kk, kk), r = e - o * kk, c = r / 9, q = r - c * 9, ky = q / 3, kx = q - ky * 3;
+            const int oy = MARLC_DIV(o, ka.d_hon, hon);
+            const int iy = 2 * oy - 1 + ky, ix = 2 * (o - oy * hon) - 1 + kx;
             cg[e] = (iy >= 0 && iy < ho && ix >= 0 && ix < ho) ? act[c * npos + iy * ho + ix] : 0.f;
         }
     }
@@ -181,22 +197,33 @@ int cnn_bwd_layer(const CnnBwdLayerArgs& a, cudaStream_t s) {
                 "cnn_bwd_layer: give either gnpart or all three accumulation targets");
     const size_t smem = ((size_t)wpc * ka.per_warp + 3 * a.cout) * sizeof(float);
     MARLC_CHECK(smem <= 200 * 1024, "cnn_bwd_layer: layer too large for shared memory (%zu B)", smem);
+    ka.d_npos = FastDiv((unsigned)ka.npos);
+    ka.d_ho = FastDiv((unsigned)a.ho);
+    ka.d_co = FastDiv((unsigned)a.cout);
+    ka.d_kk = FastDiv((unsigned)(a.cout * 9));
+    ka.d_hon = FastDiv((unsigned)std::max(a.ho_next, 1));
+    // FastDiv exactness: the largest dividends are total (/ npos, / cout) and npn * kk (/ kk)
+    const long nmax = std::max((long)ka.total, (long)ka.npn * a.cout * 9);
+    const bool fast = nmax * std::max(std::max(ka.npos, a.cout * 9), 1) < 0x100000000ll && !cnn_bwd_use_div();
     static size_t attr = 0;
     if (smem > 48 * 1024 && smem > attr) {
-        MARLC_CUDA(cudaFuncSetAttribute(cnn_bwd_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MARLC_CUDA(cudaFuncSetAttribute(cnn_bwd_layer_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MARLC_CUDA(cudaFuncSetAttribute(cnn_bwd_layer_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = smem;
     }
-    cnn_bwd_layer_kernel<<<(a.P + wpc - 1) / wpc, wpc * 32, smem, s>>>(ka);
+    if (fast) cnn_bwd_layer_kernel<true><<<(a.P + wpc - 1) / wpc, wpc * 32, smem, s>>>(ka);
+    else cnn_bwd_layer_kernel<false><<<(a.P + wpc - 1) / wpc, wpc * 32, smem, s>>>(ka);
     MARLC_LAUNCH_CHECK();
     return 0;
 }
 
 // im2col of the gathered input windows (operand of the first layer's weight gradient):
 // col[(p*npos + o), ci*9 + ky*3 + kx] = img[b, ci, py + 2oy-1+ky, px + 2ox-1+kx] (0 outside the window)
+template <bool FAST>
 __global__ void __launch_bounds__(256) cnn_im2col_input_kernel(const float* __restrict__ img,
                                                                const int* __restrict__ pos_hist, float* __restrict__ col,
                                                                int P, int M, int B, int img_c, int cin, int H, int W,
-                                                               int f, int ho) {
+                                                               int f, int ho, FastDiv d_kk, FastDiv d_ho) {
     const int lane = threadIdx.x & 31;
     const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (p >= P) return;
@@ -205,8 +232,9 @@ __global__ void __launch_bounds__(256) cnn_im2col_input_kernel(const float* __re
     const int kk = cin * 9, npos = ho * ho;
     float* cg = col + (long)p * npos * kk;
     for (int e = lane; e < npos * kk; e += 32) {
-        const int o = e / kk, r = e - o * kk, c = r / 9, q = r - c * 9, ky = q / 3, kx = q - ky * 3;
-        const int iy = 2 * (o / ho) - 1 + ky, ix = 2 * (o % ho) - 1 + kx;
+        const int o = MARLC_DIV(e, d_kk, kk), r = e - o * kk, c = r / 9, q = r - c * 9, ky = q / 3, kx = q - ky * 3;
+        const int oy = MARLC_DIV(o, d_ho, ho);
+        const int iy = 2 * oy - 1 + ky, ix = 2 * (o - oy * ho) - 1 + kx;
         cg[e] = (iy >= 0 && iy < f && ix >= 0 && ix < f) ? __ldg(src + ((long)c * H + py + iy) * W + px + ix) : 0.f;
     }
 }
@@ -214,7 +242,10 @@ __global__ void __launch_bounds__(256) cnn_im2col_input_kernel(const float* __re
 int cnn_im2col_input(const float* img, const int* pos_hist, float* col, int P, int M, int B, int img_c, int cin, int H,
                      int W, int f, int ho, cudaStream_t s) {
     if (P <= 0) return 0;
-    cnn_im2col_input_kernel<<<(P * 32 + 255) / 256, 256, 0, s>>>(img, pos_hist, col, P, M, B, img_c, cin, H, W, f, ho);
+    const FastDiv d_kk((unsigned)(cin * 9)), d_ho((unsigned)ho);
+    const bool fast = (long)ho * ho * cin * 9 * cin * 9 < 0x100000000ll && !cnn_bwd_use_div();
+    if (fast) cnn_im2col_input_kernel<true><<<(P * 32 + 255) / 256, 256, 0, s>>>(img, pos_hist, col, P, M, B, img_c, cin, H, W, f, ho, d_kk, d_ho);
+    else cnn_im2col_input_kernel<false><<<(P * 32 + 255) / 256, 256, 0, s>>>(img, pos_hist, col, P, M, B, img_c, cin, H, W, f, ho, d_kk, d_ho);
     MARLC_LAUNCH_CHECK();
     return 0;
 }

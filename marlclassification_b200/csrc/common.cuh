@@ -50,6 +50,18 @@ __device__ __forceinline__ float silu_grad_(float z) {
     return s * (1.0f + z * (1.0f - s));
 }
 
+// Division by a launch-constant d as one multiply-high: q = (n * ceil(2^32 / d)) >> 32, exact for
+// 0 <= n and n * d < 2^32 (callers check their largest n on the host).  Runtime `/` costs ~20
+// instructions; index decompositions (e -> channel, row, column) are often most of an
+// element-wise kernel's issue slots.
+struct FastDiv {
+    unsigned d, m;
+    FastDiv() : d(1), m(0) {}
+    __host__ explicit FastDiv(unsigned d_) : d(d_), m(d_ > 1 ? (unsigned)((0x100000000ull + d_ - 1) / d_) : 0u) {}
+    __device__ __forceinline__ int div(int n) const { return d > 1 ? (int)__umulhi((unsigned)n, m) : n; }
+    __device__ __forceinline__ int div_nz(int n) const { return (int)__umulhi((unsigned)n, m); }  // d >= 2 only
+};
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
