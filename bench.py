@@ -136,7 +136,7 @@ def cpu_port_iteration_fn(w: dict, nb: int, threads: int, device: str = "cpu"):
         opt.zero_grad()
         parts.loss.backward()
         opt.step()
-        return float(parts.loss)
+        return float(parts.loss.detach())
 
     return one_iteration
 
