@@ -34,59 +34,59 @@ def parse_actions(text: str, dim: int) -> List[List[int]]:
 
 def build_parser() -> argparse.ArgumentParser:
     parser = argparse.ArgumentParser("Multi agent reinforcement learning for image classification - Main")
-    parser.add_argument("--run-id", type=str, required=True, dest="run_id", help="run id (MLflow run name when MLflow is installed)")
-    parser.add_argument("-a", "--agents", type=int, default=3, dest="agents", help="Number of agents")
-    parser.add_argument("--step", type=int, default=7, help="Step number of RL episode")
+    parser.add_argument("--run-id", type=str, required=True, dest="run_id", help="name of this run (MLflow run name when MLflow is installed)")
+    parser.add_argument("-a", "--agents", type=int, default=3, dest="agents", help="agents per image")
+    parser.add_argument("--step", type=int, default=7, help="moves per episode (T)")
     parser.add_argument("--cuda", action="store_true", dest="cuda", help="Run on CUDA (required: this build has no CPU path)")
     modes = parser.add_subparsers(dest="main_choice", required=True)
 
     train = modes.add_parser("train")
-    train.add_argument("--action", type=str, default=DEFAULT_ACTIONS, dest="action", help="Discrete actions")
-    train.add_argument("--img-size", type=int, default=28, dest="img_size", help="Image side size, assume all image are squared")
-    train.add_argument("--nb-class", type=int, default=10, dest="nb_class", help="Image dataset number of class")
-    train.add_argument("-d", "--dim", type=int, default=2, help="State dimension (eg. 2 -> move on a plan)")
-    train.add_argument("--f", type=int, default=7, help="Window size")
+    train.add_argument("--action", type=str, default=DEFAULT_ACTIONS, dest="action", help="move table as a JSON list of integer pairs")
+    train.add_argument("--img-size", type=int, default=28, dest="img_size", help="side of the (square) images; recorded with the run")
+    train.add_argument("--nb-class", type=int, default=10, dest="nb_class", help="number of classes")
+    train.add_argument("-d", "--dim", type=int, default=2, help="dimension of an agent position (2 only)")
+    train.add_argument("--f", type=int, default=7, help="side f of the observation window")
     train.add_argument("--ft-extr", type=str, choices=sorted(DATASET_REGISTRY), default="mnist", dest="ft_extr_str",
-                       help="Choose features extractor (CNN)")
+                       help="dataset / feature-extractor pair from the registry")
     for flag, dest, default, text in (
-        ("--nb", "n_b", 64, "Hidden size for belief LSTM"),
-        ("--na", "n_a", 16, "Hidden size for action LSTM"),
-        ("--nm", "n_m", 16, "Message size for NNs"),
-        ("--nmo", "n_m_o", 24, "Received message output size for NNs"),
-        ("--nd", "n_d", 4, "State hidden size"),
-        ("--nlb", "n_l_b", 128, "Network internal hidden size for linear projections (belief unit)"),
-        ("--nla", "n_l_a", 128, "Network internal hidden size for linear projections (action unit)"),
+        ("--nb", "n_b", 64, "belief LSTM width n_b"),
+        ("--na", "n_a", 16, "action LSTM width n_a"),
+        ("--nm", "n_m", 16, "message width n_m"),
+        ("--nmo", "n_m_o", 24, "decoded message width n_m_o"),
+        ("--nd", "n_d", 4, "position feature width n_d"),
+        ("--nlb", "n_l_b", 128, "hidden width of the prediction head"),
+        ("--nla", "n_l_a", 128, "hidden width of the policy and critic heads"),
     ):
         train.add_argument(flag, type=int, default=default, dest=dest, help=text)
     train.add_argument("--res-folder", type=str, required=False,
                        default=abspath(join(dirname(abspath(__file__)), "..", "resources")),
-                       help="The resources path containing the download folder with datasets")
+                       help="directory holding downloaded/<dataset>")
     train.add_argument("-o", "--output-dir", type=str, required=True, dest="output_dir",
-                       help="The output directory containing results and models per epoch. Created if needed.")
+                       help="run directory (created): marl.json, class_to_idx.json, models/, pictures")
     train.add_argument("--batch-size", type=int, default=8, dest="batch_size",
-                       help="Image batch size for training and evaluation (global batch under torchrun)")
-    train.add_argument("--lr", "--learning-rate", type=float, default=1e-3, dest="learning_rate", help="learning rate")
-    train.add_argument("--gamma", type=float, default=0.99, help="discount factor")
-    train.add_argument("--nb-epoch", type=int, default=10, dest="nb_epoch", help="Number of training epochs")
+                       help="images per optimisation step (the GLOBAL batch under torchrun)")
+    train.add_argument("--lr", "--learning-rate", type=float, default=1e-3, dest="learning_rate", help="Adam step size")
+    train.add_argument("--gamma", type=float, default=0.99, help="discount of the returns")
+    train.add_argument("--nb-epoch", type=int, default=10, dest="nb_epoch", help="passes over the training split")
     train.add_argument("--workers", type=int, default=6, help="DataLoader worker processes (train.py:95 uses 6)")
 
     test = modes.add_parser("test")
-    test.add_argument("--batch-size", type=int, default=8, dest="batch_size", help="Image batch size for evaluation")
-    test.add_argument("--dataset-path", type=str, required=True, dest="dataset_path", help="Input dataset path for inference")
-    test.add_argument("--img-size", type=int, default=28, dest="img_size", help="Image side size, assume all image are squared")
-    test.add_argument("--json-path", type=str, required=True, dest="json_path", help="JSON multi agent metadata path")
-    test.add_argument("--state-dict-path", type=str, required=True, dest="state_dict_path", help="ModelsWrapper state dict path")
+    test.add_argument("--batch-size", type=int, default=8, dest="batch_size", help="images per forward episode")
+    test.add_argument("--dataset-path", type=str, required=True, dest="dataset_path", help="image folder (one sub-directory per class)")
+    test.add_argument("--img-size", type=int, default=28, dest="img_size", help="side of the (square) images; recorded with the run")
+    test.add_argument("--json-path", type=str, required=True, dest="json_path", help="marl.json written by train")
+    test.add_argument("--state-dict-path", type=str, required=True, dest="state_dict_path", help="models/nn_models_epoch_N.pt written by train")
     test.add_argument("-o", "--output-dir", type=str, required=True, dest="output_dir",
-                      help="The directory where the model outputs will be saved. Created if needed")
+                      help="where the results go (created)")
     test.add_argument("--workers", type=int, default=8, help="DataLoader worker processes (eval.py:57 uses 8)")
 
     infer = modes.add_parser("infer")
-    infer.add_argument("--images", type=str, nargs="+", required=True, dest="infer_images", help="Path of images used for inference")
-    infer.add_argument("--json-path", type=str, required=True, dest="json_path", help="JSON multi agent metadata path")
-    infer.add_argument("--state-dict-path", type=str, required=True, dest="state_dict_path", help="ModelsWrapper state dict path")
-    infer.add_argument("--class2idx", type=str, required=True, dest="class_to_idx", help="Class to index JSON file")
+    infer.add_argument("--images", type=str, nargs="+", required=True, dest="infer_images", help="image files or glob patterns")
+    infer.add_argument("--json-path", type=str, required=True, dest="json_path", help="marl.json written by train")
+    infer.add_argument("--state-dict-path", type=str, required=True, dest="state_dict_path", help="models/nn_models_epoch_N.pt written by train")
+    infer.add_argument("--class2idx", type=str, required=True, dest="class_to_idx", help="class_to_idx.json written by train")
     infer.add_argument("-o", "--output-image-dir", type=str, required=True, dest="output_image_dir",
-                       help="The directory where the model outputs will be saved. Created if needed")
+                       help="where the results go (created)")
     return parser
 
 

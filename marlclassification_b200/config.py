@@ -6,7 +6,7 @@ from __future__ import annotations
 import json
 from os.path import exists, isfile
 
-from pydantic import BaseModel
+from pydantic import BaseModel, create_model
 
 from .core import Environment, MultiAgent
 from .networks import ModelsWrapper
@@ -19,11 +19,20 @@ _FIELDS = (
 )
 
 
-class MainConfig(BaseModel):
-    step: int
-    run_id: str
-    cuda: bool
-    nb_agent: int
+def _option_group(name: str, **fields: type) -> type[BaseModel]:
+    """A validated bag of required CLI options (the reference spells each one out as a pydantic class)."""
+    return create_model(name, **{key: (kind, ...) for key, kind in fields.items()})
+
+
+# config.py:11-15 -- options shared by every mode
+MainConfig = _option_group("MainConfig", step=int, run_id=str, cuda=bool, nb_agent=int)
+# config.py:107-131 -- one group per mode
+TrainConfig = _option_group("TrainConfig", img_size=int, nb_epoch=int, learning_rate=float, batch_size=int,
+                            resources_dir=str, output_dir=str, gamma=float)
+EvalConfig = _option_group("EvalConfig", img_size=int, state_dict_path=str, batch_size=int, json_path=str,
+                           dataset_path=str, output_dir=str)
+InferConfig = _option_group("InferConfig", state_dict_path=str, json_path=str, images_path=list[str], output_dir=str,
+                            class_to_idx=str)
 
 
 class ModelConfig(BaseModel):
@@ -67,28 +76,18 @@ class ModelConfig(BaseModel):
         return networks, MultiAgent(nb_agents, networks), self.build_environment()
 
 
-class TrainConfig(BaseModel):
-    img_size: int
-    nb_epoch: int
-    learning_rate: float
-    batch_size: int
-    resources_dir: str
-    output_dir: str
-    gamma: float
+    @classmethod
+    def load_trained(cls, json_path: str, state_dict_path: str, nb_agents: int, device) -> tuple:
+        """``marl.json`` + a saved ``state_dict`` -> (config, networks in eval mode on ``device``, agents,
+        environment): the common opening of the ``test`` and ``infer`` modes (eval.py:44-61, infer.py:44-57)."""
+        import torch as th
 
-
-class EvalConfig(BaseModel):
-    img_size: int
-    state_dict_path: str
-    batch_size: int
-    json_path: str
-    dataset_path: str
-    output_dir: str
-
-
-class InferConfig(BaseModel):
-    state_dict_path: str
-    json_path: str
-    images_path: list[str]
-    output_dir: str
-    class_to_idx: str
+        for path, what in ((json_path, "JSON path"), (state_dict_path, "State dict path")):
+            assert exists(path), f'{what} "{path}" does not exist'
+            assert isfile(path), f'"{path}" is not a file'
+        config = cls.load_marl_config(json_path)
+        networks, agents, env = config.build_marl(nb_agents)
+        networks.load_state_dict(th.load(state_dict_path, map_location="cpu"))
+        networks.eval()
+        networks.to(device)
+        return config, networks, agents, env

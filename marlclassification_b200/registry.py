@@ -3,34 +3,34 @@ registry.py:27-57).  The ``cnn_constructor`` half is on the hot path; the datase
 the train / test CLI (image-folder datasets only, see data.py)."""
 from __future__ import annotations
 
-from dataclasses import dataclass
-from typing import Any, Callable
+from typing import Any, Callable, NamedTuple
 
-import torch as th
+from . import data
+from .data import default_image_pipeline, u8_image_pipeline  # noqa: F401  (re-exported, registry.py:56-57)
+from .networks import vision
 
-from .data import (  # noqa: F401  (default_image_pipeline is re-exported as in the reference)
-    default_image_pipeline, folder_dataset_constructor, u8_image_pipeline, unsupported_dataset_constructor,
+
+class DatasetSpec(NamedTuple):
+    dataset_constructor: Callable[[str, Callable[[Any], Any]], Any]   # (resources dir, image transform) -> dataset
+    cnn_constructor: Callable[[int], vision.VisionCnnModule]          # window size f -> feature extractor
+
+
+def _folder(name: str, cnn) -> DatasetSpec:
+    return DatasetSpec(data.folder_dataset_constructor(name), cnn)
+
+
+def _not_a_folder(name: str, why: str, cnn) -> DatasetSpec:
+    return DatasetSpec(data.unsupported_dataset_constructor(name, why), cnn)
+
+
+DATASET_REGISTRY: dict[str, DatasetSpec] = dict(
+    mnist=_folder("mnist", vision.MnistCnn),
+    resisc45=_folder("resisc45", vision.Resisc45Cnn),
+    aid=_folder("aid", vision.AidCnn),
+    skin_cancer=_folder("skin_cancer", vision.SkinCancerCnn),
+    worldstrat=_not_a_folder("worldstrat", "CSV metadata + land-cover masks", vision.WorldStratCnn),
+    kneemri=_not_a_folder("kneemri", "pickled 3-D volumes", vision.KneeMriCnn),
 )
-from .networks.vision import (
-    AidCnn, KneeMriCnn, MnistCnn, Resisc45Cnn, SkinCancerCnn, VisionCnnModule, WorldStratCnn,
-)
-
-
-@dataclass(frozen=True)
-class DatasetSpec:
-    dataset_constructor: Callable[[str, Callable[[Any], th.Tensor]], Any]
-    cnn_constructor: Callable[[int], VisionCnnModule]
-
-
-DATASET_REGISTRY: dict[str, DatasetSpec] = {
-    "mnist": DatasetSpec(folder_dataset_constructor("mnist"), MnistCnn),
-    "resisc45": DatasetSpec(folder_dataset_constructor("resisc45"), Resisc45Cnn),
-    "kneemri": DatasetSpec(unsupported_dataset_constructor("kneemri", "pickled 3-D volumes"), KneeMriCnn),
-    "aid": DatasetSpec(folder_dataset_constructor("aid"), AidCnn),
-    "worldstrat": DatasetSpec(unsupported_dataset_constructor("worldstrat", "CSV metadata + land-cover masks"),
-                              WorldStratCnn),
-    "skin_cancer": DatasetSpec(folder_dataset_constructor("skin_cancer"), SkinCancerCnn),
-}
 
 
 def get_dataset_spec(name: str) -> DatasetSpec:

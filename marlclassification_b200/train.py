@@ -10,17 +10,18 @@ gradient all-reduce; MLflow is optional (``tracking.RunTracker``)."""
 from __future__ import annotations
 
 import json
+import random
 from os import makedirs
 from os.path import isdir, join
-from random import randrange
-from typing import Dict
+from typing import Dict, List, Optional, Tuple
 
 import torch as th
 from torch.utils.data import DataLoader, Subset
 
 from .config import MainConfig, ModelConfig, TrainConfig
 from .core import EpisodeSampler
-from .data import ShardedBatchSampler, collate_images, default_image_pipeline, u8_image_pipeline
+from .data import ShardedBatchSampler, collate_images, to_f32_chw, u8_image_pipeline
+from .parallel import DataParallelContext
 from .registry import get_dataset_spec
 from .runtime import cuda_device, data_parallel, shutdown
 from .tracking import RunTracker
@@ -28,12 +29,36 @@ from .training import Trainer
 from .visualization import visualize_steps
 
 SPLIT_SEED = 0x5eed
+TRAIN_FRACTION = 0.85  # train.py:82
 
 
-def _loader(dataset, batch_size: int, dp, seed: int, num_workers: int) -> DataLoader:
+def split_indices(n: int, fraction: float = TRAIN_FRACTION, seed: int = SPLIT_SEED) -> Tuple[List[int], List[int]]:
+    """Seeded random split (the reference draws an unseeded ``randperm``, train.py:83-87; every
+    data-parallel rank must cut the same way, so the permutation is fixed here)."""
+    order = th.randperm(n, generator=th.Generator().manual_seed(seed)).tolist()
+    cut = int(fraction * n)
+    return order[:cut], order[cut:]
+
+
+def _batches(dataset, batch_size: int, dp: DataParallelContext, seed: int, workers: int) -> DataLoader:
     sampler = ShardedBatchSampler(len(dataset), batch_size, dp.rank, dp.world_size, shuffle=True, seed=seed)
-    return DataLoader(dataset, batch_sampler=sampler, num_workers=num_workers, pin_memory=True,
-                      collate_fn=collate_images, persistent_workers=num_workers > 0)
+    return DataLoader(dataset, batch_sampler=sampler, num_workers=workers, pin_memory=True,
+                      collate_fn=collate_images, persistent_workers=workers > 0)
+
+
+def _open_run(main_config, model_config, train_config, dataset, device, dp) -> RunTracker:
+    """Rank 0 only: run directory, tracker, ``marl.json`` and ``class_to_idx.json`` (train.py:30-75)."""
+    out = train_config.output_dir
+    makedirs(join(out, "models"), exist_ok=True)
+    if not isdir(join(out, "models")):
+        raise NotADirectoryError(f'"{join(out, "models")}" is not a directory.')
+    tracker = RunTracker("MARLClassification", f"train_{main_config.run_id}", out)
+    tracker.log_params({"output_dir": out, "model_dir": join(out, "models"), **dict(main_config), **dict(model_config),
+                        **dict(train_config), "device": device.type, "world_size": dp.world_size})
+    model_config.save_marl_config(join(out, "marl.json"))
+    with open(join(out, "class_to_idx.json"), "w", encoding="utf-8") as fh:
+        json.dump(dataset.class_to_idx, fh)
+    return tracker
 
 
 def train_main(main_config: MainConfig, model_config: ModelConfig, train_config: TrainConfig,
@@ -43,69 +68,47 @@ def train_main(main_config: MainConfig, model_config: ModelConfig, train_config:
     )
     device = cuda_device(main_config.cuda)
     dp = data_parallel(device)
-    lead = dp.rank == 0
+    out = train_config.output_dir
 
-    output_dir = train_config.output_dir
-    model_dir = join(output_dir, "models")
-    if lead:
-        makedirs(model_dir, exist_ok=True)
-        if not isdir(model_dir):
-            raise NotADirectoryError(f'"{model_dir}" is not a directory.')
+    dataset = get_dataset_spec(model_config.ft_extr_str).dataset_constructor(train_config.resources_dir,
+                                                                             u8_image_pipeline())
+    networks, agents, env = model_config.build_marl(main_config.nb_agent)
+    tracker: Optional[RunTracker] = None
+    if dp.rank == 0:
+        tracker = _open_run(main_config, model_config, train_config, dataset, device, dp)
 
-    tracker = RunTracker("MARLClassification", f"train_{main_config.run_id}", output_dir) if lead else None
+    networks.to(device)
+    networks.ensure_flat()
+    dp.broadcast_params(networks.flat_params)  # replicas start from rank 0's initialisation
 
-    dataset_spec = get_dataset_spec(model_config.ft_extr_str)
-    nn_models, marl_m, env = model_config.build_marl(main_config.nb_agent)
-    dataset = dataset_spec.dataset_constructor(train_config.resources_dir, u8_image_pipeline())
+    train_idx, held_out_idx = split_indices(len(dataset))
+    train_batches = _batches(Subset(dataset, train_idx), train_config.batch_size, dp, 1, num_workers)
+    held_out_batches = _batches(Subset(dataset, held_out_idx), train_config.batch_size, dp, 2, num_workers)
 
-    if lead:
-        tracker.log_params({"output_dir": output_dir, "model_dir": model_dir, **dict(main_config),
-                            **dict(model_config), **dict(train_config), "device": device.type,
-                            "world_size": dp.world_size})
-        model_config.save_marl_config(join(output_dir, "marl.json"))
-        with open(join(output_dir, "class_to_idx.json"), "w", encoding="utf-8") as json_f:
-            json.dump(dataset.class_to_idx, json_f)
-
-    nn_models.to(device)
-    nn_models.ensure_flat()
-    dp.broadcast_params(nn_models.flat_params)  # replicas start from rank 0's initialisation
-
-    # 85 % train / 15 % eval (train.py:82-91); the permutation is seeded so every rank agrees
-    ratio_eval = 0.85
-    idx = th.randperm(len(dataset), generator=th.Generator().manual_seed(SPLIT_SEED))
-    cut = int(ratio_eval * idx.size(0))
-    idx_train, idx_test = idx[:cut].tolist(), idx[cut:].tolist()
-    train_dataset, test_dataset = Subset(dataset, idx_train), Subset(dataset, idx_test)
-    train_dataloader = _loader(train_dataset, train_config.batch_size, dp, 1, num_workers)
-    test_dataloader = _loader(test_dataset, train_config.batch_size, dp, 2, num_workers)
-
-    def metric_logger(step: int, metrics: Dict[str, float]) -> None:
+    def log(step: int, metrics: Dict[str, float]) -> None:
         if tracker is not None:
             tracker.log_metrics(step=step, metrics=metrics)
 
-    episode_sampler = EpisodeSampler(marl_m, env, main_config.step)
-    trainer = Trainer(nn_models, marl_m.nb_class, train_config.learning_rate, train_config.gamma,
-                      metric_logger=metric_logger, dp=dp)
+    sampler = EpisodeSampler(agents, env, main_config.step)
+    trainer = Trainer(networks, agents.nb_class, train_config.learning_rate, train_config.gamma,
+                      metric_logger=log, dp=dp)
 
-    for e in range(train_config.nb_epoch):
-        train_dataloader.batch_sampler.set_epoch(e)
-        test_dataloader.batch_sampler.set_epoch(e)
-        trainer.train_epoch(train_dataloader, e, episode_sampler)
-        conf_meter_eval = trainer.eval_epoch(test_dataloader, e, episode_sampler)
-        if not lead:
-            continue  # replicas hold identical weights; rank 0 reports its shard of the eval split
-        precs, recs = conf_meter_eval.precision(), conf_meter_eval.recall()
-        conf_meter_eval.save_conf_matrix(e, output_dir, "eval")
-        tracker.log_metrics(step=trainer.curr_step,
-                            metrics={"eval_prec": precs.mean().item(), "eval_recs": recs.mean().item()})
-        th.save(nn_models.state_dict(), join(model_dir, f"nn_models_epoch_{e}.pt"))
-
-    if lead and len(idx_test) > 0:
-        to_f32 = default_image_pipeline()
-        path, _ = dataset.samples[idx_test[randrange(len(idx_test))]]
-        x = to_f32(dataset.loader(path)).to(device)
-        visualize_steps(episode_sampler, x, x, model_config.window_size, output_dir, dataset.class_to_idx)
+    for epoch in range(train_config.nb_epoch):
+        for loader in (train_batches, held_out_batches):
+            loader.batch_sampler.set_epoch(epoch)
+        trainer.train_epoch(train_batches, epoch, sampler)
+        meter = trainer.eval_epoch(held_out_batches, epoch, sampler)
+        if tracker is None:
+            continue  # replicas hold identical weights; rank 0 reports its shard of the held-out split
+        meter.save_conf_matrix(epoch, out, "eval")
+        log(trainer.curr_step, {"eval_prec": meter.precision().mean().item(),
+                                "eval_recs": meter.recall().mean().item()})
+        th.save(networks.state_dict(), join(out, "models", f"nn_models_epoch_{epoch}.pt"))
 
     if tracker is not None:
+        if held_out_idx:  # one visualised episode on a held-out image (train.py:149-166)
+            path, _ = dataset.samples[random.choice(held_out_idx)]
+            pixels = to_f32_chw(dataset.loader(path))
+            visualize_steps(sampler, pixels.to(device), pixels, model_config.window_size, out, dataset.class_to_idx)
         tracker.end()
     shutdown()
