@@ -189,3 +189,72 @@ def test_confusion_matrix_png_and_visualised_episode(tmp_path):
     # the last frame shows exactly the uncovered windows: pixel (0,0) was seen at t=0 by agent 0
     frame = np.asarray(Image.open(tmp_path / "pred_step_2.png").convert("RGB"))
     assert frame.shape[0] > H and frame.shape[1] >= W
+
+
+def test_split_is_seeded_disjoint_and_85_15():
+    from marlclassification_b200.train import split_indices
+
+    tr, te = split_indices(51)
+    assert (len(tr), len(te)) == (43, 8) and sorted(tr + te) == list(range(51))
+    assert split_indices(51) == (tr, te)  # every data-parallel rank cuts the same way
+    assert split_indices(0) == ([], [])
+
+
+def test_load_trained_names_the_missing_file(tmp_path):
+    from marlclassification_b200.config import ModelConfig
+
+    with pytest.raises(AssertionError, match="JSON path"):
+        ModelConfig.load_trained(str(tmp_path / "marl.json"), str(tmp_path / "sd.pt"), 3, "cuda")
+    (tmp_path / "marl.json").write_text("{}")
+    with pytest.raises(AssertionError, match="State dict path"):
+        ModelConfig.load_trained(str(tmp_path / "marl.json"), str(tmp_path / "sd.pt"), 3, "cuda")
+
+
+def test_multi_agent_step_protocol_with_injected_samples(monkeypatch):
+    """MultiAgent.act (agent.py:40-68) against a stub network on the CPU: the state and the message
+    are threaded from step to step, the draw goes through ``torch.multinomial`` with the
+    reference's call form (so patching it injects samples), log-probs are log(probs[action])."""
+    from marlclassification_b200.core.agent import AgentOutput, MultiAgent
+    from marlclassification_b200.networks.models import ModelOutput, RecurrentOutput
+
+    na, nb, n_act = 2, 3, 4
+    calls = []
+
+    class StubNet:
+        nb_class, device = 5, torch.device("cpu")
+
+        def random_first_state(self, a, b):
+            return RecurrentOutput(*(torch.full((a, b, 2), float(k)) for k in range(4)))
+
+        def zero_first_message(self, a, b):
+            return torch.zeros(a, b, 1)
+
+        def __call__(self, obs, msg, npos, hidden):
+            calls.append((msg.clone(), hidden.h.clone()))
+            probs = torch.softmax(torch.arange(na * nb * n_act, dtype=torch.float32).view(na, nb, n_act) / 7, -1)
+            out = ModelOutput(actions_probabilities=probs, values=torch.ones(na, nb),
+                              predictions=torch.zeros(na, nb, 5), messages=msg + 1)
+            return out, RecurrentOutput(hidden.h + 10, hidden.c, hidden.h_caret, hidden.c_caret)
+
+    agents = MultiAgent(na, StubNet())
+    assert len(agents) == na and agents.nb_class == 5 and agents.device.type == "cpu"
+    with pytest.raises(AssertionError, match="reset"):
+        agents.act(torch.zeros(na, nb, 1, 2, 2), torch.zeros(na, nb, 2))
+    agents.reset(nb)
+
+    forced = torch.tensor([[3], [0], [1], [2], [2], [0]])
+    seen = {}
+
+    def fake_multinomial(p, num_samples, replacement):
+        seen["shape"], seen["kw"] = tuple(p.shape), (num_samples, replacement)
+        return forced
+
+    monkeypatch.setattr(torch, "multinomial", fake_multinomial)
+    out = agents.act(torch.zeros(na, nb, 1, 2, 2), torch.zeros(na, nb, 2))
+    assert isinstance(out, AgentOutput) and seen == {"shape": (na * nb, n_act), "kw": (1, True)}
+    assert torch.equal(out.actions, forced.view(na, nb))
+    probs = torch.softmax(torch.arange(na * nb * n_act, dtype=torch.float32).view(na, nb, n_act) / 7, -1)
+    assert torch.equal(out.actions_log_probs, probs.gather(-1, forced.view(na, nb, 1)).squeeze(-1).log())
+    agents.act(torch.zeros(na, nb, 1, 2, 2), torch.zeros(na, nb, 2))
+    assert calls[0][0].eq(0).all() and calls[1][0].eq(1).all()      # the message of step 0 is heard at step 1
+    assert calls[0][1].eq(0).all() and calls[1][1].eq(10).all()     # and so is the recurrent state
