@@ -22,6 +22,10 @@ extern "C" {
 
 int marlc_version(void);
 const char* marlc_last_error(void);
+/* Host-only self-test of the reciprocal division used for index math in the element-wise kernels
+ * (no reference counterpart; no GPU needed).  Returns the number of inexact quotients found over
+ * divisors 1..d_max and dividends 0, stride, 2*stride, ... up to the launchers' exactness bound. */
+long marlc_selftest_fastdiv(int d_max, int stride);
 
 /* ---- Environment operators (core/environment.py) -------------------------- */
 

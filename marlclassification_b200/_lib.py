@@ -33,6 +33,7 @@ class MarlcConfig(C.Structure):
 _P = C.c_void_p
 _SIGS = {
     "marlc_version": (C.c_int, []),
+    "marlc_selftest_fastdiv": (C.c_long, [C.c_int, C.c_int]),
     "marlc_last_error": (C.c_char_p, []),
     "marlc_patch_gather": (C.c_int, [_P, _P, _P] + [C.c_int] * 6 + [_P]),
     "marlc_transition": (C.c_int, [_P, _P, _P] + [C.c_int] * 5 + [_P, _P, _P]),

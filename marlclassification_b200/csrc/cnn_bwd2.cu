@@ -204,7 +204,7 @@ int cnn_bwd_layer(const CnnBwdLayerArgs& a, cudaStream_t s) {
     ka.d_hon = FastDiv((unsigned)std::max(a.ho_next, 1));
     // FastDiv exactness: the largest dividends are total (/ npos, / cout) and npn * kk (/ kk)
     const long nmax = std::max((long)ka.total, (long)ka.npn * a.cout * 9);
-    const bool fast = nmax * std::max(std::max(ka.npos, a.cout * 9), 1) < 0x100000000ll && !cnn_bwd_use_div();
+    const bool fast = FastDiv::exact_up_to(nmax, std::max(std::max(ka.npos, a.cout * 9), 1)) && !cnn_bwd_use_div();
     static size_t attr = 0;
     if (smem > 48 * 1024 && smem > attr) {
         MARLC_CUDA(cudaFuncSetAttribute(cnn_bwd_layer_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -243,7 +243,7 @@ int cnn_im2col_input(const float* img, const int* pos_hist, float* col, int P, i
                      int W, int f, int ho, cudaStream_t s) {
     if (P <= 0) return 0;
     const FastDiv d_kk((unsigned)(cin * 9)), d_ho((unsigned)ho);
-    const bool fast = (long)ho * ho * cin * 9 * cin * 9 < 0x100000000ll && !cnn_bwd_use_div();
+    const bool fast = FastDiv::exact_up_to((long long)ho * ho * cin * 9, cin * 9) && !cnn_bwd_use_div();
     if (fast) cnn_im2col_input_kernel<true><<<(P * 32 + 255) / 256, 256, 0, s>>>(img, pos_hist, col, P, M, B, img_c, cin, H, W, f, ho, d_kk, d_ho);
     else cnn_im2col_input_kernel<false><<<(P * 32 + 255) / 256, 256, 0, s>>>(img, pos_hist, col, P, M, B, img_c, cin, H, W, f, ho, d_kk, d_ho);
     MARLC_LAUNCH_CHECK();

@@ -58,8 +58,17 @@ struct FastDiv {
     unsigned d, m;
     FastDiv() : d(1), m(0) {}
     __host__ explicit FastDiv(unsigned d_) : d(d_), m(d_ > 1 ? (unsigned)((0x100000000ull + d_ - 1) / d_) : 0u) {}
-    __device__ __forceinline__ int div(int n) const { return d > 1 ? (int)__umulhi((unsigned)n, m) : n; }
-    __device__ __forceinline__ int div_nz(int n) const { return (int)__umulhi((unsigned)n, m); }  // d >= 2 only
+    __host__ __device__ __forceinline__ static unsigned mulhi(unsigned a, unsigned b) {
+#ifdef __CUDA_ARCH__
+        return __umulhi(a, b);
+#else
+        return (unsigned)(((unsigned long long)a * b) >> 32);  // host twin, used by marlc_selftest_fastdiv
+#endif
+    }
+    __host__ __device__ __forceinline__ int div(int n) const { return d > 1 ? (int)mulhi((unsigned)n, m) : n; }
+    __host__ __device__ __forceinline__ int div_nz(int n) const { return (int)mulhi((unsigned)n, m); }  // d >= 2 only
+    // largest dividend bound the launchers check: exact for every 0 <= n with n * d < 2^32
+    __host__ static bool exact_up_to(long long n_max, long long d_) { return n_max * d_ < 0x100000000ll; }
 };
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -151,6 +151,25 @@ static void add_block(marlc_engine* e, const std::string& name, int i, int n_in,
 }
 
 extern "C" int marlc_version(void) { return 1; }
+
+// Host-side check of the reciprocal division the element-wise kernels index with (FastDiv,
+// common.cuh): for every divisor 1..d_max, every dividend the launchers' bound admits (sampled with
+// `stride`, plus the values around each multiple of d near the bound) must divide exactly.
+// Returns the number of mismatches; needs no GPU.
+extern "C" long marlc_selftest_fastdiv(int d_max, int stride) {
+    long bad = 0;
+    if (stride < 1) stride = 1;
+    for (int d = 1; d <= d_max; ++d) {
+        const marlc::FastDiv fd((unsigned)d);
+        const long long limit = std::min<long long>(0x7fffffffll, (0x100000000ll - 1) / d);  // n * d < 2^32
+        for (long long n = 0; n <= limit; n += stride) bad += fd.div((int)n) != (int)(n / d);
+        for (long long q = std::max<long long>(0, limit / d - 2); q <= limit / d; ++q)
+            for (long long n = std::max<long long>(0, q * d - 1); n <= std::min(limit, q * d + 1); ++n)
+                bad += fd.div((int)n) != (int)(n / d);
+        bad += !marlc::FastDiv::exact_up_to(limit, d);
+    }
+    return bad;
+}
 extern "C" const char* marlc_last_error(void) { return g_err; }
 
 extern "C" int marlc_engine_create(const marlc_config* c, marlc_engine** out) {

@@ -141,3 +141,11 @@ def test_bench_reference_arm_runs_without_a_gpu():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     other = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=root, env=env)
     assert other.returncode == 0 and other.stdout.strip() == ""
+
+
+def test_fastdiv_reciprocal_division_is_exact_within_its_bound():
+    """The element-wise kernels (gather, CNN backward, im2col) index with multiply-high by a
+    host-computed reciprocal; the library's host twin of that code must agree with `/` for every
+    divisor up to 4096 over the whole range the launchers admit (n * d < 2^32)."""
+    assert _lib.lib().marlc_selftest_fastdiv(4096, 9973) == 0
+    assert _lib.lib().marlc_selftest_fastdiv(64, 1 << 12) == 0
