@@ -258,3 +258,24 @@ def test_multi_agent_step_protocol_with_injected_samples(monkeypatch):
     agents.act(torch.zeros(na, nb, 1, 2, 2), torch.zeros(na, nb, 2))
     assert calls[0][0].eq(0).all() and calls[1][0].eq(1).all()      # the message of step 0 is heard at step 1
     assert calls[0][1].eq(0).all() and calls[1][1].eq(10).all()     # and so is the recurrent state
+
+
+@pytest.mark.parametrize("nb_class", [2, 7, 31])
+def test_reference_metrics_scenarios(tmp_path, nb_class):
+    """The two scenarios of the reference's tests/test_metrics.py, through the alias package: identity
+    predictions with one planted error, picture written; mean of a loss window."""
+    from marl_classification.metrics import ConfusionMeter, LossMeter
+
+    y_pred = torch.eye(nb_class)
+    y_pred[0, 0], y_pred[0, 1] = 0.0, 1.0  # sample 0 (class 0) is predicted as class 1
+    meter = ConfusionMeter(nb_class, None)
+    meter.add(y_pred, torch.arange(nb_class))
+    cm = meter.conf_mat()
+    assert cm[0, 0] == 0 and cm[0, 1] == 1 and (torch.diag(cm)[1:] == 1).all() and cm.sum() == nb_class
+    assert meter.recall()[0] == 0 and meter.precision()[1] == 0.5
+    meter.save_conf_matrix(0, str(tmp_path), "unittest")
+    assert (tmp_path / "confusion_matrix_epoch_0_unittest.png").stat().st_size > 0
+    losses = LossMeter(None)
+    for v in (0.5, 0.25, 0.75, 0.5):
+        losses.add(v)
+    assert losses.loss() == 0.5
