@@ -2,6 +2,7 @@
 bookkeeping only; the confusion-matrix picture is drawn with PIL (no matplotlib needed)."""
 from __future__ import annotations
 
+from collections import deque
 from typing import Optional
 
 import torch as th
@@ -13,34 +14,60 @@ def format_metric(metric: th.Tensor, class_map: dict) -> str:
 
 
 class ConfusionMeter:
-    """Keeps (argmax prediction, target) pairs of the last ``window_size`` batches
-    and derives per-class precision / recall (metrics.py:25-108)."""
+    """Confusion matrix over the last ``window_size`` batches (all batches when ``None``) and the
+    per-class precision / recall derived from it (metrics.py:25-108).
+
+    The reference keeps the (prediction, target) pairs and rebuilds the matrix from all of them on
+    every query (``cat`` over the window + ``bincount``, twice per training iteration).  Here the
+    matrix is kept as a running count on the tensors' device: a batch adds its ``bincount``, the
+    batch that leaves the window subtracts its own, so a query costs nothing that grows with the
+    window.  Same numbers, same device placement, no host synchronisation."""
 
     def __init__(self, nb_class: int, window_size: Optional[int] = None) -> None:
         self.__nb_class = nb_class
         self.__window_size = window_size
-        self.__results: list[tuple[th.Tensor, th.Tensor]] = []
+        self.__cells: deque[th.Tensor] = deque()   # per batch: flat cell index true * Nc + pred
+        self.__counts: Optional[th.Tensor] = None  # int64[Nc * Nc], lives where the batches live
+
+    def __bincount(self, cells: th.Tensor) -> th.Tensor:
+        return th.bincount(cells, minlength=self.__nb_class**2)
 
     def add(self, y_proba: th.Tensor, y_true: th.Tensor) -> None:
-        self.__results.append((y_proba.argmax(dim=1).detach(), y_true.detach()))
-        if self.__window_size is not None and len(self.__results) > self.__window_size:
-            self.__results.pop(0)
+        cells = (y_true.detach() * self.__nb_class + y_proba.detach().argmax(dim=1)).to(th.int64)
+        if self.__counts is None or self.__counts.device != cells.device:
+            self.__counts = th.zeros(self.__nb_class**2, dtype=th.int64, device=cells.device)
+            for old in self.__cells:
+                self.__counts += self.__bincount(old.to(cells.device))
+        self.__counts += self.__bincount(cells)
+        self.__cells.append(cells)
+        if self.__window_size is not None and len(self.__cells) > self.__window_size:
+            self.__counts -= self.__bincount(self.__cells.popleft().to(cells.device))
 
     def conf_mat(self) -> th.Tensor:
-        pred = th.cat([p for p, _ in self.__results])
-        true = th.cat([t for _, t in self.__results])
-        flat = true * self.__nb_class + pred
-        return th.bincount(flat, minlength=self.__nb_class**2).view(self.__nb_class, self.__nb_class)
+        """int64[Nc, Nc], rows = true class, columns = predicted class."""
+        if self.__counts is None:
+            return th.zeros(self.__nb_class, self.__nb_class, dtype=th.int64)
+        return self.__counts.view(self.__nb_class, self.__nb_class).clone()
+
+    @staticmethod
+    def __ratio(hits: th.Tensor, totals: th.Tensor) -> th.Tensor:
+        """hits / totals where totals != 0, else 0 (metrics.py:71-108)."""
+        return th.where(totals != 0, hits / totals.clamp(min=1.0), th.zeros_like(totals))
 
     def precision(self) -> th.Tensor:
         cm = self.conf_mat().to(th.float)
-        tot = cm.sum(dim=0)
-        return th.where(tot != 0, cm.diagonal() / tot.clamp(min=1.0), th.zeros_like(tot))
+        return self.__ratio(cm.diagonal(), cm.sum(dim=0))
 
     def recall(self) -> th.Tensor:
         cm = self.conf_mat().to(th.float)
-        tot = cm.sum(dim=1)
-        return th.where(tot != 0, cm.diagonal() / tot.clamp(min=1.0), th.zeros_like(tot))
+        return self.__ratio(cm.diagonal(), cm.sum(dim=1))
+
+    def mean_precision_recall(self) -> th.Tensor:
+        """f32[2] = (mean precision, mean recall) on the matrix's device: what the training loop logs,
+        computed from ONE matrix and ready to be packed into a single device->host read."""
+        cm = self.conf_mat().to(th.float)
+        diag = cm.diagonal()
+        return th.stack((self.__ratio(diag, cm.sum(dim=0)).mean(), self.__ratio(diag, cm.sum(dim=1)).mean()))
 
     def save_conf_matrix(self, epoch: int, output_dir: str, stage: str) -> None:
         """Row-normalised confusion matrix as ``confusion_matrix_epoch_{e}_{stage}.png``

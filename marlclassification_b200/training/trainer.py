@@ -95,15 +95,15 @@ class Trainer:
             loss_out = self.train_step(staged, None, episode_sampler)
             eng = episode_sampler.engine_for(staged, gamma=self.__gamma)
             y_train = self.__steps[id(eng)].static_y.clone()
-            # meters: one packed D2H read of the five scalars
-            loss_item, path_item, error_item, actor_item, critic_item = loss_out[:5].tolist()
+            # meters: ONE packed device->host read per iteration (the five loss scalars + mean
+            # precision / recall of the running confusion matrix) instead of the reference's 7+ syncs
             self.__conf_meter.add(eng.step_preds[-1].mean(dim=0), y_train)
+            packed = th.cat((loss_out[:5], self.__conf_meter.mean_precision_recall().to(loss_out.dtype)))
+            loss_item, path_item, error_item, actor_item, critic_item, *prec_rec = packed.tolist()
             self.__path_loss_meter.add(path_item)
             self.__error_meter.add(error_item)
             self.__actor_loss_meter.add(actor_item)
             self.__critic_loss_meter.add(critic_item)
-            precs, recs = self.__conf_meter.precision(), self.__conf_meter.recall()
-            prec_rec = th.stack((precs.mean(), recs.mean())).tolist()
             if self.__metric_logger is not None and self.__curr_step % self.__log_interval == 0:
                 self.__metric_logger(
                     self.__curr_step,
@@ -126,7 +126,7 @@ class Trainer:
                 vote = self.eval_step(staged, episode_sampler)  # mean over agents, trainer.py:180
                 eng = episode_sampler.engine_for(staged, gamma=self.__gamma)
                 conf_meter.add(vote, self.__eval_steps[id(eng)].static_y.clone())
-                pr = th.stack((conf_meter.precision().mean(), conf_meter.recall().mean())).tolist()
+                pr = conf_meter.mean_precision_recall().tolist()
                 tqdm_bar.set_description(
                     f"Epoch {epoch_index} - Eval, eval_prec = {pr[0]:.4f}, eval_rec = {pr[1]:.4f}"
                 )

@@ -279,3 +279,32 @@ def test_reference_metrics_scenarios(tmp_path, nb_class):
     for v in (0.5, 0.25, 0.75, 0.5):
         losses.add(v)
     assert losses.loss() == 0.5
+
+
+@pytest.mark.parametrize("window", [None, 1, 4])
+def test_running_confusion_matrix_equals_rebuild_from_window(window):
+    """The meter keeps a running count (add the new batch, subtract the one leaving the window);
+    the reference rebuilds from the stored window on every query (metrics.py:56-108).  Same matrix,
+    precision, recall and packed means after every batch, ragged batch sizes included."""
+    from marlclassification_b200.metrics import ConfusionMeter
+
+    nc, g = 5, torch.Generator().manual_seed(7)
+    meter, kept = ConfusionMeter(nc, window), []
+    assert meter.conf_mat().sum() == 0
+    for step in range(12):
+        b = int(torch.randint(1, 9, (1,), generator=g))
+        proba, true = torch.rand(b, nc, generator=g), torch.randint(nc, (b,), generator=g)
+        meter.add(proba, true)
+        kept.append((proba.argmax(1), true))
+        if window is not None:
+            kept = kept[-window:]
+        pred, tgt = torch.cat([p for p, _ in kept]), torch.cat([t for _, t in kept])
+        want = torch.zeros(nc, nc, dtype=torch.int64)
+        for p, t in zip(pred.tolist(), tgt.tolist()):
+            want[t, p] += 1
+        assert torch.equal(meter.conf_mat(), want)
+        wf = want.float()
+        prec = torch.where(wf.sum(0) != 0, wf.diag() / wf.sum(0).clamp(min=1), torch.zeros(nc))
+        rec = torch.where(wf.sum(1) != 0, wf.diag() / wf.sum(1).clamp(min=1), torch.zeros(nc))
+        assert torch.equal(meter.precision(), prec) and torch.equal(meter.recall(), rec)
+        assert torch.allclose(meter.mean_precision_recall(), torch.stack((prec.mean(), rec.mean())))
