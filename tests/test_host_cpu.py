@@ -149,3 +149,37 @@ def test_fastdiv_reciprocal_division_is_exact_within_its_bound():
     divisor up to 4096 over the whole range the launchers admit (n * d < 2^32)."""
     assert _lib.lib().marlc_selftest_fastdiv(4096, 9973) == 0
     assert _lib.lib().marlc_selftest_fastdiv(64, 1 << 12) == 0
+
+
+REFERENCE_ROOT = "/root/reference"
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE_ROOT, "marl_classification")),
+                    reason="the reference checkout only exists in the build container")
+@pytest.mark.parametrize("name", ["mnist_ckpt", "resisc_small", "aid_small"])
+def test_same_seed_gives_the_reference_initialisation(name, tmp_path):
+    """Drop-in property of construction (init.py:6-29, models.py:30-76): under the same
+    ``torch.manual_seed`` our ModelsWrapper consumes the RNG exactly like the reference's, so a run
+    started from a seed begins from bit-identical weights.  The reference is imported in a
+    subprocess (its package name collides with this repo's alias package)."""
+    import json
+    import subprocess
+    import sys
+
+    mc = load_golden(name)["model_config"]
+    out = tmp_path / "ref_init.pt"
+    code = (
+        "import sys, json, torch; sys.path.insert(0, sys.argv[1]);"
+        "from marl_classification.config import ModelConfig;"
+        "torch.manual_seed(1234);"
+        "torch.save(ModelConfig(**json.loads(sys.argv[2])).build_networks().state_dict(), sys.argv[3])"
+    )
+    env = {k: v for k, v in os.environ.items() if k != "PYTHONPATH"}
+    subprocess.run([sys.executable, "-c", code, REFERENCE_ROOT, json.dumps(mc), str(out)], check=True, cwd=str(tmp_path),
+                   env=env)
+    ref = torch.load(out, map_location="cpu")
+    torch.manual_seed(1234)
+    ours = ModelConfig(**mc).build_networks().state_dict()
+    assert list(ours) == list(ref)
+    for k in ref:
+        assert torch.equal(ours[k], ref[k]), k
