@@ -14,7 +14,7 @@ import torch as th
 from tqdm import tqdm
 
 from ..core import EpisodeSampler
-from ..input_pipeline import DevicePrefetcher, StagedBatch
+from ..input_pipeline import DevicePrefetcher
 from ..metrics import ConfusionMeter, LossMeter
 from ..networks import ModelsWrapper
 from ..parallel import DataParallelContext
