@@ -69,6 +69,8 @@ def build_parser() -> argparse.ArgumentParser:
     train.add_argument("--gamma", type=float, default=0.99, help="discount of the returns")
     train.add_argument("--nb-epoch", type=int, default=10, dest="nb_epoch", help="passes over the training split")
     train.add_argument("--workers", type=int, default=6, help="DataLoader worker processes (train.py:95 uses 6)")
+    train.add_argument("--resident", action="store_true",
+                       help="decode the dataset once and keep it in HBM as bytes: no per-step host work or PCIe traffic")
 
     test = modes.add_parser("test")
     test.add_argument("--batch-size", type=int, default=8, dest="batch_size", help="images per forward episode")
@@ -122,7 +124,7 @@ def main(argv: Optional[Sequence[str]] = None) -> None:
         _ensure_dir(args.output_dir)
         from .train import train_main
 
-        train_main(main_config, model_config, train_config, num_workers=args.workers)
+        train_main(main_config, model_config, train_config, num_workers=args.workers, resident=args.resident)
     elif args.main_choice == "test":
         eval_config = EvalConfig(
             img_size=args.img_size, state_dict_path=args.state_dict_path, batch_size=args.batch_size,

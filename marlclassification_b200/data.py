@@ -159,3 +159,70 @@ class ShardedBatchSampler:
 def collate_images(items: Sequence[Tuple[th.Tensor, int]]) -> Tuple[th.Tensor, th.Tensor]:
     """Stack equally-sized images (u8 HWC or f32 CHW) and their labels (int64)."""
     return th.stack([x for x, _ in items]), th.tensor([int(y) for _, y in items], dtype=th.int64)
+
+
+class ResidentImages:
+    """A whole image-folder split decoded ONCE and kept as ``u8[N,H,W,C]`` on the device.
+
+    The reference re-decodes every file with PIL in DataLoader workers each epoch and ships fp32
+    pixels over PCIe each step (train.py:91-107).  At B200 rates (thousands of image-episodes per
+    second per GPU) the decode workers become the limit long before the GPU does, while the
+    datasets themselves are small next to 180 GB of HBM (RESISC45: 31 500 x 256 x 256 x 3 bytes =
+    6.2 GB; AID: 10 000 x 600 x 600 x 3 = 10.8 GB; MNIST: 0.16 GB).  So: decode once (thread pool -
+    PIL releases the GIL while decoding), one H2D copy of the bytes, and every batch afterwards is
+    an ``index_select`` in HBM followed by the device ``ToTensor`` kernel - no host work and no
+    PCIe traffic per step.  Iterating yields ``(u8[B,H,W,C], int64[B])`` device tensors, which
+    ``Trainer.prefetch`` passes through untouched.
+
+    All images must share one size (true for the reference's folder datasets).  Under data
+    parallelism every rank keeps the whole split (any image can land in any rank's shard after a
+    reshuffle); the sampler still hands each rank only its slice of every global batch."""
+
+    def __init__(self, dataset, indices: Sequence[int], batch_sampler: ShardedBatchSampler, device,
+                 decode_threads: int = 8, hbm_fraction: float = 0.5) -> None:
+        from concurrent.futures import ThreadPoolExecutor
+
+        self.batch_sampler = batch_sampler
+        self.device = th.device(device)
+        if batch_sampler.length != len(indices):
+            raise ValueError(f"batch sampler covers {batch_sampler.length} samples, the split holds {len(indices)}")
+        samples = [dataset.samples[i] for i in indices]
+        if not samples:
+            self.images = th.empty(0, 0, 0, 0, dtype=th.uint8, device=self.device)
+            self.labels = th.empty(0, dtype=th.int64, device=self.device)
+            return
+        first = to_u8_hwc(dataset.loader(samples[0][0]))
+        need = len(samples) * first.numel()
+        if self.device.type == "cuda":
+            free, _ = th.cuda.mem_get_info(self.device)
+            if need > hbm_fraction * free:
+                raise MemoryError(f"resident split needs {need / 2**30:.1f} GiB of HBM but only "
+                                  f"{hbm_fraction:.0%} of the free {free / 2**30:.1f} GiB may be used: "
+                                  "drop --resident (streaming loader) or shard over more GPUs")
+        host = th.empty((len(samples), *first.shape), dtype=th.uint8, pin_memory=self.device.type == "cuda")
+
+        def decode(k: int) -> None:
+            img = first if k == 0 else to_u8_hwc(dataset.loader(samples[k][0]))
+            if img.shape != first.shape:
+                raise ValueError(f"{samples[k][0]}: size {tuple(img.shape)} differs from {tuple(first.shape)}; "
+                                 "a resident split needs equally sized images")
+            host[k] = img
+
+        with ThreadPoolExecutor(max_workers=max(1, decode_threads)) as pool:
+            list(pool.map(decode, range(len(samples))))
+        self.images = host.to(self.device, non_blocking=True)
+        self.labels = th.tensor([t for _, t in samples], dtype=th.int64).to(self.device)
+        if self.device.type == "cuda":
+            th.cuda.current_stream(self.device).synchronize()  # the pinned staging buffer is freed on return
+
+    @property
+    def nbytes(self) -> int:
+        return self.images.numel()
+
+    def __len__(self) -> int:
+        return len(self.batch_sampler)
+
+    def __iter__(self):
+        for batch in self.batch_sampler:
+            idx = th.as_tensor(batch, dtype=th.int64, device=self.device)
+            yield self.images.index_select(0, idx), self.labels.index_select(0, idx)

@@ -6,7 +6,8 @@ visualised episode.
 Differences that come from the B200 path, not from the interface: batches travel as decoded
 bytes and become fp32 on the device (``u8_image_pipeline`` + ``Trainer.prefetch``); under
 ``torch.distributed.run`` every rank trains on its shard of each global batch with the flat
-gradient all-reduce; MLflow is optional (``tracking.RunTracker``)."""
+gradient all-reduce; ``--resident`` decodes each split once and serves every batch from HBM
+(``data.ResidentImages``); MLflow is optional (``tracking.RunTracker``)."""
 from __future__ import annotations
 
 import json
@@ -20,7 +21,7 @@ from torch.utils.data import DataLoader, Subset
 
 from .config import MainConfig, ModelConfig, TrainConfig
 from .core import EpisodeSampler
-from .data import ShardedBatchSampler, collate_images, to_f32_chw, u8_image_pipeline
+from .data import ResidentImages, ShardedBatchSampler, collate_images, to_f32_chw, u8_image_pipeline
 from .parallel import DataParallelContext
 from .registry import get_dataset_spec
 from .runtime import cuda_device, data_parallel, shutdown
@@ -40,9 +41,14 @@ def split_indices(n: int, fraction: float = TRAIN_FRACTION, seed: int = SPLIT_SE
     return order[:cut], order[cut:]
 
 
-def _batches(dataset, batch_size: int, dp: DataParallelContext, seed: int, workers: int) -> DataLoader:
-    sampler = ShardedBatchSampler(len(dataset), batch_size, dp.rank, dp.world_size, shuffle=True, seed=seed)
-    return DataLoader(dataset, batch_sampler=sampler, num_workers=workers, pin_memory=True,
+def _batches(dataset, indices: List[int], batch_size: int, dp: DataParallelContext, seed: int, workers: int,
+             resident_on=None):
+    """Batches of one split: streamed by DataLoader workers (decoded bytes, pinned), or - with
+    ``resident_on`` a device - decoded once and served from HBM (``data.ResidentImages``)."""
+    sampler = ShardedBatchSampler(len(indices), batch_size, dp.rank, dp.world_size, shuffle=True, seed=seed)
+    if resident_on is not None:
+        return ResidentImages(dataset, indices, sampler, resident_on, decode_threads=max(1, workers))
+    return DataLoader(Subset(dataset, indices), batch_sampler=sampler, num_workers=workers, pin_memory=True,
                       collate_fn=collate_images, persistent_workers=workers > 0)
 
 
@@ -62,7 +68,7 @@ def _open_run(main_config, model_config, train_config, dataset, device, dp) -> R
 
 
 def train_main(main_config: MainConfig, model_config: ModelConfig, train_config: TrainConfig,
-               num_workers: int = 6) -> None:
+               num_workers: int = 6, resident: bool = False) -> None:
     assert model_config.state_dim == 2, (
         "Only 2D is supported by the CUDA episode (the reference also admits 3-D volumes, train.py:23-28)"
     )
@@ -82,8 +88,9 @@ def train_main(main_config: MainConfig, model_config: ModelConfig, train_config:
     dp.broadcast_params(networks.flat_params)  # replicas start from rank 0's initialisation
 
     train_idx, held_out_idx = split_indices(len(dataset))
-    train_batches = _batches(Subset(dataset, train_idx), train_config.batch_size, dp, 1, num_workers)
-    held_out_batches = _batches(Subset(dataset, held_out_idx), train_config.batch_size, dp, 2, num_workers)
+    where = device if resident else None
+    train_batches = _batches(dataset, train_idx, train_config.batch_size, dp, 1, num_workers, where)
+    held_out_batches = _batches(dataset, held_out_idx, train_config.batch_size, dp, 2, num_workers, where)
 
     def log(step: int, metrics: Dict[str, float]) -> None:
         if tracker is not None:

@@ -308,3 +308,41 @@ def test_running_confusion_matrix_equals_rebuild_from_window(window):
         rec = torch.where(wf.sum(1) != 0, wf.diag() / wf.sum(1).clamp(min=1), torch.zeros(nc))
         assert torch.equal(meter.precision(), prec) and torch.equal(meter.recall(), rec)
         assert torch.allclose(meter.mean_precision_recall(), torch.stack((prec.mean(), rec.mean())))
+
+
+def test_resident_split_serves_the_same_batches_as_the_streaming_loader(tmp_path):
+    """data.ResidentImages (decode once, index in device memory) against a DataLoader over the same
+    sampler: identical bytes and labels batch for batch, across an epoch change, ragged tail
+    included.  (Device-agnostic torch indexing, exercised here on the CPU.)"""
+    from torch.utils.data import DataLoader, Subset
+
+    from marlclassification_b200.data import ResidentImages
+
+    root = make_image_folder(str(tmp_path / "imgs"), classes=3, per_class=7, size=12, grey_every=3)
+    ds = FolderDataset(root, u8_image_pipeline())
+    indices = [20, 3, 5, 8, 13, 1, 0, 19, 7, 11, 2]
+    for world, rank in ((1, 0), (2, 1)):
+        sampler = ShardedBatchSampler(len(indices), 4, rank, world, shuffle=True, seed=5)
+        resident = ResidentImages(ds, indices, sampler, "cpu", decode_threads=3)
+        assert resident.images.shape == (11, 12, 12, 3) and resident.nbytes == 11 * 12 * 12 * 3
+        stream = DataLoader(Subset(ds, indices), batch_sampler=sampler, collate_fn=collate_images)
+        for epoch in (0, 1):
+            sampler.set_epoch(epoch)
+            got, want = list(resident), list(stream)
+            assert len(got) == len(want) == len(resident) > 0
+            for (xg, yg), (xw, yw) in zip(got, want):
+                assert xg.dtype == torch.uint8 and torch.equal(xg, xw) and torch.equal(yg, yw)
+
+
+def test_resident_split_rejects_mixed_sizes_and_foreign_samplers(tmp_path):
+    from marlclassification_b200.data import ResidentImages
+
+    root = make_image_folder(str(tmp_path / "imgs"), classes=2, per_class=2, size=8)
+    Image.fromarray(np.zeros((9, 8, 3), np.uint8), "RGB").save(os.path.join(root, "class_1", "odd.png"))
+    ds = FolderDataset(root, u8_image_pipeline())
+    with pytest.raises(ValueError, match="equally sized"):
+        ResidentImages(ds, list(range(len(ds))), ShardedBatchSampler(len(ds), 2), "cpu")
+    with pytest.raises(ValueError, match="batch sampler covers"):
+        ResidentImages(ds, [0, 1], ShardedBatchSampler(3, 2), "cpu")
+    empty = ResidentImages(ds, [], ShardedBatchSampler(0, 2), "cpu")
+    assert len(empty) == 0 and list(empty) == []
