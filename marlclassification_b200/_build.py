@@ -1,6 +1,7 @@
 """Build libmarlc.so (hand-written sm_100a CUDA, C ABI) in-tree with nvcc."""
 from __future__ import annotations
 
+import fcntl
 import glob
 import os
 import shutil
@@ -34,16 +35,29 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libmarlc.so")
-    cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("MARLC_NVCC_EXTRA", "").split(), "-o", LIB + ".tmp", *sources()]
-    if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError(f"nvcc failed:\n{res.stdout}\n{res.stderr}")
-    os.replace(LIB + ".tmp", LIB)
-    if verbose:
-        print(res.stderr)
+    # Under torchrun every rank of a fresh checkout gets here at once: one builds, the others wait on the
+    # lock and then find the library up to date.  The compiler writes to a per-process name and the
+    # result is moved into place atomically, so no rank can dlopen a half-written file.
+    with open(LIB + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():
+                return LIB
+            tmp = f"{LIB}.{os.getpid()}.tmp"
+            cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("MARLC_NVCC_EXTRA", "").split(), "-o", tmp, *sources()]
+            if verbose:
+                cmd.insert(1, "-Xptxas")
+                cmd.insert(2, "-v")
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError(f"nvcc failed:\n{res.stdout}\n{res.stderr}")
+            os.replace(tmp, LIB)
+            if verbose:
+                print(res.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 

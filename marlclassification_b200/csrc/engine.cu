@@ -9,6 +9,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: ranges show up in nsys / ncu --nvtx, cost ~nothing otherwise
+
 #include "../../include/marlc.h"
 #include "kernels.cuh"
 #include "chain.cuh"
@@ -40,6 +42,14 @@ struct BufInfo {
 }  // namespace marlc
 
 using namespace marlc;
+
+// NVTX range over a host-side phase of the engine (tracing).  Ranges mark where the
+// launches of a phase are ISSUED (under CUDA-graph capture that is capture time; eager runs and
+// `ncu --nvtx --nvtx-include "marlc/..."` attribute kernels to phases with them).
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 struct marlc_engine {
     marlc_config cfg;
@@ -744,6 +754,7 @@ extern "C" int marlc_episode_forward(marlc_engine* e, const float* img, const in
                                      const float* const* hidden0, const int64_t* actions, void* stream) {
     MARLC_CHECK(e && e->ws, "engine not bound");
     MARLC_CHECK(img, "null image batch");
+    NvtxRange nvtx_fwd("marlc/forward");
     cudaStream_t s = (cudaStream_t)stream;
     const marlc_config& c = e->cfg;
     const int M = e->M, T = c.T;
@@ -777,6 +788,7 @@ extern "C" int marlc_episode_forward(marlc_engine* e, const float* img, const in
     }
 
     for (int t = 0; t < T; ++t) {
+        NvtxRange nvtx_step("marlc/forward/step");
         MARLC_TRY(step_networks(e, t, img, pos_hist + (size_t)t * M * 2, nullptr, msg + (size_t)t * M * c.n_m,
                                 npos + (size_t)t * M * 2, H + (size_t)t * M * c.n_b, Cb + (size_t)t * M * c.n_b,
                                 Hc + (size_t)t * M * c.n_a, Cc + (size_t)t * M * c.n_a, s));
@@ -786,6 +798,7 @@ extern "C" int marlc_episode_forward(marlc_engine* e, const float* img, const in
     if (e->debug_stop >= 11 && e->debug_stop <= 14) { e->last_launches = g_launch_count - start; return 0; }
     // critic and prediction heads do not feed back into the trajectory: batch them
     // over all T steps (R = T*M rows)
+    NvtxRange nvtx_heads("marlc/forward/batched_heads");
     MARLC_TRY(value_pred_heads(e, e->TM, s));
     MARLC_TRY(rng_advance(rng, s));
     e->last_launches = g_launch_count - start;
@@ -837,6 +850,7 @@ static LossArgs loss_args(marlc_engine* e, const int64_t* targets) {
 
 extern "C" int marlc_loss_phase_a(marlc_engine* e, const int64_t* targets, void* stream) {
     MARLC_CHECK(e && e->ws && targets, "loss: engine not bound / null targets");
+    NvtxRange nvtx_loss("marlc/loss/phase_a");
     const int start = g_launch_count;
     MARLC_TRY(loss_phase_a(loss_args(e, targets), (cudaStream_t)stream));
     e->last_launches = g_launch_count - start;
@@ -844,6 +858,7 @@ extern "C" int marlc_loss_phase_a(marlc_engine* e, const int64_t* targets, void*
 }
 extern "C" int marlc_loss_phase_b(marlc_engine* e, void* stream) {
     MARLC_CHECK(e && e->ws, "loss: engine not bound");
+    NvtxRange nvtx_loss("marlc/loss/phase_b");
     const int start = g_launch_count;
     MARLC_TRY(loss_phase_b(loss_args(e, nullptr), (cudaStream_t)stream));
     e->last_launches = g_launch_count - start;
@@ -900,6 +915,7 @@ static int head_bwd_params(marlc_engine* e, const std::string& name, const float
 extern "C" int marlc_episode_backward(marlc_engine* e, const float* img, int accumulate, void* stream) {
     MARLC_CHECK(e && e->ws && e->G, "backward: engine not bound (need a grads buffer)");
     MARLC_CHECK(img, "null image batch");
+    NvtxRange nvtx_bwd("marlc/backward");
     cudaStream_t s = (cudaStream_t)stream;
     const marlc_config& c = e->cfg;
     const int M = e->M, T = c.T, TM = e->TM, Kin = e->Kin, F = e->F;
@@ -914,6 +930,8 @@ extern "C" int marlc_episode_backward(marlc_engine* e, const float* img, int acc
 
     // ---- heads, batched over T*M rows (their gradients do not depend on the sweep)
     // (prediction head on a side stream, policy + critic heads on the main one)
+    {
+    NvtxRange nvtx_heads("marlc/backward/heads");
     if (c.use_chains) {
         // three heads on three streams up to dY; the policy and critic heads share their input h^, so
         // their state gradients are ONE dual-pair GEMM: dh^ = dY_pol W0_pol + dY_cri W0_cri
@@ -965,6 +983,7 @@ extern "C" int marlc_episode_backward(marlc_engine* e, const float* img, int acc
                            c.n_a, c.nl_a, e->buf("dHc_heads"), 1, s));
     }
 
+    }  // heads
     auto join_sides = [&]() -> int {  // early (profiling) exits must not leave forked work unjoined
         if (!c.use_chains) return 0;
         MARLC_TRY(e->chain(e->side[0], s));
@@ -979,6 +998,7 @@ extern "C" int marlc_episode_backward(marlc_engine* e, const float* img, int acc
     //      underneath it, one chunk of time steps behind.
     const bool par = c.use_chains != 0;
     auto batched = [&](int t0, int t1, cudaStream_t sL, cudaStream_t s1, cudaStream_t s0) -> int {
+        NvtxRange nvtx_batched("marlc/backward/batched_grads");
         const size_t r0 = (size_t)t0 * M;       // first row of the chunk
         const int R = (t1 - t0) * M;            // rows in the chunk
         if (R <= 0) return 0;
@@ -1085,6 +1105,7 @@ extern "C" int marlc_episode_backward(marlc_engine* e, const float* img, int acc
         return 0;
     };
     // ---- BPTT sweep
+    NvtxRange nvtx_sweep("marlc/backward/sweep");
     float* dh = e->buf("dh");
     float* dhc = e->buf("dhc");
     float* dc[2] = {e->buf("dc0"), e->buf("dc1")};

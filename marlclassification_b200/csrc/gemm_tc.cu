@@ -26,6 +26,7 @@ constexpr int UMMA_K = 8;
 constexpr int TC_THREADS = 192;
 constexpr int TC_THREADS_X3 = 320;  // + 4 warps that only split operands (the splitter is throughput-bound)
 constexpr int TC_SPLITTERS = TC_THREADS_X3 - 64;
+constexpr int TC_MAX_CHAIN = 4096;  // longest K range one CTA accumulates in TMEM when split-K is allowed
 
 // ---------------------------------------------------------------------------------
 // host: tensor maps
@@ -833,6 +834,15 @@ int tc_gemm_group(const TcGemmArgs* args, int count, cudaStream_t s) {
             // (in-kernel trace: 5.3 us per CTA, 13.4 us for the 190-CTA dX group)
             splits = min(a.allow_split >= 2 ? nkb : max(1, nkb * KS / 4), max(1, MARLC_SMS / ctas));
             splits = min(splits, nkb);
+        }
+        if (a.allow_split) {
+            // Long reductions (weight gradients: K = T*M rows, up to millions for the conv layers): the
+            // tensor core adds into its fp32 TMEM accumulator with truncation, a bias that grows with the
+            // length of the chain (measured on dW_ih: 2.5e-5 rel. at K = 2048, 6.3e-4 at K = 65536).  Chains are
+            // therefore capped at TC_MAX_CHAIN elements of K per CTA; the partial sums meet in the epilogue's
+            // f32 reduce-add (round-to-nearest in L2).  Those launches are throughput-bound: extra waves are free.
+            const int chain_blocks = max(1, TC_MAX_CHAIN / BKS);
+            splits = max(splits, (nkb + chain_blocks - 1) / chain_blocks);
             // every split must own at least one K block
             while (splits > 1 && ((nkb + splits - 1) / splits) * (splits - 1) >= nkb) --splits;
         }

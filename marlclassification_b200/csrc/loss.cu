@@ -29,7 +29,9 @@ __global__ void reward_kernel(const LossArgs a) {
     for (int c = lane; c < a.Nc; c += 32) s += expf(x[c] - mx);
     s = warp_sum(s);
     if (lane == 0) {
-        const float ce = (mx + logf(s)) - x[a.targets[b]];
+        // labels outside [0, Nc) are flagged by vote_kernel; here they are only kept from reading out of bounds
+        const long yb = a.targets[b];
+        const float ce = (mx + logf(s)) - x[(yb >= 0 && yb < a.Nc) ? yb : 0];
         const float lnc = logf((float)a.Nc);
         a.rewards[w] = (lnc - ce) / lnc;
     }
@@ -56,7 +58,13 @@ __global__ void vote_kernel(const LossArgs a) {
     float s = 0.f;
     for (int c = lane; c < a.Nc; c += 32) s += expf(vote(c) - mx);
     s = warp_sum(s);
-    const int y = (int)a.targets[b];
+    // a label outside [0, Nc) (e.g. --nb-class smaller than the dataset's class count) is the reference's
+    // device assert in cross_entropy (trainer.py:83-87): counted in stats[7], reported as loss_out[5] and
+    // turned into a NaN loss by loss_finalize_kernel; the index is clamped so nothing is read out of bounds
+    const long y_raw = a.targets[b];
+    const bool y_bad = y_raw < 0 || y_raw >= a.Nc;
+    const int y = y_bad ? 0 : (int)y_raw;
+    if (y_bad && lane == 0 && t == 0) atomicAdd(&a.stats[7], 1.0);
     const float lse = mx + logf(s);
     const float scale = 1.0f / ((float)a.Na * (float)a.Nb);
     float* dbase = a.d_preds + ((long)t * a.Na * a.Nb + b) * a.Nc;
@@ -142,6 +150,9 @@ __global__ void loss_finalize_kernel(const LossArgs a) {
     a.loss_out[2] = (float)(a.stats[5] / ((double)a.T * a.Nb));  // error.mean()
     a.loss_out[3] = (float)(path + err_sum_t);           // actor_loss.sum(0).mean()
     a.loss_out[4] = (float)critic;
+    a.loss_out[5] = (float)a.stats[7];  // number of images whose label is outside [0, Nc)
+    if (a.stats[7] > 0.0)
+        for (int i = 0; i < 5; ++i) a.loss_out[i] = __int_as_float(0x7fc00000);  // NaN: never a silently wrong number
 }
 
 int loss_phase_b(const LossArgs& a, cudaStream_t s) {

@@ -89,8 +89,24 @@ class EpisodeEngine:
         self.Hc_state = self.view("Hc", f32, (T + 1, na, nb, d["n_a"]))
         self.Cc_state = self.view("Cc", f32, (T + 1, na, nb, d["n_a"]))
         self.msg = self.view("msg", f32, (T + 1, na, nb, d["n_m"]))
-        self.seed(seed if seed is not None else int(th.initial_seed() & 0x7FFFFFFFFFFFFFFF))
+        self.seed(seed if seed is not None else self._default_seed())
         self.launches = {"forward": 0, "loss": 0, "backward": 0}
+        # bumped by every forward(): an autograd node built on one rollout refuses to run its backward
+        # once another rollout has overwritten the workspace (H, C, U, probs, actions, positions)
+        self.generation = 0
+
+    def _default_seed(self) -> int:
+        """torch's seed mixed with the process rank and the engine's geometry: data-parallel ranks that all
+        called ``torch.manual_seed(s)`` (the usual practice) must not draw identical initial positions /
+        states / action uniforms for the same local slot, and two engines of one process (main batch and
+        ragged last batch) must not replay the same Philox stream."""
+        import os
+        import zlib
+
+        rank = int(os.environ.get("RANK", "0"))
+        geo = zlib.crc32(repr((self.na, self.nb, self.T, self.C, self.H, self.W)).encode())
+        mixed = int(th.initial_seed()) ^ (rank * 0x9E3779B97F4A7C15) ^ (geo * 0xC2B2AE3D27D4EB4F)
+        return mixed & 0x7FFFFFFFFFFFFFFF
 
     def __del__(self):
         try:
@@ -154,6 +170,7 @@ class EpisodeEngine:
             keep.append(actions)
         self._last_img = img
         self._keep = keep
+        self.generation += 1
         _lib.check(self._L.marlc_episode_forward(self._h, img.data_ptr(), p0, hid, act, self._stream()))
         self.launches["forward"] = self._L.marlc_engine_last_launches(self._h)
 
@@ -185,6 +202,7 @@ class EpisodeEngine:
     def model_step(self, patch, msg, npos, hidden) -> None:
         hid = (ct.c_void_p * 4)(*[h.data_ptr() for h in hidden])
         self._keep = [patch, msg, npos, *hidden]
+        self.generation += 1
         _lib.check(self._L.marlc_model_step(self._h, patch.data_ptr(), msg.data_ptr(), npos.data_ptr(), hid,
                                             self._stream()))
 
@@ -214,6 +232,7 @@ class _RolloutFn(th.autograd.Function):
     def forward(ctx, engine: EpisodeEngine, img, pos0, hidden0, actions, *params):
         engine.forward(img, pos0, hidden0, actions)
         ctx.engine = engine
+        ctx.generation = engine.generation
         ctx.img = img
         ctx.n_params = len(params)
         ctx.mark_non_differentiable(engine.step_pos)
@@ -222,6 +241,12 @@ class _RolloutFn(th.autograd.Function):
     @staticmethod
     def backward(ctx, g_preds, g_logp, g_values, _g_pos):
         eng: EpisodeEngine = ctx.engine
+        if eng.generation != ctx.generation:
+            raise RuntimeError(
+                "run_episode(): the engine's workspace was overwritten by a later rollout of the same geometry "
+                "(another run_episode / eval / visualisation call) before loss.backward() of this one; the "
+                "activations BPTT needs are gone.  Call backward() before the next episode on this sampler "
+                "(gradient accumulation: backward each episode in turn).")
         eng.d_preds.copy_(g_preds) if g_preds is not None else eng.d_preds.zero_()
         eng.d_logp.copy_(g_logp) if g_logp is not None else eng.d_logp.zero_()
         eng.d_values.copy_(g_values) if g_values is not None else eng.d_values.zero_()
@@ -242,6 +267,25 @@ def rollout_autograd(engine: EpisodeEngine, img, pos0=None, hidden0=None, action
 
 
 # ---- stand-alone module forwards ------------------------------------------------------
+class _ForwardOnly(th.autograd.Function):
+    """The step-wise API (ModelsWrapper.forward / MultiAgent.act) computes through the engine, which keeps
+    no per-call autograd graph.  In grad mode its outputs are routed through this node so that a
+    ``backward()`` reaching them fails with a clear message instead of silently training nothing (the
+    reference's models.py:78-138 / agent.py:40-68 are differentiable; here training goes through
+    ``EpisodeSampler.run_episode`` -- one autograd node with the hand-written BPTT -- or ``Trainer``)."""
+
+    @staticmethod
+    def forward(ctx, anchor, *outs):
+        return tuple(o.view_as(o) for o in outs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        raise RuntimeError(
+            "ModelsWrapper.forward / MultiAgent.act are forward-only in this build: gradients flow through "
+            "EpisodeSampler.run_episode(...) (whole episode = one autograd node with hand-written BPTT) or "
+            "Trainer.train_step; wrap step-wise inference in torch.no_grad().")
+
+
 def model_step(model, img_patch, msg_t, norm_pos, hidden):
     """ModelsWrapper.forward (models.py:78-138) through the engine, slot 0."""
     from .networks.models import ModelOutput, RecurrentOutput
@@ -264,6 +308,13 @@ def model_step(model, img_patch, msg_t, norm_pos, hidden):
         messages=eng.msg[1].clone(),
     )
     rec = RecurrentOutput(eng.H_state[1].clone(), eng.C_state[1].clone(), eng.Hc_state[1].clone(), eng.Cc_state[1].clone())
+    if th.is_grad_enabled():
+        anchor = next((p for p in model.parameters() if p.requires_grad), None)
+        if anchor is not None:  # same values; a backward() through them raises (see _ForwardOnly)
+            o = _ForwardOnly.apply(anchor, out.actions_probabilities, out.values, out.predictions, out.messages,
+                                   rec.h, rec.c, rec.h_caret, rec.c_caret)
+            out = ModelOutput(*o[:4])
+            rec = RecurrentOutput(*o[4:])
     return out, rec
 
 

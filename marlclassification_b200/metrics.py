@@ -30,7 +30,11 @@ class ConfusionMeter:
         self.__counts: Optional[th.Tensor] = None  # int64[Nc * Nc], lives where the batches live
 
     def __bincount(self, cells: th.Tensor) -> th.Tensor:
-        return th.bincount(cells, minlength=self.__nb_class**2)
+        out = th.bincount(cells, minlength=self.__nb_class**2)
+        if out.numel() != self.__nb_class**2:
+            raise RuntimeError(f"ConfusionMeter: a label is outside [0, {self.__nb_class}) "
+                               "(nb_class smaller than the dataset's number of classes?)")
+        return out
 
     def add(self, y_proba: th.Tensor, y_true: th.Tensor) -> None:
         cells = (y_true.detach() * self.__nb_class + y_proba.detach().argmax(dim=1)).to(th.int64)

@@ -26,12 +26,17 @@ class TrainStep:
         dev = engine.device
         self.static_img = th.zeros(engine.nb, engine.C, engine.H, engine.W, dtype=th.float32, device=dev)
         self.static_y = th.zeros(engine.nb, dtype=th.int64, device=dev)
-        self._graphs: Optional[list] = None
-        self._warm = 0
+        # one set of graphs per mode: drawn on the device (False) / injected draws in static buffers (True)
+        self._graphs: dict = {False: None, True: None}
+        self._warm = {False: 0, True: 0}
+        self._inj: Optional[dict] = None  # static pos0 / hidden0 / actions (parity runs through the graph path)
 
     # ---- the segments between collectives -----------------------------------------
-    def _seg_forward(self) -> None:
-        self.engine.forward(self.static_img)
+    def _seg_forward(self, injected: bool = False) -> None:
+        if injected:
+            self.engine.forward(self.static_img, self._inj["pos0"], self._inj["hidden0"], self._inj["actions"])
+        else:
+            self.engine.forward(self.static_img)
         self.engine.loss_phase_a(self.static_y)
 
     def _seg_backward(self) -> None:
@@ -41,35 +46,37 @@ class TrainStep:
     def _seg_update(self) -> None:
         self.optim.step(1.0 / self.dp.world_size)
 
-    def _segments(self):
+    def _segments(self, injected: bool = False):
+        fwd = lambda: self._seg_forward(injected)  # noqa: E731
         if self.dp.enabled:
-            return [self._seg_forward, self._seg_backward, self._seg_update]
-        return [lambda: (self._seg_forward(), self._seg_backward(), self._seg_update())]
+            return [fwd, self._seg_backward, self._seg_update]
+        return [lambda: (fwd(), self._seg_backward(), self._seg_update())]
 
-    def _capture(self) -> None:
+    def _capture(self, injected: bool) -> None:
         graphs = []
-        for seg in self._segments():
+        for seg in self._segments(injected):
             g = th.cuda.CUDAGraph()
             with th.cuda.graph(g):
                 seg()
             graphs.append(g)
-        self._graphs = graphs
+        self._graphs[injected] = graphs
 
     @property
     def launches_per_step(self) -> int:
         l = self.engine.launches
         return l["forward"] + l["loss"] + l["backward"] + 2  # + Adam (2 kernels)
 
-    def run_static(self) -> th.Tensor:
-        """Run one step on whatever is in static_img / static_y."""
+    def run_static(self, injected: bool = False) -> th.Tensor:
+        """Run one step on whatever is in static_img / static_y (and, when ``injected``, in the static
+        draw buffers).  Two eager steps, then the step is captured and replayed."""
         eng, dp = self.engine, self.dp
-        if self.use_graph and self._graphs is None and self._warm >= 2:
-            self._capture()
-        if self._graphs is not None:
-            segs = [g.replay for g in self._graphs]
+        if self.use_graph and self._graphs[injected] is None and self._warm[injected] >= 2:
+            self._capture(injected)
+        if self._graphs[injected] is not None:
+            segs = [g.replay for g in self._graphs[injected]]
         else:
-            segs = self._segments()
-            self._warm += 1
+            segs = self._segments(injected)
+            self._warm[injected] += 1
         if dp.enabled:
             segs[0]()
             dp.all_reduce_stats(eng.loss_stats)
@@ -86,25 +93,27 @@ class TrainStep:
         if isinstance(img, StagedBatch):
             img.deliver(self.static_img, self.static_y)
             return self.run_static()
-        if inject.get("pos0") is not None or inject.get("hidden0") is not None or inject.get("actions") is not None:
-            return self._run_injected(img, y, inject)
         self.static_img.copy_(img, non_blocking=True)
         self.static_y.copy_(y, non_blocking=True)
+        if inject.get("pos0") is not None or inject.get("hidden0") is not None or inject.get("actions") is not None:
+            self._stage_injection(inject)
+            return self.run_static(injected=True)
         return self.run_static()
 
-    def _run_injected(self, img, y, inject) -> th.Tensor:
-        """Parity path: explicit draws, eager (pointers differ per call)."""
-        eng, dp = self.engine, self.dp
-        self.static_img.copy_(img, non_blocking=True)
-        self.static_y.copy_(y, non_blocking=True)
-        eng.forward(self.static_img, inject.get("pos0"), inject.get("hidden0"), inject.get("actions"))
-        eng.loss_phase_a(self.static_y)
-        dp.all_reduce_stats(eng.loss_stats)
-        eng.loss_phase_b()
-        eng.backward(self.static_img)
-        dp.all_reduce_grads_sum(eng.model.flat_grads)
-        self._seg_update()
-        return eng.loss_out
+    def _stage_injection(self, inject) -> None:
+        """Parity path: the three random sites of the reference (initial positions, initial recurrent
+        state, per-step actions) are copied into STATIC buffers, so the injected step runs through the
+        same capture / replay machinery as the production step (all three must be given)."""
+        if any(inject.get(k) is None for k in ("pos0", "hidden0", "actions")):
+            raise RuntimeError("injected train step: pos0, hidden0 and actions must all be given")
+        if self._inj is None:
+            self._inj = {"pos0": th.empty_like(inject["pos0"], device=self.engine.device).contiguous(),
+                         "hidden0": [th.empty_like(h, device=self.engine.device).contiguous() for h in inject["hidden0"]],
+                         "actions": th.empty_like(inject["actions"], device=self.engine.device).contiguous()}
+        self._inj["pos0"].copy_(inject["pos0"], non_blocking=True)
+        for dst, src in zip(self._inj["hidden0"], inject["hidden0"]):
+            dst.copy_(src, non_blocking=True)
+        self._inj["actions"].copy_(inject["actions"], non_blocking=True)
 
 
 class EvalStep:
@@ -117,30 +126,38 @@ class EvalStep:
         self.static_img = th.zeros(engine.nb, engine.C, engine.H, engine.W, dtype=th.float32, device=dev)
         self.static_y = th.zeros(engine.nb, dtype=th.int64, device=dev)
         self.vote = th.zeros(engine.nb, engine.step_preds.shape[-1], dtype=th.float32, device=dev)
-        self._graph: Optional[th.cuda.CUDAGraph] = None
-        self._warm = 0
+        self._graph: dict = {False: None, True: None}
+        self._warm = {False: 0, True: 0}
+        self._inj: Optional[dict] = None
 
-    def _body(self) -> None:
-        self.engine.forward(self.static_img)
+    def _body(self, injected: bool = False) -> None:
+        if injected:
+            self.engine.forward(self.static_img, self._inj["pos0"], self._inj["hidden0"], self._inj["actions"])
+        else:
+            self.engine.forward(self.static_img)
         th.mean(self.engine.step_preds[-1], dim=0, out=self.vote)  # prediction.mean(0), trainer.py:180
 
-    def run_static(self) -> th.Tensor:
-        if self.use_graph and self._graph is None and self._warm >= 2:
+    def run_static(self, injected: bool = False) -> th.Tensor:
+        if self.use_graph and self._graph[injected] is None and self._warm[injected] >= 2:
             g = th.cuda.CUDAGraph()
             with th.cuda.graph(g):
-                self._body()
-            self._graph = g
-        if self._graph is not None:
-            self._graph.replay()
+                self._body(injected)
+            self._graph[injected] = g
+        if self._graph[injected] is not None:
+            self._graph[injected].replay()
         else:
-            self._body()
-            self._warm += 1
+            self._body(injected)
+            self._warm[injected] += 1
         return self.vote
 
-    def __call__(self, img) -> th.Tensor:
-        """Returns the [Nb, Nc] vote (a static buffer: clone it to keep it across calls)."""
+    def __call__(self, img, **inject) -> th.Tensor:
+        """Returns the [Nb, Nc] vote (a static buffer: clone it to keep it across calls).  ``pos0`` /
+        ``hidden0`` / ``actions`` inject the reference's random draws (static buffers, same graph path)."""
         if isinstance(img, StagedBatch):
             img.deliver(self.static_img, self.static_y)
         else:
             self.static_img.copy_(img, non_blocking=True)
+        if any(inject.get(k) is not None for k in ("pos0", "hidden0", "actions")):
+            TrainStep._stage_injection(self, inject)
+            return self.run_static(injected=True)
         return self.run_static()

@@ -72,16 +72,17 @@ class Trainer:
             self.__steps[id(eng)] = step
         return step(x, y, **inject)
 
-    def eval_step(self, x, episode_sampler: EpisodeSampler) -> th.Tensor:
+    def eval_step(self, x, episode_sampler: EpisodeSampler, **inject) -> th.Tensor:
         """Forward-only episode; returns the [Nb, Nc] agent-mean prediction of the last step
-        (static device buffer, overwritten by the next call).  ``x``: tensor or StagedBatch."""
+        (static device buffer, overwritten by the next call).  ``x``: tensor or StagedBatch.
+        ``pos0`` / ``hidden0`` / ``actions`` inject the reference's random draws (parity tests)."""
         eng = episode_sampler.engine_for(x, gamma=self.__gamma)
         step = self.__eval_steps.get(id(eng))
         if step is None:
             step = EvalStep(eng, use_graph=self.__cuda_graph)
             self.__eval_steps[id(eng)] = step
         with th.no_grad():
-            return step(x)
+            return step(x, **inject)
 
     def prefetch(self, batches, *, hwc: bool = True) -> DevicePrefetcher:
         """Wrap an iterable of host ``(images, labels)`` batches (fp32 NCHW as the reference's
@@ -98,8 +99,11 @@ class Trainer:
             # meters: ONE packed device->host read per iteration (the five loss scalars + mean
             # precision / recall of the running confusion matrix) instead of the reference's 7+ syncs
             self.__conf_meter.add(eng.step_preds[-1].mean(dim=0), y_train)
-            packed = th.cat((loss_out[:5], self.__conf_meter.mean_precision_recall().to(loss_out.dtype)))
-            loss_item, path_item, error_item, actor_item, critic_item, *prec_rec = packed.tolist()
+            packed = th.cat((loss_out[:6], self.__conf_meter.mean_precision_recall().to(loss_out.dtype)))
+            loss_item, path_item, error_item, actor_item, critic_item, bad_labels, *prec_rec = packed.tolist()
+            if bad_labels > 0:  # the reference's cross_entropy raises a device assert here (trainer.py:83-87)
+                raise RuntimeError(f"{int(bad_labels)} label(s) of the batch are outside [0, {self.__nb_class}): "
+                                   "nb_class is smaller than the dataset's number of classes")
             self.__path_loss_meter.add(path_item)
             self.__error_meter.add(error_item)
             self.__actor_loss_meter.add(actor_item)

@@ -353,6 +353,48 @@ def loss_and_grads(p, cfg, img, targets, pos0, hidden0, actions, nb_step, gamma)
     return ro, parts, {k: (g if g is not None else torch.zeros_like(leaf[k])) for k, g in zip(names, grads)}
 
 
+def train_steps(p, cfg, img, targets, pos0, hidden0, actions, nb_step, gamma, lr, n_steps):
+    """``n_steps`` optimisation steps of trainer.py:66-116 on ONE batch with the same injected draws
+    every step: rollout -> loss -> ``backward`` -> ``th.optim.Adam(lr)`` (trainer.py:33 defaults:
+    betas (0.9, 0.999), eps 1e-8).  Returns (final params, [loss per step])."""
+    leaf = {k: v.detach().clone().requires_grad_(True) for k, v in p.items()}
+    opt = torch.optim.Adam(list(leaf.values()), lr=lr)
+    losses = []
+    for _ in range(n_steps):
+        ro = rollout(leaf, cfg, img, pos0, hidden0, actions, nb_step)
+        parts = a2c_loss(ro.step_preds, ro.step_log_probas, ro.step_values, targets, gamma)
+        opt.zero_grad()
+        parts.loss.backward()
+        opt.step()
+        losses.append(float(parts.loss.detach()))
+    return {k: v.detach() for k, v in leaf.items()}, losses
+
+
+def confusion_matrix(batches, nb_class: int, window_size=None):
+    """metrics.py:25-108: the meter keeps the last ``window_size`` (argmax prediction, target) batches
+    (all when None), rebuilds the matrix from their concatenation with ``bincount`` (rows = true
+    class), and derives per-class precision (diag / column sum) and recall (diag / row sum), 0 where
+    the denominator is 0.  ``batches``: iterable of (y_proba [B, Nc], y_true [B]).
+    Returns (conf_mat int64 [Nc, Nc], precision f32 [Nc], recall f32 [Nc])."""
+    kept = []
+    for y_proba, y_true in batches:
+        if window_size is not None and len(kept) >= window_size:  # metrics.py:38-44
+            kept.pop(0)
+        kept.append((y_proba.argmax(dim=1), y_true))
+    y_pred = torch.cat([a for a, _ in kept])
+    y_true = torch.cat([b for _, b in kept])
+    cm = torch.bincount(y_true * nb_class + y_pred, minlength=nb_class**2).reshape(nb_class, nb_class)
+    diag = torch.diagonal(cm, 0)
+
+    def ratio(tot):
+        out = torch.zeros(nb_class)
+        mask = tot != 0
+        out[mask] = diag[mask] / tot[mask]
+        return out
+
+    return cm, ratio(cm.sum(dim=0)), ratio(cm.sum(dim=1))
+
+
 def init_params(cfg: OracleConfig, seed: int = 0) -> Dict[str, torch.Tensor]:
     """Random parameters with the reference's shapes and init distribution
     (init.py:6-29: orthogonal(gain sqrt2) weights, zero biases, norm affine

@@ -12,7 +12,7 @@ if ROOT not in sys.path:
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 GOLDEN_NAMES = sorted(n for n in (os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.pt")))
-                      if n != "input_pipeline")  # episode fixtures; input_pipeline.pt holds ToTensor vectors
+                      if n not in ("input_pipeline", "metrics"))  # episode fixtures; the others hold ToTensor / meter vectors
 
 
 def pytest_configure(config):

@@ -1,5 +1,11 @@
-"""Two-rank NCCL run of the real train step: sharded batch + stats exchange + ONE flat
-gradient all-reduce + fused Adam  ==  the single-GPU full-batch step (needs >= 2 GPUs)."""
+"""Data-parallel train step over NCCL, on the path bench.py times: default tf32x3 mode, CUDA-graph
+replay, sharded batch + advantage-statistics exchange + flat gradient all-reduce + fused Adam.
+
+Checked against the ORACLE's full-batch optimisation steps (trainer.py:66-116 restated on the CPU:
+rollout -> loss -> backward -> Adam) with the same injected draws: a G-rank run on shards of the batch
+must follow the single-process reference trajectory.  Needs >= 2 GPUs; the world size
+follows the box (2 and, when available, every visible GPU).
+"""
 import os
 import socket
 
@@ -8,9 +14,12 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from tests.conftest import load_golden, rel_l2
+from tests.conftest import load_golden, oracle_config, rel_l2
 
 pytestmark = pytest.mark.gpu
+
+STEPS = 6
+LR = 1e-3
 
 
 def _free_port() -> int:
@@ -24,9 +33,9 @@ def _build(fx, dev):
     from marlclassification_b200.core import EpisodeSampler
 
     model, marl, env = ModelConfig(**fx["model_config"]).build_marl(fx["na"])
-    model.use_tc = False
     model.load_state_dict(fx["state_dict"])
     model.to(dev)
+    assert model.use_tc and model.precision == "tf32x3"  # the default (timed) arithmetic
     return model, EpisodeSampler(marl, env, fx["T"], gamma=fx["gamma"])
 
 
@@ -43,34 +52,70 @@ def _worker(rank, world, port, out_path):
     nb = fx["nb"] - fx["nb"] % world
     dp = DataParallelContext()
     model, sampler = _build(fx, dev)
-    trainer = Trainer(model, fx["model_config"]["nb_class"], 1e-3, fx["gamma"], dp=dp, cuda_graph=False)
-    sl = lambda t, dim: dp.shard(t[(slice(None),) * dim + (slice(0, nb),)].transpose(0, dim)).transpose(0, dim).contiguous().to(dev)  # noqa: E731
+    trainer = Trainer(model, fx["model_config"]["nb_class"], LR, fx["gamma"], dp=dp, cuda_graph=True)
+
+    def sl(t, dim):  # this rank's images along the batch axis `dim`
+        t = t.movedim(dim, 0)[:nb]
+        return dp.shard(t).movedim(0, dim).contiguous().to(dev)
+
     img, y = sl(fx["img"], 0), sl(fx["targets"], 0)
     inject = dict(pos0=sl(fx["pos0"], 1), hidden0=[sl(h, 1) for h in fx["hidden0"]], actions=sl(fx["actions"], 2))
-    for _ in range(2):
+    losses = []
+    for _ in range(STEPS):  # 2 eager steps, capture, replays
         out = trainer.train_step(img, y, sampler, **inject)
+        losses.append(out[:5].clone())
     torch.cuda.synchronize()
+    step = next(iter(trainer._Trainer__steps.values()))
+    assert step._graphs[True] is not None, "the injected step was never captured"
+    # replicas must stay bit-identical (same all-reduced gradients, same Adam)
+    mine = model.flat_params.clone()
+    ref = mine.clone()
+    dist.broadcast(ref, src=0)
+    same = torch.tensor([float(torch.equal(mine, ref))], device=dev)
+    dist.all_reduce(same, op=dist.ReduceOp.MIN)
     if rank == 0:
-        torch.save({"params": model.flat_params.cpu(), "loss": out.cpu()}, out_path)
+        torch.save({"params": {k: p.detach().cpu() for k, p in model.named_parameters()},
+                    "losses": torch.stack(losses).cpu(), "replicas_identical": bool(same.item())}, out_path)
     dist.barrier()
     dist.destroy_process_group()
 
 
+def _worlds():
+    n = torch.cuda.device_count()
+    return sorted({w for w in (2, n) if 2 <= w <= n})
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_gpu_step_matches_single_gpu(tmp_path):
-    from marlclassification_b200.training import Trainer
+@pytest.mark.parametrize("world", _worlds() or [2])
+def test_dp_graph_steps_follow_oracle_full_batch(tmp_path, world):
+    from oracle import marl_oracle as O
 
     out = str(tmp_path / "dp.pt")
-    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
-    res = torch.load(out)
+    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    res = torch.load(out, weights_only=False)
+    assert res["replicas_identical"]
     fx = load_golden("conftest_odd")
-    nb = fx["nb"] - fx["nb"] % 2
-    dev = torch.device("cuda", 0)
-    model, sampler = _build(fx, dev)
-    trainer = Trainer(model, fx["model_config"]["nb_class"], 1e-3, fx["gamma"], cuda_graph=False)
-    inject = dict(pos0=fx["pos0"][:, :nb].contiguous().to(dev), hidden0=[h[:, :nb].contiguous().to(dev) for h in fx["hidden0"]],
-                  actions=fx["actions"][:, :, :nb].contiguous().to(dev))
-    for _ in range(2):
-        trainer.train_step(fx["img"][:nb].to(dev), fx["targets"][:nb].to(dev), sampler, **inject)
-    torch.cuda.synchronize()
-    assert rel_l2(res["params"], model.flat_params.cpu()) < 1e-5
+    nb = fx["nb"] - fx["nb"] % world
+    ocfg = oracle_config(fx["model_config"])
+    new, losses = O.train_steps(fx["state_dict"], ocfg, fx["img"][:nb], fx["targets"][:nb], fx["pos0"][:, :nb],
+                                [h[:, :nb] for h in fx["hidden0"]], fx["actions"][:, :, :nb], fx["T"], fx["gamma"],
+                                LR, STEPS)
+    # the loss the ranks report is their SHARD's (trainer.py:111 is a mean over the local images); the
+    # global one is its mean over ranks, which rank 0 cannot see -- so compare trajectories through
+    # the parameters: total update after STEPS Adam steps, per parameter tensor
+    worst, worst_k = 0.0, ""
+    for k, p0 in fx["state_dict"].items():
+        upd_ref = new[k] - p0
+        if upd_ref.norm() == 0:
+            continue
+        err = rel_l2(res["params"][k] - p0, upd_ref)
+        if err > worst:
+            worst, worst_k = err, k
+    flat = lambda d: torch.cat([d[k].flatten() for k in fx["state_dict"]])  # noqa: E731
+    e_params = rel_l2(flat(res["params"]), flat(new))
+    print(f"dp world={world}: params rel-L2 vs oracle after {STEPS} steps = {e_params:.2e}; worst per-tensor UPDATE "
+          f"rel-L2 = {worst:.2e} ({worst_k.split('__')[-1]}); oracle losses {losses[0]:.4f} -> {losses[-1]:.4f}")
+    assert e_params < 1e-4
+    # Adam divides by |g|: elements whose gradient is ~0 amplify fp32-level differences, hence a loose
+    # bound on the update itself (a wrong 1/world scale or a missing statistics exchange gives O(1))
+    assert worst < 5e-2, (worst_k, worst)
