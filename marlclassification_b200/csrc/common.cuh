@@ -181,6 +181,11 @@ int gemm_nt(const float* X, long ldx, const float* W, long ldw, const float* bia
 int gemm_nn(const float* dY, long lddy, const float* W, long ldw, float* dX, long lddx, int M, int N, int K,
             int accumulate, cudaStream_t s);
 // dW[N,K] (+)= dY[R,N]^T X[R,K]            (weight gradient, reduction over rows)
+// ---- skinny.cu: products with a handful of outputs per row (HBM-bound reductions)
+int rowdot(const float* X, long ldx, const float* w, const float* bias, float* Y, long ldy, int R, int K, int accumulate,
+           cudaStream_t s);
+int tn_skinny(const float* dY, long lddy, const float* X, long ldx, float* dW, long lddw, int R, int N, int K,
+              int accumulate, cudaStream_t s, bool* done);
 int gemm_tn(const float* dY, long lddy, const float* X, long ldx, float* dW, long lddw, int R, int N, int K,
             int accumulate, cudaStream_t s);
 

@@ -335,7 +335,9 @@ extern "C" int marlc_engine_create(const marlc_config* c, marlc_engine** out) {
     for (int l = 0; l < e->L; ++l) {
         const size_t npos = (size_t)d.hout[l] * d.hout[l];
         e->add_buf("cnn_dY" + std::to_string(l), TM * npos * d.cout[l] * F4);
-        e->add_buf("cnn_col" + std::to_string(l), TM * npos * d.cin[l] * 9 * F4);
+        // (rows padded to a multiple of 4 floats: the 27-float rows of the first layer become a TMA-addressable
+        //  operand of the weight-gradient GEMM)
+        e->add_buf("cnn_col" + std::to_string(l), TM * npos * (size_t)((d.cin[l] * 9 + 3) & ~3) * F4);
         e->add_buf("cnn_gnpart" + std::to_string(l), TM * 2 * d.cout[l] * F4);
         if (l > 0) e->add_buf("cnn_dcol" + std::to_string(l), TM * npos * d.cin[l] * 9 * F4);
     }
@@ -487,7 +489,7 @@ static int G_nn_on(const marlc_engine* e, const float* dY, long lddy, const floa
 // dW[N,K] += dY[R,N]^T X[R,K]   (reduction over rows R; both operands MN-major)
 static int G_tn(const marlc_engine* e, const float* dY, long lddy, const float* X, long ldx, float* dW, long lddw, int R,
                 int N, int K, cudaStream_t s) {
-    if (e->cfg.use_tc && tc_worth(N, K, R) && K >= 16) {
+    if (e->cfg.use_tc && N > 8 && tc_worth(N, K, R) && K >= 16) {  // N <= 8: one-pass reduction (skinny.cu)
         TcGemmArgs a;
         a.A = tc_op(dY, lddy, true); a.B = tc_op(X, ldx, true); a.K = R;
         a.C = dW; a.ldc = lddw; a.M = N; a.N = K; a.accumulate = 1;
@@ -1046,13 +1048,14 @@ extern "C" int marlc_episode_backward(marlc_engine* e, const float* img, int acc
             const size_t npos = (size_t)d.hout[l] * d.hout[l];
             ysave[l] = e->buf("cnn_y" + std::to_string(l)) + (par ? r0 * e->cnn_sz[l] : 0);
             bb.dY[l] = e->buf("cnn_dY" + std::to_string(l)) + (par ? r0 * npos * d.cout[l] : 0);
-            bb.col[l] = e->buf("cnn_col" + std::to_string(l)) + (par ? r0 * npos * d.cin[l] * 9 : 0);
+            bb.col[l] = e->buf("cnn_col" + std::to_string(l)) + (par ? r0 * npos * (size_t)((d.cin[l] * 9 + 3) & ~3) : 0);
             bb.gnpart[l] = e->buf("cnn_gnpart" + std::to_string(l)) + (par ? r0 * 2 * d.cout[l] : 0);
             if (l > 0) dcol[l] = e->buf("cnn_dcol" + std::to_string(l)) + (par ? r0 * npos * d.cin[l] * 9 : 0);
         }
         auto conv_weight_grad = [&](int l, cudaStream_t st) -> int {
             const int npos = d.hout[l] * d.hout[l], kk = d.cin[l] * 9, co = d.cout[l];
-            return G_tn(e, bb.dY[l], co, bb.col[l], kk, e->grd(CNN_PREFIX + std::to_string(3 * l) + ".weight"), kk,
+            const int pitch = (par && l == 0) ? (kk + 3) & ~3 : kk;  // the batched im2col pads the input layer's rows
+            return G_tn(e, bb.dY[l], co, bb.col[l], pitch, e->grd(CNN_PREFIX + std::to_string(3 * l) + ".weight"), kk,
                         R * npos, co, kk, st);
         };
         if (!par) {  // unfused reference path: one whole-episode call of the per-window kernel

@@ -133,6 +133,7 @@ static GemmProblem blank() {
 
 int gemm_nt(const float* X, long ldx, const float* W, long ldw, const float* bias, float* Y, long ldy, int M, int N,
             int K, int accumulate, cudaStream_t s) {
+    if (N == 1 && M >= 256) return rowdot(X, ldx, W, bias, Y, ldy, M, K, accumulate, s);  // critic head: a row-wise dot
     GemmLaunch g;
     g.count = 1;
     g.splits = 1;
@@ -166,6 +167,11 @@ int gemm_nn(const float* dY, long lddy, const float* W, long ldw, float* dX, lon
 int gemm_tn(const float* dY, long lddy, const float* X, long ldx, float* dW, long lddw, int R, int N, int K,
             int accumulate, cudaStream_t s) {
     // dW[n,k] = sum_r dY[r,n] X[r,k]: reduction over rows R (split-K with atomics).
+    {   // a handful of outputs per row: one coalesced pass over the tall operand (skinny.cu)
+        bool done = false;
+        MARLC_TRY(tn_skinny(dY, lddy, X, ldx, dW, lddw, R, N, K, accumulate, s, &done));
+        if (done) return 0;
+    }
     GemmLaunch g;
     g.count = 1;
     GemmProblem p = blank();
