@@ -4,7 +4,10 @@
 // so a rollout step is 4 launches forward and 3 backward instead of 17 + 13.
 #include <initializer_list>
 
+#include <stdlib.h>
+
 #include "chain.cuh"
+#include "cnn_wide.cuh"
 
 namespace marlc {
 
@@ -268,6 +271,14 @@ static int staged_floats(int maxw, int n1, int p1, int n2, int p2) {
     const size_t w = (size_t)n1 * p1 + (size_t)n2 * p2;
     return (chain_smem_bytes(maxw) + sizeof(float) * w <= CHAIN_SMEM_LIMIT) ? (int)w : 0;
 }
+// Weights resident in shared memory make ONE row block fast (no L2 round trips inside its dependent chain) but
+// cost 80-190 KB per CTA: one CTA = 4 rows per SM at a time.  With many row blocks per SM (sharded-batch
+// configurations: 1024 row blocks at 4096 rows) the latency of each chain is better hidden by running several
+// small CTAs per SM that read the weights through L1/L2.  Threshold in row blocks: MARLC_CHAIN_STAGE_MAX_RB.
+static bool stage_weights_for(int M) {
+    static const int max_rb = getenv("MARLC_CHAIN_STAGE_MAX_RB") ? atoi(getenv("MARLC_CHAIN_STAGE_MAX_RB")) : (1 << 30);
+    return (M + RB - 1) / RB <= max_rb;
+}
 static int maxw_of(std::initializer_list<int> v) {
     int m = 4;
     for (int x : v) m = max(m, x);
@@ -277,6 +288,165 @@ static int maxw_of(std::initializer_list<int> v) {
 // ---------------------------------------------------------------------------------
 // forward "pre": CNN role (blocks [0,M)) | decoder + position-feature role
 // ---------------------------------------------------------------------------------
+// Many windows per step (sharded-batch configurations): grid = feature-extractor CTAs (first, so they are
+// scheduled first) + decoder CTAs, all persistent.
+//   cnn_blocks: wide feature extractor (cnn_wide.cuh), each CTA loops over batches of CW_NW windows;
+//   dec_blocks: PERSISTENT row-block CTAs: weights and LayerNorm affines are staged once per CTA, then the CTA
+//               walks row blocks rb = i, i + dec_blocks, ...  (At 4096 rows a step had 1024 CTAs that each
+//               re-staged 82 KB of decoder weights for 4 rows: 81 us per step, ncu launch list round 2.)
+struct StepPreWideArgs { StepPreArgs a; int maxw; int staged; int cnn_blocks; int dec_blocks; CnnWidePlan wide; };
+
+__global__ void __launch_bounds__(CT) step_pre_wide_kernel(const StepPreWideArgs ka) {
+    extern __shared__ __align__(16) float sm[];
+    const StepPreArgs& a = ka.a;
+    if ((int)blockIdx.x < ka.cnn_blocks) {
+        cnn_fwd_wide(a.cnn, ka.wide, blockIdx.x, ka.cnn_blocks, sm);
+        return;
+    }
+    const int db = (int)blockIdx.x - ka.cnn_blocks;
+    const int nrb = (a.M + RB - 1) / RB;
+    const int n_m = a.d0.n_in, n1 = a.d0.n_out, n2 = a.d3.n_out;
+    ChainSmem S(sm, ka.maxw);
+    const int P0 = odd_pitch(n_m), P3 = odd_pitch(n1);
+    float* W0s = S.wres;
+    float* W3s = W0s + n1 * P0;
+    const int tid = threadIdx.x;
+    const bool fast = ka.staged && RB * n_m <= CT && n1 <= CT && n2 <= CT && 2 * (n1 + n2) <= CT * WT_P;
+    float* sG0 = S.wt;  // fast path: LayerNorm affines parked in the (otherwise unused) weight-tile scratch
+    float* sB0 = sG0 + n1;
+    float* sG3 = sB0 + n1;
+    float* sB3 = sG3 + n2;
+    const int mr = tid / n_m, mj = tid - mr * n_m;  // fast path: (row, column) of the collected message this thread owns
+    auto load_mean = [&](int rb) -> float {
+        const int row0 = rb * RB;
+        return (tid < RB * n_m && rb < nrb && row0 + mr < a.M) ? other_agents_mean(a.msg_in, row0 + mr, mj, a.Na, a.Nb, n_m) : 0.f;
+    };
+    // ---- once per CTA.  Every global operand is requested up front, grouped ahead of any use (see bwd_pre):
+    //      the first row block's message mean and the affines, then the (synchronously staged) weights
+    float mv = fast ? load_mean(db) : 0.f;
+    if (fast) {
+        float g0 = 0.f, b0 = 0.f, g3 = 0.f, b3 = 0.f;
+        if (tid < n1) { g0 = a.d0.g[tid]; b0 = a.d0.be[tid]; }
+        if (tid < n2) { g3 = a.d3.g[tid]; b3 = a.d3.be[tid]; }
+        stage_w(W0s, a.d0.W, n1, n_m, P0);
+        stage_w(W3s, a.d3.W, n2, n1, P3);
+        if (tid < n1) { sG0[tid] = g0; sB0[tid] = b0; }
+        if (tid < n2) { sG3[tid] = g3; sB3[tid] = b3; }
+    } else if (ka.staged) {
+        stage_w(W0s, a.d0.W, n1, n_m, P0);
+        stage_w(W3s, a.d3.W, n2, n1, P3);
+    }
+    for (int rb = db; rb < nrb; rb += ka.dec_blocks) {
+        const int row0 = rb * RB;
+        const int rows_valid = min(RB, a.M - row0);
+        if (fast) {
+            if (tid < RB * n_m) {
+                if (mr < rows_valid) a.coll[(long)(row0 + mr) * n_m + mj] = mv;
+                S.bufT[mj * RB + mr] = mv;
+            }
+            __syncthreads();
+            mv = load_mean(rb + ka.dec_blocks);  // next row block's operand, in flight under this block's chain
+            rb_linear_s(S.bufT, W0s, P0, a.d0.b, S.bufA, ka.maxw, n1, n_m);
+            rb_ln_silu(S.bufA, ka.maxw, n1, sG0, sB0, rows_valid, row0, a.dec_y1, n1, a.dec_s1, n1, S.bufT);
+            rb_linear_s(S.bufT, W3s, P3, a.d3.b, S.bufA, ka.maxw, n2, n1);
+            rb_ln_silu(S.bufA, ka.maxw, n2, sG3, sB3, rows_valid, row0, a.dec_y2, n2, a.U + a.F, a.ldu, nullptr,
+                       a.U_lo ? a.U_lo + a.F : nullptr);
+        } else {
+            // collected message (mean of the other agents)                      message.py:5-17
+            for (int e = tid; e < RB * n_m; e += CT) {
+                const int r = e / n_m, j = e % n_m;
+                float v = 0.f;
+                if (r < rows_valid) {
+                    v = other_agents_mean(a.msg_in, row0 + r, j, a.Na, a.Nb, n_m);
+                    a.coll[(long)(row0 + r) * n_m + j] = v;
+                }
+                S.bufT[j * RB + r] = v;
+            }
+            __syncthreads();
+            // decoder block 0 and block 3                                        message.py:36-49
+            if (ka.staged) rb_linear_s(S.bufT, W0s, P0, a.d0.b, S.bufA, ka.maxw, n1, n_m);
+            else rb_linear(S.bufT, a.d0.W, a.d0.b, S.bufA, ka.maxw, n1, n_m, S.wt);
+            rb_ln_silu(S.bufA, ka.maxw, n1, a.d0.g, a.d0.be, rows_valid, row0, a.dec_y1, n1, a.dec_s1, n1, S.bufT);
+            if (ka.staged) rb_linear_s(S.bufT, W3s, P3, a.d3.b, S.bufA, ka.maxw, n2, n1);
+            else rb_linear(S.bufT, a.d3.W, a.d3.b, S.bufA, ka.maxw, n2, n1, S.wt);
+            rb_ln_silu(S.bufA, ka.maxw, n2, a.d3.g, a.d3.be, rows_valid, row0, a.dec_y2, n2, a.U + a.F, a.ldu, nullptr,
+                       a.U_lo ? a.U_lo + a.F : nullptr);
+        }
+        // position features                                                  state.py:7-17
+        {
+            const int warp = tid >> 5, lane = tid & 31, nd = a.pos.n_out;
+            if (warp < rows_valid) {
+                const long m = row0 + warp;
+                const float p0 = a.npos[2 * m], p1 = a.npos[2 * m + 1];
+                const float inv = 1.0f / (float)nd;
+                float sum = 0.f;
+                for (int j = lane; j < nd; j += 32) {
+                    const float y = fmaf(p1, a.pos.W[2 * j + 1], p0 * a.pos.W[2 * j]) + a.pos.b[j];
+                    a.pos_y[m * nd + j] = y;
+                    S.bufB[warp * ka.maxw + j] = y;
+                    sum += y;
+                }
+                const float mean = warp_sum(sum) * inv;
+                float v = 0.f;
+                for (int j = lane; j < nd; j += 32) { const float d = S.bufB[warp * ka.maxw + j] - mean; v += d * d; }
+                const float rstd = 1.0f / sqrtf(warp_sum(v) * inv + LN_EPS_C);
+                float* o = a.U + m * a.ldu + a.F + n2;
+                float* ol = a.U_lo ? a.U_lo + m * a.ldu + a.F + n2 : nullptr;
+                for (int j = lane; j < nd; j += 32) {
+                    const float v2 = siluf_((S.bufB[warp * ka.maxw + j] - mean) * rstd * a.pos.g[j] + a.pos.be[j]);
+                    o[j] = v2;
+                    if (ol) ol[j] = tf32_lo(v2);
+                }
+            }
+        }
+        __syncthreads();  // the row buffers are reused by the next row block
+    }
+}
+
+// CTAs of a persistent row-block role: every row block gets its own CTA while that fits in `waves` waves of the
+// machine (the latency-bound regime: nothing to amortise), more rows make the CTAs loop
+static int persistent_blocks(int nrb, size_t smem_bytes, int waves = 1) {
+    const int per_sm = (int)max((size_t)1, min((size_t)8, (size_t)(220 * 1024) / max(smem_bytes, (size_t)1)));
+    return max(1, min(nrb, MARLC_SMS * per_sm * waves));
+}
+
+static int step_pre_small(const StepPreArgs& a, cudaStream_t s);
+
+int step_pre(const StepPreArgs& a, cudaStream_t s) {
+    if (a.M <= 0) return 0;
+    // feature extractor: one CTA per window while a step has few windows (latency-bound, every SM gets one:
+    // step_pre_kernel); from MARLC_CNN_WIDE_MIN windows on, persistent CTAs with stationary weights, 8 windows
+    // per pass, next to persistent decoder CTAs (step_pre_wide_kernel)
+    static const int wide_min = getenv("MARLC_CNN_WIDE_MIN") ? atoi(getenv("MARLC_CNN_WIDE_MIN")) : 256;
+    static_assert(CW_THREADS == CT, "the wide feature extractor runs inside the chain kernel's CTA shape");
+    StepPreWideArgs ka;
+    memset(&ka.wide, 0, sizeof(ka.wide));
+    if (a.M >= wide_min) ka.wide = cnn_wide_plan(a.cnn.d, a.cnn.img != nullptr && a.cnn.patch == nullptr);
+    if (!ka.wide.ok) return step_pre_small(a, s);
+    ka.a = a;
+    ka.maxw = maxw_of({a.d0.n_in, a.d0.n_out, a.d3.n_out, a.pos.n_out});
+    const int wfl = staged_floats(ka.maxw, a.d0.n_out, odd_pitch(a.d0.n_in), a.d3.n_out, odd_pitch(a.d3.n_in));
+    ka.staged = wfl > 0;
+    ka.cnn_blocks = min((a.M + CW_NW - 1) / CW_NW, MARLC_SMS);
+    const size_t smem = max(chain_smem_bytes(ka.maxw) + sizeof(float) * (size_t)wfl, sizeof(float) * (size_t)ka.wide.smem_floats);
+    MARLC_CHECK(smem <= 226 * 1024, "step_pre: shared memory %zu B too large", smem);
+    static size_t attr = 0;
+    if (smem > 48 * 1024 && smem > attr) {
+        MARLC_CUDA(cudaFuncSetAttribute(step_pre_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = smem;
+    }
+    // (the launch's shared memory is the larger role's: one CTA per SM, so the decoder CTAs share the SMs with the
+    //  feature extractor's in time; one wave of them)
+    ka.dec_blocks = persistent_blocks((a.M + RB - 1) / RB, smem);
+    // profiling aid (WRONG results): time the feature-extractor role alone (1) / the decoder role alone (2)
+    static const int prof = getenv("MARLC_PROFILE_PRE_ROLE") ? atoi(getenv("MARLC_PROFILE_PRE_ROLE")) : 0;
+    if (prof == 2) ka.cnn_blocks = 0;
+    const int grid = ka.cnn_blocks + (prof == 1 ? 0 : ka.dec_blocks);
+    step_pre_wide_kernel<<<grid, CT, smem, s>>>(ka);
+    MARLC_LAUNCH_CHECK();
+    return 0;
+}
+
 struct StepPreKernelArgs { StepPreArgs a; int maxw; int staged; };
 
 __global__ void __launch_bounds__(CT) step_pre_kernel(const StepPreKernelArgs ka) {
@@ -372,7 +542,7 @@ __global__ void __launch_bounds__(CT) step_pre_kernel(const StepPreKernelArgs ka
     }
 }
 
-int step_pre(const StepPreArgs& a, cudaStream_t s) {
+static int step_pre_small(const StepPreArgs& a, cudaStream_t s) {
     if (a.M <= 0) return 0;
     StepPreKernelArgs ka;
     ka.a = a;
@@ -585,7 +755,7 @@ int step_post(const StepPostArgs& a, cudaStream_t s) {
     ka.a = a;
     ka.maxw = maxw_of({a.e3.n_in, a.e3.n_out});
     ka.pol_blocks = (a.M + CT / 32 - 1) / (CT / 32);
-    const int wfl = staged_floats(ka.maxw, a.e3.n_out, odd_pitch(a.e3.n_in), 0, 0);
+    const int wfl = stage_weights_for(a.M) ? staged_floats(ka.maxw, a.e3.n_out, odd_pitch(a.e3.n_in), 0, 0) : 0;
     ka.staged = wfl > 0;
     const size_t smem = max(chain_smem_bytes(ka.maxw) + sizeof(float) * (size_t)wfl, sizeof(float) * (size_t)(CT / 32) * a.act.nl);
     MARLC_CHECK(smem <= 200 * 1024, "step_post: shared memory %zu B too large", smem);
@@ -856,7 +1026,7 @@ int bwd_pre(const BwdPreArgs& a, cudaStream_t s) {
     BwdPreKernelArgs ka;
     ka.a = a;
     ka.maxw = maxw_of({a.n_m, a.e0.n_out, a.n[0]});
-    const int wfl = staged_floats(ka.maxw, a.n_m, a.e0.n_out, a.e0.n_out, a.n[0]);
+    const int wfl = stage_weights_for(a.M) ? staged_floats(ka.maxw, a.n_m, a.e0.n_out, a.e0.n_out, a.n[0]) : 0;
     ka.staged = wfl > 0;
     const size_t smem = chain_smem_bytes(ka.maxw) + sizeof(float) * (size_t)wfl;
     MARLC_CHECK(smem <= 200 * 1024, "bwd_pre: shared memory %zu B too large", smem);
@@ -974,7 +1144,7 @@ int bwd_post(const BwdPostArgs& a, cudaStream_t s) {
     BwdPostKernelArgs ka;
     ka.a = a;
     ka.maxw = maxw_of({a.n_m, a.d0.n_out, a.n_m_o});
-    const int wfl = staged_floats(ka.maxw, a.n_m_o, a.d0.n_out, a.d0.n_out, a.n_m);
+    const int wfl = stage_weights_for(a.M) ? staged_floats(ka.maxw, a.n_m_o, a.d0.n_out, a.d0.n_out, a.n_m) : 0;
     ka.staged = wfl > 0;
     const size_t smem = chain_smem_bytes(ka.maxw) + sizeof(float) * (size_t)wfl;
     MARLC_CHECK(smem <= 200 * 1024, "bwd_post: shared memory %zu B too large", smem);

@@ -1,0 +1,371 @@
+// Wide gather + CNN forward: NW windows per pass, weights stationary in shared memory.
+//
+// The per-window block (cnn_device.cuh) is the right shape for the reference's batch sizes (128
+// windows = one CTA per SM, latency-bound).  At the sharded-batch configurations (M = 512 .. 4096
+// windows per step) it re-stages 95 KB of weights per window (390 MB of L2 -> SMEM traffic per step
+// at M = 4096) and runs one window's three-layer dependency chain per SM at a time: 265 us per
+// step at M = 4096, i.e. 4 TFLOP/s of fp32 (ncu launch list, round 2).  Here a CTA
+//   * loads all conv weights (transposed [cin*9][cout]), biases and GroupNorm affines ONCE and
+//     then loops over batches of NW = 8 windows (persistent, grid <= #SM);
+//   * keeps activations as [channel][y][x][window] (window fastest, zero border): a thread owns 4
+//     output channels x 8 windows at one output position, so a tap costs three 128-bit shared
+//     loads (8 inputs, 4 weights) for 32 FMAs -- 10x fewer shared-memory bytes per FMA than one
+//     window at a time -- and the lanes of a warp read distinct banks or broadcast;
+//   * splits the input channels of the narrow late layers over `ks` thread groups (partial
+//     planes, summed when the pre-norm outputs are saved for backward);
+//   * computes GroupNorm statistics two-pass (as the reference) with lanes = 4 elements x 8
+//     windows (conflict-free), and writes y_save / the output with 32-byte coalesced rows;
+//   * prefetches the next batch's windows with cp.async as soon as layer 0 has consumed the
+//     current ones.
+// Same arithmetic as cnn_fwd_block_t (fp32 FFMA, fast SiLU); summation order differs (parity tests
+// hold both to the oracle).  vision.py:23-57.
+#pragma once
+#include "cnn_device.cuh"
+
+namespace marlc {
+
+constexpr int CW_NW = 8;        // windows per pass
+constexpr int CW_THREADS = 256;  // = the chain kernels' CTA (step_pre hosts this role); 512 threads as a separate launch
+                                 // measured no faster per batch and cost a fork / join per step
+constexpr int CW_MAX_KS = 8;
+
+struct CnnWidePlan {
+    int ok;                          // 0: shapes not supported (caller uses the per-window block)
+    int w_off[MAX_CNN_LAYERS];       // floats: transposed weights of layer l
+    int p_off[MAX_CNN_LAYERS];       // bias | gamma | beta (3 * cout)
+    int in_off[MAX_CNN_LAYERS];      // zero-bordered input of layer l: [cin][hin+2][hin+2][NW]
+    int y_off;                       // pre-norm outputs, up to CW_MAX_KS partial planes of [cout][npos][NW]
+    int st_off;                      // GroupNorm: (unused) mean[G][NW] | rstd[G][NW] | cross-warp scratch [warps][NW]
+    int ks[MAX_CNN_LAYERS];          // input-channel slices of layer l
+    int smem_floats;
+};
+
+inline CnnWidePlan cnn_wide_plan(const CnnDesc& d, bool have_img) {
+    CnnWidePlan p;
+    memset(&p, 0, sizeof(p));
+    if (!have_img || !d.wT[0]) return p;
+    int off = 0;
+    for (int l = 0; l < d.L; ++l) {
+        if (!d.wT[l] || (d.cout[l] & 3) || d.groups[l] > 32 || d.cout[l] % d.groups[l]) return p;
+        p.w_off[l] = off;
+        off += d.cout[l] * d.cin[l] * 9;
+    }
+    for (int l = 0; l < d.L; ++l) { p.p_off[l] = off; off += 3 * d.cout[l]; }
+    off = (off + 3) & ~3;
+    for (int l = 0; l < d.L; ++l) {
+        p.in_off[l] = off;
+        off += d.cin[l] * (d.hin[l] + 2) * (d.hin[l] + 2) * CW_NW;
+    }
+    // input-channel slices: as many as there are idle threads, within what is left of shared memory for the
+    // partial planes (224 KB budget: one CTA per SM owns practically all of its shared memory)
+    const int st_floats = (2 * 32 + CW_THREADS / 32) * CW_NW;
+    const int ybudget = 224 * 256 - off - st_floats;
+    int ymax = 0;
+    for (int l = 0; l < d.L; ++l) {
+        const int items = d.hout[l] * d.hout[l] * (d.cout[l] >> 2);
+        const int plane = d.cout[l] * d.hout[l] * d.hout[l] * CW_NW;
+        if (plane > ybudget) return p;
+        int ks = 1;
+        while (ks < CW_MAX_KS && items * (ks + 1) <= CW_THREADS && ks + 1 <= d.cin[l] && (ks + 1) * plane <= ybudget) ++ks;
+        const int cpk = (d.cin[l] + ks - 1) / ks;
+        ks = (d.cin[l] + cpk - 1) / cpk;  // drop slices that would be empty
+        p.ks[l] = ks;
+        ymax = max(ymax, ks * plane);
+    }
+    p.y_off = off;
+    off += ymax;
+    p.st_off = off;
+    off += st_floats;
+    p.smem_floats = off;
+    p.ok = (size_t)off * sizeof(float) <= 224 * 1024;
+    return p;
+}
+
+__device__ __forceinline__ int cw_div(int n, float rcp) { return __float2int_rz(((float)n + 0.5f) * rcp); }  // n < 2^16
+
+// Request the interior of layer 0's input for the windows of a batch (4-byte cp.async: rows of f floats are
+// contiguous in the image, the destination is window-interleaved).  One thread per (window, channel, row):
+// the window's corner and image index come from shared memory (`win`: {py, px, image} per window, loaded by
+// cw_load_windows one phase earlier), the f copies of a row need no index arithmetic.  (First version: one
+// element per thread iteration with three divisions, a modulo and two dependent global loads of the
+// position each -- 4.8 M warp instructions per launch at 4096 windows and ~5000 exposed cycles per batch.)
+__device__ __forceinline__ void cw_load_windows(const CnnFwdArgs& a, int* win, int batch) {
+    const int m = batch * CW_NW + (int)threadIdx.x;
+    if (threadIdx.x < CW_NW && m < a.M) {
+        win[threadIdx.x * 4 + 0] = a.pos[2 * m];
+        win[threadIdx.x * 4 + 1] = a.pos[2 * m + 1];
+        win[threadIdx.x * 4 + 2] = m % a.B;
+    }
+}
+__device__ __forceinline__ void cw_issue_gather(const CnnFwdArgs& a, float* in0, const int* win, int batch) {
+    const CnnDesc& d = a.d;
+    const int f = d.f, c0 = d.cin[0], hp = f + 2;
+    const int nvalid = min(CW_NW, a.M - batch * CW_NW);
+    const int rows_per = c0 * f;
+    const float r_per = 1.0f / (float)rows_per, r_f = 1.0f / (float)f;
+    const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(in0);
+    for (int r = threadIdx.x; r < nvalid * rows_per; r += CW_THREADS) {
+        const int w = cw_div(r, r_per), q = r - w * rows_per, c = cw_div(q, r_f), i = q - c * f;
+        const int py = win[w * 4], px = win[w * 4 + 1], b = win[w * 4 + 2];
+        const float* src = a.img + ((long)(b * d.img_c + c) * a.H + py + i) * a.W + px;
+        uint32_t dst = dst0 + 4u * (uint32_t)(((c * hp + i + 1) * hp + 1) * CW_NW + w);
+        for (int j = 0; j < f; ++j, dst += 4u * CW_NW)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src + j) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+// CTA `cta` of `n_cta` cooperating CTAs; all CW_THREADS threads must call.
+__device__ __forceinline__ void cnn_fwd_wide(const CnnFwdArgs& a, const CnnWidePlan& pl, const int cta, const int n_cta,
+                                             float* sm) {
+    const CnnDesc& d = a.d;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nbatch = (a.M + CW_NW - 1) / CW_NW;
+    if (cta >= nbatch) return;
+#ifdef MARLC_CNN_TRACE  // timeline of CTA 0 (cycles since entry): setup, then per batch / layer: conv, pass A, B, C
+    __shared__ long long cw_tr[48];
+    const long long cw_t0 = clock64();
+    int cw_i = 0;
+#define CW_TRACE() do { if (cta == 0 && tid == 0 && cw_i < 48) cw_tr[cw_i] = clock64() - cw_t0; ++cw_i; } while (0)
+#else
+#define CW_TRACE() do { } while (0)
+#endif
+    // ---- once per CTA: zero the activation buffers (their borders stay zero), stage weights + affines
+    __shared__ __align__(8) uint64_t wbar;
+    __shared__ int s_win[2][CW_NW * 4];  // {py, px, image} of the current / next batch's windows
+    cw_load_windows(a, s_win[0], cta);
+    const uint32_t wbar_a = (uint32_t)__cvta_generic_to_shared(&wbar);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(wbar_a));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    {
+        float4* z = reinterpret_cast<float4*>(sm + pl.in_off[0]);
+        const int n4 = (pl.y_off - pl.in_off[0]) >> 2;
+        for (int i = tid; i < n4; i += CW_THREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();  // the gather below writes into the zeroed buffer
+    cw_issue_gather(a, sm + pl.in_off[0], s_win[0], cta);
+    // weights: ONE bulk copy per layer (the copy engine moves them while the threads go on), completion on wbar
+    if (tid == 0) {
+        uint32_t bytes = 0;
+        for (int l = 0; l < d.L; ++l) bytes += (uint32_t)(d.cout[l] * d.cin[l] * 9 * 4);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(wbar_a), "r"(bytes) : "memory");
+        for (int l = 0; l < d.L; ++l)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             (uint32_t)__cvta_generic_to_shared(sm + pl.w_off[l])), "l"(d.wT[l]),
+                         "r"((uint32_t)(d.cout[l] * d.cin[l] * 9 * 4)), "r"(wbar_a) : "memory");
+    }
+    for (int l = 0; l < d.L; ++l) {
+        float* pp = sm + pl.p_off[l];
+        for (int i = tid; i < d.cout[l]; i += CW_THREADS) {
+            pp[i] = d.b[l][i];
+            pp[d.cout[l] + i] = d.gn_w[l][i];
+            pp[2 * d.cout[l] + i] = d.gn_b[l][i];
+        }
+    }
+    CW_TRACE();  // 0: zeroed, gather + weight staging issued
+    float* ybuf = sm + pl.y_off;
+    float* s_mean = sm + pl.st_off;
+    float* s_rstd = s_mean + 32 * CW_NW;
+    float* s_red = s_rstd + 32 * CW_NW;
+
+    int wbuf = 0;
+    for (int batch = cta; batch < nbatch; batch += n_cta, wbuf ^= 1) {
+        const int m0 = batch * CW_NW, nvalid = min(CW_NW, a.M - m0);
+        if (batch + n_cta < nbatch) cw_load_windows(a, s_win[wbuf ^ 1], batch + n_cta);  // visible after layer 0's barrier
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (batch == cta) {  // first batch: the weights must have landed
+            uint32_t done;
+            do {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(done) : "r"(wbar_a) : "memory");
+            } while (!done);
+        }
+        __syncthreads();  // windows of this batch (and, first time, the affines) are in shared memory
+        CW_TRACE();  // batch start: inputs ready
+        for (int l = 0; l < d.L; ++l) {
+            const int ci_n = d.cin[l], co_n = d.cout[l], hi = d.hin[l], ho = d.hout[l];
+            const int hp = hi + 2, npos = ho * ho, total = co_n * npos, ncg = co_n >> 2;
+            const int G = d.groups[l], cpg = co_n / G, ng = cpg * npos;
+            const bool last = (l + 1 == d.L);
+            const float* in = sm + pl.in_off[l];
+            const float* wl = sm + pl.w_off[l];
+            const float* prm = sm + pl.p_off[l];
+            const int ks = pl.ks[l], cpk = (ci_n + ks - 1) / ks, items = npos * ncg;
+            // ---- convolution: work item = (input-channel slice, output position, group of 4 output channels)
+            {
+                const float r_items = 1.0f / (float)items, r_ncg = 1.0f / (float)ncg, r_ho = 1.0f / (float)ho;
+                for (int wk = tid; wk < items * ks; wk += CW_THREADS) {
+                    const int kslice = cw_div(wk, r_items), item = wk - kslice * items;
+                    const int pos = cw_div(item, r_ncg), c4 = (item - pos * ncg) << 2;
+                    const int oy = cw_div(pos, r_ho), ox = pos - oy * ho;
+                    const int ci0 = kslice * cpk, ci1 = min(ci_n, ci0 + cpk);
+                    float acc[4][CW_NW];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float bj = kslice == 0 ? prm[c4 + j] : 0.f;
+#pragma unroll
+                        for (int w = 0; w < CW_NW; ++w) acc[j][w] = bj;
+                    }
+                    const float* x = in + ((ci0 * hp + 2 * oy) * hp + 2 * ox) * CW_NW;
+                    const float* wq = wl + (ci0 * 9) * co_n + c4;
+                    for (int ci = ci0; ci < ci1; ++ci, x += hp * hp * CW_NW, wq += 9 * co_n) {
+#pragma unroll
+                        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                            for (int kx = 0; kx < 3; ++kx) {
+                                const float4 x0 = *reinterpret_cast<const float4*>(x + (ky * hp + kx) * CW_NW);
+                                const float4 x1 = *reinterpret_cast<const float4*>(x + (ky * hp + kx) * CW_NW + 4);
+                                const float4 w4 = *reinterpret_cast<const float4*>(wq + (ky * 3 + kx) * co_n);
+                                const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+                                const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                                    for (int w = 0; w < CW_NW; ++w) acc[j][w] = fmaf(wv[j], xv[w], acc[j][w]);
+                            }
+                    }
+                    float* y = ybuf + (kslice * total + c4 * npos + pos) * CW_NW;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        *reinterpret_cast<float4*>(y + j * npos * CW_NW) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+                        *reinterpret_cast<float4*>(y + j * npos * CW_NW + 4) = make_float4(acc[j][4], acc[j][5], acc[j][6], acc[j][7]);
+                    }
+                }
+            }
+            __syncthreads();
+            CW_TRACE();  // conv done
+            if (l == 0 && batch + n_cta < nbatch)  // layer 0's input buffer is free: prefetch the next batch's windows
+                cw_issue_gather(a, sm + pl.in_off[0], s_win[wbuf ^ 1], batch + n_cta);
+            // ---- GroupNorm + SiLU.  Warps are bound to groups (nwarps / G warps share a group when G < nwarps,
+            //      their partial sums meet in shared memory); lane = (4 elements) x (8 windows): conflict-free
+            //      shared accesses, 16-byte rows per window in global memory.  Two-pass statistics as the
+            //      reference.  Three COMPACT loops over shared memory (4 elements in flight per lane each):
+            //      a version that kept the values in registers through fully unrolled loops was 96 KB of
+            //      straight-line code per layer and ran out of the instruction cache -- `no_instruction` was the
+            //      top stall reason in ncu, 35 % issue-active.
+            {
+#ifdef CW_NO_YSAVE
+                float* ysave = nullptr;
+#else
+                float* ysave = a.y_save[l];
+#endif
+                const float* gam = prm + co_n;
+                const float* bet = prm + 2 * co_n;
+                const int w = lane & 7, es = lane >> 3;
+                constexpr int nwarps = CW_THREADS / 32;
+                const bool shared_groups = G < nwarps && nwarps % G == 0;
+                const int wpg = shared_groups ? nwarps / G : 1;
+                const int estep = 4 * wpg;
+                const float inv = 1.0f / (float)ng, r_npos = 1.0f / (float)npos, r_ho = 1.0f / (float)ho;
+                float* nxt = last ? nullptr : sm + pl.in_off[l + 1];
+                const int hop = ho + 2;
+                const bool wok = w < nvalid;
+                for (int g0 = 0; g0 < G; g0 += (shared_groups ? G : nwarps)) {
+                    const int g = shared_groups ? warp / wpg : g0 + warp;
+                    const int sub = shared_groups ? warp % wpg : 0;
+                    const int el0 = sub * 4 + es;
+                    const int n_el = (g < G) ? ng : 0;  // inactive warps run empty loops (they still meet the barriers)
+                    float* yg = ybuf + (g < G ? g : 0) * ng * CW_NW + w;
+                    float* ys = ysave ? ysave + (long)(m0 + w) * total + g * ng : nullptr;
+                    // pass 1: sum the input-channel slices (kept in plane 0), save for backward, accumulate the sum
+                    float s = 0.f;
+#pragma unroll 1
+                    for (int el = el0; el < n_el; el += 4 * estep) {
+                        float x[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int e = el + u * estep;
+                            x[u] = e < n_el ? yg[e * CW_NW] : 0.f;
+                        }
+                        for (int p = 1; p < ks; ++p)
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const int e = el + u * estep;
+                                if (e < n_el) x[u] += yg[(p * total + e) * CW_NW];
+                            }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int e = el + u * estep;
+                            if (e < n_el) {
+                                if (ks > 1) yg[e * CW_NW] = x[u];
+                                if (ys && wok) ys[e] = x[u];
+                            }
+                            s += x[u];
+                        }
+                    }
+                    s += __shfl_xor_sync(0xffffffffu, s, 8);
+                    s += __shfl_xor_sync(0xffffffffu, s, 16);
+                    if (shared_groups) {
+                        if (es == 0) s_red[warp * CW_NW + w] = s;
+                        __syncthreads();
+                        s = 0.f;
+                        for (int i = 0; i < wpg; ++i) s += s_red[(g * wpg + i) * CW_NW + w];
+                        __syncthreads();
+                    }
+                    const float mean = s * inv;
+                    // pass 2: centred second moment
+                    float q = 0.f;
+#pragma unroll 1
+                    for (int el = el0; el < n_el; el += 4 * estep) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int e = el + u * estep;
+                            const float dd = e < n_el ? yg[e * CW_NW] - mean : 0.f;
+                            q = fmaf(dd, dd, q);
+                        }
+                    }
+                    q += __shfl_xor_sync(0xffffffffu, q, 8);
+                    q += __shfl_xor_sync(0xffffffffu, q, 16);
+                    if (shared_groups) {
+                        if (es == 0) s_red[warp * CW_NW + w] = q;
+                        __syncthreads();
+                        q = 0.f;
+                        for (int i = 0; i < wpg; ++i) q += s_red[(g * wpg + i) * CW_NW + w];
+                        __syncthreads();
+                    }
+                    const float rstd = 1.0f / sqrtf(q * inv + GN_EPS);
+                    // pass 3: normalise, SiLU, hand over (next layer's zero-bordered input, or the output rows)
+#pragma unroll 1
+                    for (int el = el0; el < n_el; el += 4 * estep) {
+                        float x[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int e = el + u * estep;
+                            x[u] = e < n_el ? yg[e * CW_NW] : 0.f;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int el_u = el + u * estep;
+                            if (el_u < n_el) {
+                                const int e = g * ng + el_u, c = cw_div(e, r_npos), pos = e - c * npos;
+                                const float z = (x[u] - mean) * rstd * gam[c] + bet[c];
+                                const float o = __fdividef(z, 1.0f + __expf(-z));  // SiLU
+                                if (!last) {
+                                    const int oy = cw_div(pos, r_ho), ox = pos - oy * ho;
+                                    nxt[((c * hop + oy + 1) * hop + ox + 1) * CW_NW + w] = o;
+                                } else if (wok) {
+                                    a.out[(long)(m0 + w) * a.ldo + e] = o;
+                                    if (a.out_lo) a.out_lo[(long)(m0 + w) * a.ldo + e] = tf32_lo(o);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            CW_TRACE();  // GroupNorm + SiLU done
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#ifdef MARLC_CNN_TRACE
+    if (cta == 0 && tid == 0) {
+        printf("cnn wide trace:");
+        for (int i = 0; i < cw_i && i < 48; ++i) printf(" %lld", cw_tr[i]);
+        printf(" | end %lld\n", clock64() - cw_t0);
+    }
+#endif
+}
+
+}  // namespace marlc
