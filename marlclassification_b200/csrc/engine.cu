@@ -622,6 +622,8 @@ static int step_networks(marlc_engine* e, int t, const float* img, const int* po
                 TcLstmArgs& a = la[k];
                 a.U.lo = e->lo_on ? e->buf("U_lo") : nullptr;
                 a.Hprev.lo = e->lo_of(a.Hprev.ptr);
+                static const int a_lo = getenv("MARLC_LSTM_A_LO") ? atoi(getenv("MARLC_LSTM_A_LO")) : 1;  // A/B toggle
+                if (!a_lo) { a.U.lo = nullptr; a.Hprev.lo = nullptr; }  // activations' lo part split in-kernel
                 a.Wih_lo = e->lo_of(a.Wih); a.Whh_lo = e->lo_of(a.Whh);
                 a.h_new_lo = const_cast<float*>(e->lo_of(a.h_new));
             }

@@ -507,7 +507,7 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
             // 128 x 64 tile, ~40 % of a small launch.  The pipeline ring is dead by now (every MMA has
             // retired), so the staging tile reuses it.
             constexpr int PITCH = BN + 4;  // 16-byte aligned rows, conflict-free for 128-bit accesses
-            static_assert(4 * 32 * PITCH * 4 <= S::BYTES - 1024, "epilogue staging tile does not fit in the ring");
+            static_assert(EPI != EPI_STORE || 4 * 32 * PITCH * 4 <= S::BYTES - 1024, "epilogue staging tile does not fit in the ring");
             float* stg = reinterpret_cast<float*>(smem) + q * 32 * PITCH;
             const int nbase = n_tile * BN;
             const bool vec = ((e_ldc & 3) == 0) && (((uintptr_t)e_C & 15) == 0);
@@ -904,7 +904,7 @@ int tc_gemm(const TcGemmArgs& a, cudaStream_t s) { return tc_gemm_group(&a, 1, s
 template <int BN, bool X3, int KS>
 static int launch_lstm(TcKernelGroup& kp, int gx, int gy, int nkb, cudaStream_t s) {
     (void)nkb;
-    constexpr int STAGES = KS > 1 ? 2 : (BN >= 128 ? 3 : 4);  // KS == 1: 3 x 32 KB, two CTAs per SM
+    constexpr int STAGES = BN >= 256 ? (X3 ? 2 : 4) : (KS > 1 ? 2 : (BN >= 128 ? 3 : 4));  // KS == 1: 3 x 32 KB, two CTAs per SM
     using S = TcSmem<BN, STAGES, X3, KS>;
     static_assert(S::BYTES <= 227 * 1024, "tile configuration exceeds shared memory");
     auto kern = tc_gemm_kernel<BN, false, false, EPI_LSTM, STAGES, X3, KS>;
@@ -954,6 +954,12 @@ int tc_lstm_pair(const TcLstmArgs& c0, const TcLstmArgs& c1, cudaStream_t s) {
     // hidden units per CTA: small tiles when M is small (more CTAs), 32 when rows are plentiful
     const int mt = (c0.M + BM - 1) / BM;
     int HU = mt >= 8 ? 32 : (mt >= 2 ? 16 : 8);
+    // 128 x 256 tiles (64 hidden units x 4 gates) once they still fill the machine: a kind::tf32 MMA reads its
+    // operands from shared memory at 128 B/clk for a 128 x 128 tile (the whole shared-memory bandwidth of the
+    // SM, before the TMA writes and the 3xTF32 low-order tiles), 96 B/clk for 128 x 256 -- and the tile streams
+    // 25 % fewer operand bytes per flop (MARLC_LSTM_HU64=0 switches it off)
+    static const int hu64 = getenv("MARLC_LSTM_HU64") ? atoi(getenv("MARLC_LSTM_HU64")) : 1;
+    if (hu64 && c0.n % 64 == 0 && c1.n % 64 == 0 && 2 * mt * (c0.n / 64) >= MARLC_SMS) HU = 64;
     while (HU > 8 && (c0.n % HU != 0 || c1.n % HU != 0)) HU >>= 1;
     MARLC_CHECK(c0.n % HU == 0 && c1.n % HU == 0, "tc_lstm_pair: hidden size not a multiple of %d", HU);
     TcKernelGroup kp;
@@ -1025,11 +1031,13 @@ int tc_lstm_pair(const TcLstmArgs& c0, const TcLstmArgs& c1, cudaStream_t s) {
     if (c0.x3) {
         if (HU == 8) return launch_lstm<32, true, 1>(kp, gx, mt, nkb, s);
         if (HU == 16) return launch_lstm<64, true, 1>(kp, gx, mt, nkb, s);
-        return launch_lstm<128, true, 1>(kp, gx, mt, nkb, s);
+        if (HU == 32) return launch_lstm<128, true, 1>(kp, gx, mt, nkb, s);
+        return launch_lstm<256, true, 1>(kp, gx, mt, nkb, s);
     }
     if (HU == 8) return launch_lstm<32, false, 1>(kp, gx, mt, nkb, s);
     if (HU == 16) return launch_lstm<64, false, 1>(kp, gx, mt, nkb, s);
-    return launch_lstm<128, false, 1>(kp, gx, mt, nkb, s);
+    if (HU == 32) return launch_lstm<128, false, 1>(kp, gx, mt, nkb, s);
+    return launch_lstm<256, false, 1>(kp, gx, mt, nkb, s);
 }
 
 }  // namespace marlc
