@@ -26,6 +26,7 @@ constexpr int UMMA_K = 8;
 constexpr int TC_THREADS = 192;
 constexpr int TC_THREADS_X3 = 320;  // + 4 warps that only split operands (the splitter is throughput-bound)
 constexpr int TC_SPLITTERS = TC_THREADS_X3 - 64;
+#define TC_SPLIT_GROUPS(stages) (((stages) % 2 == 0) ? 2 : 1)  // operand-splitter groups (see tc_gemm_body)
 constexpr int TC_MAX_CHAIN = 4096;  // longest K range one CTA accumulates in TMEM when split-K is allowed
 
 // ---------------------------------------------------------------------------------
@@ -313,7 +314,7 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
             // with A multicast a slot is refilled by every CTA of the cluster, so it is free only when
             // ALL of them have consumed it: every MMA warp arrives on every CTA's empty barrier
             mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], cl);
-            mbar_init(&split_bar[s], TC_SPLITTERS / 2);  // one of the two splitter groups
+            mbar_init(&split_bar[s], TC_SPLITTERS / TC_SPLIT_GROUPS(STAGES));  // one splitter group per slot
         }
         mbar_init(&tmem_full_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -463,10 +464,18 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
             // ---- operand splitter: lo = x - trunc_tf32(x) for every landed stage
             // two groups of 4 warps take alternate K blocks, so one group's barrier wake-up / proxy
             // fence / arrive latency overlaps the other group's copy loop
-            constexpr int GRP = TC_SPLITTERS / 2;
+            // (EVEN ring depth only: a group then meets the same slots on every round.  With an odd depth the two
+            //  groups alternate on a slot and each sees only every other phase of its full barrier; a parity wait
+            //  is unambiguous only against the immediately preceding phase, so a group that arrived while the
+            //  round it SKIPPED was still in flight -- TMA copies complete out of order -- took "parity differs"
+            //  for "my round has landed", split stale data and arrived on the other group's split barrier: phases
+            //  slipped, then a hang or `unspecified launch failure`.  Seen with the 3-stage 128-wide MN/MN variant
+            //  next to other streams' kernels, never under the serialising sanitizer.  Odd depths use ONE group.)
+            constexpr int NGRP = TC_SPLIT_GROUPS(STAGES);
+            constexpr int GRP = TC_SPLITTERS / NGRP;
             const int t = (threadIdx.x - 64) % GRP, grp = (threadIdx.x - 64) / GRP;
             const bool split_a = !p.a_lo_g, split_b = !p.b_lo_g;
-            for (int i = grp; (split_a || split_b) && i < my_kb; i += 2) {
+            for (int i = grp; (split_a || split_b) && i < my_kb; i += NGRP) {
                 const int s = i % stages, ph = (i / stages) & 1;
                 mbar_wait(&full_bar[s], ph);
                 float4* a_hi = reinterpret_cast<float4*>(sA + s * S::A_BYTES);
@@ -783,11 +792,9 @@ static int pick_bn(const TcGemmArgs* args, int count) {
         ctas128 += (long)((a.M + BM - 1) / BM) * ((a.N + 127) / 128) * chains;
     }
     static const int bn_cap = getenv("MARLC_TC_BN_MAX") ? atoi(getenv("MARLC_TC_BN_MAX")) : 128;  // A/B toggles
-    // 128-wide tiles for the MN-major x MN-major (weight-gradient) variant: OFF.  Measured in round 2: correct and
-    // clean under compute-sanitizer (serialised), but `unspecified launch failure` / a hang when its CTAs run next
-    // to other streams' kernels at T*M = 65 536 rows (graph replay, config c4); the 64-wide variant that round 1
-    // shipped is sound under the same concurrency.  Not understood yet -> kept behind this switch.
-    static const int dw128 = getenv("MARLC_TC_BN128_DW") ? atoi(getenv("MARLC_TC_BN128_DW")) : 0;
+    // (A/B toggles.  The 128-wide MN/MN weight-gradient variant exposed a phase-aliasing bug of the operand
+    //  splitter with odd ring depths -- fixed in tc_gemm_body, see the comment there.)
+    static const int dw128 = getenv("MARLC_TC_BN128_DW") ? atoi(getenv("MARLC_TC_BN128_DW")) : 1;
     static const int dx128 = getenv("MARLC_TC_BN128_DX") ? atoi(getenv("MARLC_TC_BN128_DX")) : 1;
     if (max_n <= 32) return 32;
     if (max_n <= 64 || ctas128 < MARLC_SMS / 2 || bn_cap < 128) return 64;
@@ -842,7 +849,8 @@ int tc_gemm_group(const TcGemmArgs* args, int count, cudaStream_t s) {
         }
         p.M = a.M; p.N = a.N; p.C = a.C; p.ldc = a.ldc; p.bias = a.bias; p.bias2 = a.bias2;
         p.accumulate = a.accumulate;
-        p.c_tma = ((a.ldc & 3) == 0 && ((uintptr_t)a.C & 15) == 0) ? 1 : 0;
+        static const int no_ctma = getenv("MARLC_TC_NO_CTMA") ? atoi(getenv("MARLC_TC_NO_CTMA")) : 0;  // A/B toggle
+        p.c_tma = (!no_ctma && (a.ldc & 3) == 0 && ((uintptr_t)a.C & 15) == 0) ? 1 : 0;
         if (p.c_tma) MARLC_TRY(make_map_c(&p.cmap, a.C, a.M, a.N, a.ldc));
         const int mt = (a.M + BM - 1) / BM, nt = (a.N + BN - 1) / BN, nkb = p.nk1 + p.nk2;
         int splits = 1;
