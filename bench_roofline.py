@@ -17,6 +17,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 FALLBACK = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
+MARLC_SMS = 148
 
 
 def peaks() -> tuple[dict, str]:
@@ -172,39 +173,122 @@ def to_tensor_u8(B: int, C: int, H: int, W: int, dev, reps: int = 50) -> dict:
             "us_per_launch": t * 1e6, "bytes_per_launch": bytes_alg, "gbs": bytes_alg / t / 1e9}
 
 
+def weight_grad_gemm(R: int, N: int, K: int, dev, reps: int = 20, x3: int = 1) -> dict:
+    """The batched weight-gradient product dW[N,K] += dY[R,N]^T X[R,K] (reduction over the R = T*M rows of an
+    iteration; both operands MN-major, split-K chains of 4096 rows, f32 reduce-add epilogue): the launch the
+    engine issues per LSTM cell for weight_ih (N = 4n, K = K_in)."""
+    from marlclassification_b200 import _lib
+
+    L = _lib.lib()
+    g = torch.Generator(device=dev).manual_seed(0)
+    dY = torch.randn(R, N, device=dev, generator=g)
+    X = torch.randn(R, K, device=dev, generator=g)
+    dW = torch.zeros(N, K, device=dev)
+
+    def run():
+        _lib.check(L.marlc_tc_gemm(dY.data_ptr(), N, 1, X.data_ptr(), K, 1, None, 0, None, 0, 0, None, dW.data_ptr(), K,
+                                   N, K, R, 1, 1, x3, _lib.stream_ptr(dev)))
+
+    t = _time(run, reps)
+    flops = 2.0 * R * N * K
+    return {"kernel": "tc_gemm_kernel<128, MN-major A, MN-major B, EPI_STORE> (batched weight gradient)",
+            "shape": {"R": R, "N": N, "K": K}, "us_per_launch": t * 1e6, "flops_per_launch": flops,
+            "tflops": flops / t / 1e12, "min_bytes_per_launch": 4.0 * (R * N + R * K + N * K)}
+
+
+def step_pre_wide(model, w: dict, nb: int, dev, reps: int = 20) -> dict:
+    """The per-step 'pre' launch of the episode at this batch (gather + feature extractor | message mean +
+    decoder + position features), timed through the engine's profiling stop (forward with only that launch
+    per step).  fp32 FFMA: reported against the CUDA-core peak, 148 SMs x 128 lanes x 2 flop x max clock."""
+    from marlclassification_b200.config import ModelConfig  # noqa: F401
+    from marlclassification_b200.engine import get_engine
+
+    img = torch.rand(nb, w["C"], w["H"], w["W"], device=dev)
+    eng = get_engine(model, na=w["na"], nb=nb, T=w["T"], C=w["C"], H=w["H"], W=w["W"], actions=w["actions"], gamma=0.99)
+
+    def run():
+        eng._L.marlc_engine_debug_stop(eng._h, 11)
+        eng.forward(img)
+        eng._L.marlc_engine_debug_stop(eng._h, 0)
+
+    t = _time(run, reps) / w["T"]  # T launches per forward (+ two small init launches)
+    M = w["na"] * nb
+    spec = model.feature_extractor.cnn_spec
+    f, layers = spec[0], spec[1]
+    h, flops_win = f, 0.0
+    for ci, co in layers:
+        h = (h - 1) // 2 + 1
+        flops_win += 2.0 * co * h * h * ci * 9
+    d = model.dims
+    flops = M * (flops_win + 2.0 * (d["n_m"] * 2 * d["n_m"] + 2 * d["n_m"] * d["n_m_o"]))
+    return {"kernel": "step_pre_wide_kernel" if M >= 256 else "step_pre_kernel", "shape": {"windows": M},
+            "us_per_launch": t * 1e6, "flops_per_launch": flops, "tflops": flops / t / 1e12}
+
+
 def roofline_for(model, w: dict, nb: int, dev) -> dict:
-    """The `roofline` object of bench.py's JSON line (+ the secondary kernels)."""
+    """The `roofline` object of bench.py's JSON line.  Main entry = the kernel with the LARGEST TIME SHARE of the
+    iteration among the kernels a roofline bounds (profiles/r2/launches_*.txt: the weight-gradient GEMM at
+    config c4; the fused LSTM pair at the batch-8 configurations), measured live here; `others` holds the rest of
+    the top of the launch list and the saturating micro-benchmarks of the HBM-bound kernels."""
     pk, src = peaks()
     d = model.dims
     M = w["na"] * nb
+    TM = M * w["T"]
     Kin = model.feature_extractor.out_size + d["n_m_o"] + d["n_d"]
     tf32_peak = tf32_cublas_peak(dev)
+    half_bf16 = 0.5 * float(pk.get("bf16_tflops", FALLBACK["bf16_tflops"]))
     x3 = 1 if getattr(model, "precision", "tf32x3") == "tf32x3" else 0
-    lstm = lstm_pair(M, Kin, d["n_b"], dev, x3=x3)
-    lstm_big = lstm_pair(4096, Kin, d["n_b"], dev, reps=50, x3=x3)
+    prec = "tf32x3 (3 MMAs per K step; achieved counts ALGORITHMIC flops once)" if x3 else "tf32"
+    lstm = lstm_pair(M, Kin, d["n_b"], dev, x3=x3, reps=50 if M > 1024 else 200)
+    dw = weight_grad_gemm(TM, 4 * d["n_b"], Kin, dev, reps=10 if TM > 16384 else 50, x3=x3)
+    pre = step_pre_wide(model, w, nb, dev)
     g_small = gather(w["na"], nb, w["C"], w["H"], w["W"], w["f"], dev)
     g_big = gather(256, 256, w["C"], w["H"], w["W"], w["f"], dev, reps=50)  # 65536 windows: saturating
     tr_big = transition(1 << 24, w["H"], w["W"], w["f"], dev, reps=20)
     n_img = max(1, (1 << 28) // (w["C"] * w["H"] * w["W"]))  # 268 M elements: 1.3 GB moved, far beyond L2
     tt_big = to_tensor_u8(n_img, w["C"], w["H"], w["W"], dev, reps=20)
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    traffic, ncu_lstm = None, None
+    tpath = os.path.join(ROOT, "profiles", "r2", "ncu_lstm_pair_m4096.json")
     if os.path.exists(tpath):
         with open(tpath) as fh:
-            traffic = json.load(fh).get("lstm_pair_dram_bytes_per_launch")
-    return {
-        "bound": "tensor", "kernel": lstm["kernel"], "achieved": lstm["tflops"], "peak": tf32_peak, "unit": "TFLOP/s",
-        "frac": lstm["tflops"] / tf32_peak, "traffic": traffic,
+            cap = json.load(fh)["captures"]
+        best = cap.get("tile 128x256 (HU=64, default from M>=2368)", {})
+        try:
+            traffic = (float(best["dram__bytes_read.sum"][0]) + float(best["dram__bytes_write.sum"][0])) * 1e6
+            ncu_lstm = {"tensor_pipe_active_pct": float(best["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"][0]),
+                        "tensor_pipe_active_pct_of_elapsed": float(best["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"][0]),
+                        "l2_to_sm_read_mbytes": float(best["l1tex__m_xbar2l1tex_read_bytes.sum"][0]),
+                        "source": "profiles/r2/ncu_lstm_pair_m4096.json (ncu --set full, one launch at M=4096)"}
+        except Exception:
+            pass
+    ffma_peak = MARLC_SMS * 128 * 2 * float(pk.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12
+
+    def tensor_entry(r, name, extra=None):
+        e = {"kernel": name, "bound": "tensor", "achieved": r["tflops"], "peak": tf32_peak, "unit": "TFLOP/s",
+             "frac": r["tflops"] / tf32_peak, "frac_of_half_bf16_peak": r["tflops"] / half_bf16,
+             "launch_us": r["us_per_launch"], "flops_per_launch": r["flops_per_launch"], "shape": r["shape"]}
+        if extra:
+            e.update(extra)
+        return e
+
+    lstm_e = tensor_entry(lstm, lstm["kernel"] + f" @ M={M}", {"ncu": ncu_lstm} if (ncu_lstm and M == 4096) else None)
+    dw_e = tensor_entry(dw, dw["kernel"] + f" @ R=T*M={TM}")
+    big = M >= 1024  # sharded-batch configurations: the weight gradients lead the launch list; else the LSTM pair
+    main = dict(dw_e if big else lstm_e)
+    main.update({
+        "traffic": None if big else traffic,
         "peak_source": "cuBLAS TF32 8192^3 measured in this run (MEASURED_PEAKS.json holds bf16 only: "
-                       f"{pk.get('bf16_tflops')} TFLOP/s burst, {src})",
-        "launch_us": lstm["us_per_launch"], "flops_per_launch": lstm["flops_per_launch"],
-        "precision": "tf32x3 (3 MMAs per K step; achieved counts ALGORITHMIC flops once)" if x3 else "tf32",
-        "note": f"M={M} rows per launch: one 128-row MMA tile, latency-bound (SURVEY 7.3-2); "
-                "the same kernel at M=4096 is listed under 'others'",
+                       f"{pk.get('bf16_tflops')} TFLOP/s burst, {src}; frac_of_half_bf16_peak uses half of it)",
+        "precision": prec,
+        "time_share": ("largest single-kernel share of the iteration in the ncu launch list of this workload "
+                       "(profiles/r2/launches_c4_nb256_summary.txt)" if big else
+                       "largest tensor-kernel share at the batch-8 configurations (profiles/launches_r1_c2_summary.txt)"),
         "others": [
-            {"kernel": lstm_big["kernel"] + " @ M=4096 (config c4 per-GPU rows)", "bound": "tensor",
-             "achieved": lstm_big["tflops"], "peak": tf32_peak, "unit": "TFLOP/s", "frac": lstm_big["tflops"] / tf32_peak,
-             "launch_us": lstm_big["us_per_launch"]},
+            lstm_e if big else dw_e,
+            {"kernel": pre["kernel"] + " (gather + CNN | decoder + position features)", "bound": "fp32-ffma",
+             "achieved": pre["tflops"], "peak": ffma_peak, "unit": "TFLOP/s", "frac": pre["tflops"] / ffma_peak,
+             "launch_us": pre["us_per_launch"], "flops_per_launch": pre["flops_per_launch"], "shape": pre["shape"],
+             "peak_source": "CUDA-core fp32: 148 SMs x 128 lanes x 2 flop x sm_max_mhz (no measured figure in MEASURED_PEAKS.json)"},
             {"kernel": "patch_gather_kernel @ workload", "bound": "hbm", "achieved": g_small["gbs"],
              "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": g_small["gbs"] / pk["hbm_gbs"],
              "launch_us": g_small["us_per_launch"], "bytes_per_launch": g_small["bytes_per_launch"]},
@@ -218,7 +302,8 @@ def roofline_for(model, w: dict, nb: int, dev) -> dict:
              "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": tt_big["gbs"] / pk["hbm_gbs"],
              "launch_us": tt_big["us_per_launch"], "bytes_per_launch": tt_big["bytes_per_launch"]},
         ],
-    }
+    })
+    return main
 
 
 if __name__ == "__main__":

@@ -421,13 +421,18 @@ int step_pre(const StepPreArgs& a, cudaStream_t s) {
     static_assert(CW_THREADS == CT, "the wide feature extractor runs inside the chain kernel's CTA shape");
     StepPreWideArgs ka;
     memset(&ka.wide, 0, sizeof(ka.wide));
-    if (a.M >= wide_min) ka.wide = cnn_wide_plan(a.cnn.d, a.cnn.img != nullptr && a.cnn.patch == nullptr);
+    // 8 windows per pass; 4 (MARLC_CNN_WIDE_NW=4: twice the CTAs while 8 leave SMs idle) measured slower at
+    // 512 and 1024 windows (476 vs 438 us, 795 vs 745 us per 16 steps): a pass is bound by the latency of its
+    // phases, not by its FMA count
+    static const int nw_env = getenv("MARLC_CNN_WIDE_NW") ? atoi(getenv("MARLC_CNN_WIDE_NW")) : 0;
+    const int nw = nw_env ? nw_env : CW_NW;
+    if (a.M >= wide_min) ka.wide = cnn_wide_plan(a.cnn.d, a.cnn.img != nullptr && a.cnn.patch == nullptr, nw);
     if (!ka.wide.ok) return step_pre_small(a, s);
     ka.a = a;
     ka.maxw = maxw_of({a.d0.n_in, a.d0.n_out, a.d3.n_out, a.pos.n_out});
     const int wfl = staged_floats(ka.maxw, a.d0.n_out, odd_pitch(a.d0.n_in), a.d3.n_out, odd_pitch(a.d3.n_in));
     ka.staged = wfl > 0;
-    ka.cnn_blocks = min((a.M + CW_NW - 1) / CW_NW, MARLC_SMS);
+    ka.cnn_blocks = min((a.M + nw - 1) / nw, MARLC_SMS);
     const size_t smem = max(chain_smem_bytes(ka.maxw) + sizeof(float) * (size_t)wfl, sizeof(float) * (size_t)ka.wide.smem_floats);
     MARLC_CHECK(smem <= 226 * 1024, "step_pre: shared memory %zu B too large", smem);
     static size_t attr = 0;

@@ -24,13 +24,14 @@
 
 namespace marlc {
 
-constexpr int CW_NW = 8;        // windows per pass
+constexpr int CW_NW = 8;        // windows per pass (template parameter NW: 8; 4 exists for A/B runs, slower)
 constexpr int CW_THREADS = 256;  // = the chain kernels' CTA (step_pre hosts this role); 512 threads as a separate launch
                                  // measured no faster per batch and cost a fork / join per step
 constexpr int CW_MAX_KS = 8;
 
 struct CnnWidePlan {
     int ok;                          // 0: shapes not supported (caller uses the per-window block)
+    int nw;                          // windows per pass: 8 or 4
     int w_off[MAX_CNN_LAYERS];       // floats: transposed weights of layer l
     int p_off[MAX_CNN_LAYERS];       // bias | gamma | beta (3 * cout)
     int in_off[MAX_CNN_LAYERS];      // zero-bordered input of layer l: [cin][hin+2][hin+2][NW]
@@ -40,10 +41,11 @@ struct CnnWidePlan {
     int smem_floats;
 };
 
-inline CnnWidePlan cnn_wide_plan(const CnnDesc& d, bool have_img) {
+inline CnnWidePlan cnn_wide_plan(const CnnDesc& d, bool have_img, int nw = CW_NW) {
     CnnWidePlan p;
     memset(&p, 0, sizeof(p));
-    if (!have_img || !d.wT[0]) return p;
+    p.nw = nw;
+    if (!have_img || !d.wT[0] || (nw != 8 && nw != 4)) return p;
     int off = 0;
     for (int l = 0; l < d.L; ++l) {
         if (!d.wT[l] || (d.cout[l] & 3) || d.groups[l] > 32 || d.cout[l] % d.groups[l]) return p;
@@ -54,16 +56,16 @@ inline CnnWidePlan cnn_wide_plan(const CnnDesc& d, bool have_img) {
     off = (off + 3) & ~3;
     for (int l = 0; l < d.L; ++l) {
         p.in_off[l] = off;
-        off += d.cin[l] * (d.hin[l] + 2) * (d.hin[l] + 2) * CW_NW;
+        off += d.cin[l] * (d.hin[l] + 2) * (d.hin[l] + 2) * nw;
     }
     // input-channel slices: as many as there are idle threads, within what is left of shared memory for the
     // partial planes (224 KB budget: one CTA per SM owns practically all of its shared memory)
-    const int st_floats = (2 * 32 + CW_THREADS / 32) * CW_NW;
+    const int st_floats = (2 * 32 + CW_THREADS / 32) * nw;
     const int ybudget = 224 * 256 - off - st_floats;
     int ymax = 0;
     for (int l = 0; l < d.L; ++l) {
         const int items = d.hout[l] * d.hout[l] * (d.cout[l] >> 2);
-        const int plane = d.cout[l] * d.hout[l] * d.hout[l] * CW_NW;
+        const int plane = d.cout[l] * d.hout[l] * d.hout[l] * nw;
         if (plane > ybudget) return p;
         int ks = 1;
         while (ks < CW_MAX_KS && items * (ks + 1) <= CW_THREADS && ks + 1 <= d.cin[l] && (ks + 1) * plane <= ybudget) ++ks;
@@ -89,18 +91,20 @@ __device__ __forceinline__ int cw_div(int n, float rcp) { return __float2int_rz(
 // cw_load_windows one phase earlier), the f copies of a row need no index arithmetic.  (First version: one
 // element per thread iteration with three divisions, a modulo and two dependent global loads of the
 // position each -- 4.8 M warp instructions per launch at 4096 windows and ~5000 exposed cycles per batch.)
+template <int NW>
 __device__ __forceinline__ void cw_load_windows(const CnnFwdArgs& a, int* win, int batch) {
-    const int m = batch * CW_NW + (int)threadIdx.x;
-    if (threadIdx.x < CW_NW && m < a.M) {
+    const int m = batch * NW + (int)threadIdx.x;
+    if (threadIdx.x < NW && m < a.M) {
         win[threadIdx.x * 4 + 0] = a.pos[2 * m];
         win[threadIdx.x * 4 + 1] = a.pos[2 * m + 1];
         win[threadIdx.x * 4 + 2] = m % a.B;
     }
 }
+template <int NW>
 __device__ __forceinline__ void cw_issue_gather(const CnnFwdArgs& a, float* in0, const int* win, int batch) {
     const CnnDesc& d = a.d;
     const int f = d.f, c0 = d.cin[0], hp = f + 2;
-    const int nvalid = min(CW_NW, a.M - batch * CW_NW);
+    const int nvalid = min(NW, a.M - batch * NW);
     const int rows_per = c0 * f;
     const float r_per = 1.0f / (float)rows_per, r_f = 1.0f / (float)f;
     const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(in0);
@@ -108,19 +112,20 @@ __device__ __forceinline__ void cw_issue_gather(const CnnFwdArgs& a, float* in0,
         const int w = cw_div(r, r_per), q = r - w * rows_per, c = cw_div(q, r_f), i = q - c * f;
         const int py = win[w * 4], px = win[w * 4 + 1], b = win[w * 4 + 2];
         const float* src = a.img + ((long)(b * d.img_c + c) * a.H + py + i) * a.W + px;
-        uint32_t dst = dst0 + 4u * (uint32_t)(((c * hp + i + 1) * hp + 1) * CW_NW + w);
-        for (int j = 0; j < f; ++j, dst += 4u * CW_NW)
+        uint32_t dst = dst0 + 4u * (uint32_t)(((c * hp + i + 1) * hp + 1) * NW + w);
+        for (int j = 0; j < f; ++j, dst += 4u * NW)
             asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src + j) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
 // CTA `cta` of `n_cta` cooperating CTAs; all CW_THREADS threads must call.
-__device__ __forceinline__ void cnn_fwd_wide(const CnnFwdArgs& a, const CnnWidePlan& pl, const int cta, const int n_cta,
-                                             float* sm) {
+template <int NW>
+__device__ __forceinline__ void cnn_fwd_wide_t(const CnnFwdArgs& a, const CnnWidePlan& pl, const int cta, const int n_cta,
+                                               float* sm) {
     const CnnDesc& d = a.d;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nbatch = (a.M + CW_NW - 1) / CW_NW;
+    const int nbatch = (a.M + NW - 1) / NW;
     if (cta >= nbatch) return;
 #ifdef MARLC_CNN_TRACE  // timeline of CTA 0 (cycles since entry): setup, then per batch / layer: conv, pass A, B, C
     __shared__ long long cw_tr[48];
@@ -131,12 +136,12 @@ __device__ __forceinline__ void cnn_fwd_wide(const CnnFwdArgs& a, const CnnWideP
 #define CW_TRACE() do { } while (0)
 #endif
     // ---- once per CTA: zero the activation buffers (their borders stay zero), stage weights + affines
-    __shared__ __align__(8) uint64_t wbar;
-    __shared__ int s_win[2][CW_NW * 4];  // {py, px, image} of the current / next batch's windows
-    cw_load_windows(a, s_win[0], cta);
-    const uint32_t wbar_a = (uint32_t)__cvta_generic_to_shared(&wbar);
+    __shared__ __align__(8) uint64_t wbar[MAX_CNN_LAYERS];  // one per layer: layer 0 (1.7 KB at RESISC45) must not wait for layer 2 (73 KB)
+    __shared__ int s_win[2][NW * 4];  // {py, px, image} of the current / next batch's windows
+    cw_load_windows<NW>(a, s_win[0], cta);
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(wbar_a));
+        for (int l = 0; l < d.L; ++l)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&wbar[l])));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     {
@@ -145,16 +150,16 @@ __device__ __forceinline__ void cnn_fwd_wide(const CnnFwdArgs& a, const CnnWideP
         for (int i = tid; i < n4; i += CW_THREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncthreads();  // the gather below writes into the zeroed buffer
-    cw_issue_gather(a, sm + pl.in_off[0], s_win[0], cta);
+    cw_issue_gather<NW>(a, sm + pl.in_off[0], s_win[0], cta);
     // weights: ONE bulk copy per layer (the copy engine moves them while the threads go on), completion on wbar
     if (tid == 0) {
-        uint32_t bytes = 0;
-        for (int l = 0; l < d.L; ++l) bytes += (uint32_t)(d.cout[l] * d.cin[l] * 9 * 4);
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(wbar_a), "r"(bytes) : "memory");
-        for (int l = 0; l < d.L; ++l)
+        for (int l = 0; l < d.L; ++l) {
+            const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&wbar[l]);
+            const uint32_t bytes = (uint32_t)(d.cout[l] * d.cin[l] * 9 * 4);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                             (uint32_t)__cvta_generic_to_shared(sm + pl.w_off[l])), "l"(d.wT[l]),
-                         "r"((uint32_t)(d.cout[l] * d.cin[l] * 9 * 4)), "r"(wbar_a) : "memory");
+                             (uint32_t)__cvta_generic_to_shared(sm + pl.w_off[l])), "l"(d.wT[l]), "r"(bytes), "r"(bar) : "memory");
+        }
     }
     for (int l = 0; l < d.L; ++l) {
         float* pp = sm + pl.p_off[l];
@@ -167,21 +172,14 @@ __device__ __forceinline__ void cnn_fwd_wide(const CnnFwdArgs& a, const CnnWideP
     CW_TRACE();  // 0: zeroed, gather + weight staging issued
     float* ybuf = sm + pl.y_off;
     float* s_mean = sm + pl.st_off;
-    float* s_rstd = s_mean + 32 * CW_NW;
-    float* s_red = s_rstd + 32 * CW_NW;
+    float* s_rstd = s_mean + 32 * NW;
+    float* s_red = s_rstd + 32 * NW;
 
     int wbuf = 0;
     for (int batch = cta; batch < nbatch; batch += n_cta, wbuf ^= 1) {
-        const int m0 = batch * CW_NW, nvalid = min(CW_NW, a.M - m0);
-        if (batch + n_cta < nbatch) cw_load_windows(a, s_win[wbuf ^ 1], batch + n_cta);  // visible after layer 0's barrier
+        const int m0 = batch * NW, nvalid = min(NW, a.M - m0);
+        if (batch + n_cta < nbatch) cw_load_windows<NW>(a, s_win[wbuf ^ 1], batch + n_cta);  // visible after layer 0's barrier
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-        if (batch == cta) {  // first batch: the weights must have landed
-            uint32_t done;
-            do {
-                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                             : "=r"(done) : "r"(wbar_a) : "memory");
-            } while (!done);
-        }
         __syncthreads();  // windows of this batch (and, first time, the affines) are in shared memory
         CW_TRACE();  // batch start: inputs ready
         for (int l = 0; l < d.L; ++l) {
@@ -193,6 +191,14 @@ __device__ __forceinline__ void cnn_fwd_wide(const CnnFwdArgs& a, const CnnWideP
             const float* wl = sm + pl.w_off[l];
             const float* prm = sm + pl.p_off[l];
             const int ks = pl.ks[l], cpk = (ci_n + ks - 1) / ks, items = npos * ncg;
+            if (batch == cta) {  // first batch: this layer's weights must have landed
+                const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&wbar[l]);
+                uint32_t done;
+                do {
+                    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                                 : "=r"(done) : "r"(bar) : "memory");
+                } while (!done);
+            }
             // ---- convolution: work item = (input-channel slice, output position, group of 4 output channels)
             {
                 const float r_items = 1.0f / (float)items, r_ncg = 1.0f / (float)ncg, r_ho = 1.0f / (float)ho;
@@ -201,43 +207,47 @@ __device__ __forceinline__ void cnn_fwd_wide(const CnnFwdArgs& a, const CnnWideP
                     const int pos = cw_div(item, r_ncg), c4 = (item - pos * ncg) << 2;
                     const int oy = cw_div(pos, r_ho), ox = pos - oy * ho;
                     const int ci0 = kslice * cpk, ci1 = min(ci_n, ci0 + cpk);
-                    float acc[4][CW_NW];
+                    float acc[4][NW];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const float bj = kslice == 0 ? prm[c4 + j] : 0.f;
 #pragma unroll
-                        for (int w = 0; w < CW_NW; ++w) acc[j][w] = bj;
+                        for (int w = 0; w < NW; ++w) acc[j][w] = bj;
                     }
-                    const float* x = in + ((ci0 * hp + 2 * oy) * hp + 2 * ox) * CW_NW;
+                    const float* x = in + ((ci0 * hp + 2 * oy) * hp + 2 * ox) * NW;
                     const float* wq = wl + (ci0 * 9) * co_n + c4;
-                    for (int ci = ci0; ci < ci1; ++ci, x += hp * hp * CW_NW, wq += 9 * co_n) {
+                    for (int ci = ci0; ci < ci1; ++ci, x += hp * hp * NW, wq += 9 * co_n) {
 #pragma unroll
                         for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
                             for (int kx = 0; kx < 3; ++kx) {
-                                const float4 x0 = *reinterpret_cast<const float4*>(x + (ky * hp + kx) * CW_NW);
-                                const float4 x1 = *reinterpret_cast<const float4*>(x + (ky * hp + kx) * CW_NW + 4);
+                                float xv[NW];
+#pragma unroll
+                                for (int h4 = 0; h4 < NW / 4; ++h4) {
+                                    const float4 xq = *reinterpret_cast<const float4*>(x + (ky * hp + kx) * NW + 4 * h4);
+                                    xv[4 * h4] = xq.x; xv[4 * h4 + 1] = xq.y; xv[4 * h4 + 2] = xq.z; xv[4 * h4 + 3] = xq.w;
+                                }
                                 const float4 w4 = *reinterpret_cast<const float4*>(wq + (ky * 3 + kx) * co_n);
-                                const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
                                 const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
                                 for (int j = 0; j < 4; ++j)
 #pragma unroll
-                                    for (int w = 0; w < CW_NW; ++w) acc[j][w] = fmaf(wv[j], xv[w], acc[j][w]);
+                                    for (int w = 0; w < NW; ++w) acc[j][w] = fmaf(wv[j], xv[w], acc[j][w]);
                             }
                     }
-                    float* y = ybuf + (kslice * total + c4 * npos + pos) * CW_NW;
+                    float* y = ybuf + (kslice * total + c4 * npos + pos) * NW;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        *reinterpret_cast<float4*>(y + j * npos * CW_NW) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
-                        *reinterpret_cast<float4*>(y + j * npos * CW_NW + 4) = make_float4(acc[j][4], acc[j][5], acc[j][6], acc[j][7]);
-                    }
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int h4 = 0; h4 < NW / 4; ++h4)
+                            *reinterpret_cast<float4*>(y + j * npos * NW + 4 * h4) =
+                                make_float4(acc[j][4 * h4], acc[j][4 * h4 + 1], acc[j][4 * h4 + 2], acc[j][4 * h4 + 3]);
                 }
             }
             __syncthreads();
             CW_TRACE();  // conv done
             if (l == 0 && batch + n_cta < nbatch)  // layer 0's input buffer is free: prefetch the next batch's windows
-                cw_issue_gather(a, sm + pl.in_off[0], s_win[wbuf ^ 1], batch + n_cta);
+                cw_issue_gather<NW>(a, sm + pl.in_off[0], s_win[wbuf ^ 1], batch + n_cta);
             // ---- GroupNorm + SiLU.  Warps are bound to groups (nwarps / G warps share a group when G < nwarps,
             //      their partial sums meet in shared memory); lane = (4 elements) x (8 windows): conflict-free
             //      shared accesses, 16-byte rows per window in global memory.  Two-pass statistics as the
@@ -253,11 +263,12 @@ __device__ __forceinline__ void cnn_fwd_wide(const CnnFwdArgs& a, const CnnWideP
 #endif
                 const float* gam = prm + co_n;
                 const float* bet = prm + 2 * co_n;
-                const int w = lane & 7, es = lane >> 3;
+                constexpr int EPL = 32 / NW;  // elements a warp covers per step: lane = (EPL elements) x (NW windows)
+                const int w = lane & (NW - 1), es = lane / NW;
                 constexpr int nwarps = CW_THREADS / 32;
                 const bool shared_groups = G < nwarps && nwarps % G == 0;
                 const int wpg = shared_groups ? nwarps / G : 1;
-                const int estep = 4 * wpg;
+                const int estep = EPL * wpg;
                 const float inv = 1.0f / (float)ng, r_npos = 1.0f / (float)npos, r_ho = 1.0f / (float)ho;
                 float* nxt = last ? nullptr : sm + pl.in_off[l + 1];
                 const int hop = ho + 2;
@@ -265,9 +276,9 @@ __device__ __forceinline__ void cnn_fwd_wide(const CnnFwdArgs& a, const CnnWideP
                 for (int g0 = 0; g0 < G; g0 += (shared_groups ? G : nwarps)) {
                     const int g = shared_groups ? warp / wpg : g0 + warp;
                     const int sub = shared_groups ? warp % wpg : 0;
-                    const int el0 = sub * 4 + es;
+                    const int el0 = sub * EPL + es;
                     const int n_el = (g < G) ? ng : 0;  // inactive warps run empty loops (they still meet the barriers)
-                    float* yg = ybuf + (g < G ? g : 0) * ng * CW_NW + w;
+                    float* yg = ybuf + (g < G ? g : 0) * ng * NW + w;
                     float* ys = ysave ? ysave + (long)(m0 + w) * total + g * ng : nullptr;
                     // pass 1: sum the input-channel slices (kept in plane 0), save for backward, accumulate the sum
                     float s = 0.f;
@@ -277,31 +288,31 @@ __device__ __forceinline__ void cnn_fwd_wide(const CnnFwdArgs& a, const CnnWideP
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             const int e = el + u * estep;
-                            x[u] = e < n_el ? yg[e * CW_NW] : 0.f;
+                            x[u] = e < n_el ? yg[e * NW] : 0.f;
                         }
                         for (int p = 1; p < ks; ++p)
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
                                 const int e = el + u * estep;
-                                if (e < n_el) x[u] += yg[(p * total + e) * CW_NW];
+                                if (e < n_el) x[u] += yg[(p * total + e) * NW];
                             }
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             const int e = el + u * estep;
                             if (e < n_el) {
-                                if (ks > 1) yg[e * CW_NW] = x[u];
+                                if (ks > 1) yg[e * NW] = x[u];
                                 if (ys && wok) ys[e] = x[u];
                             }
                             s += x[u];
                         }
                     }
-                    s += __shfl_xor_sync(0xffffffffu, s, 8);
-                    s += __shfl_xor_sync(0xffffffffu, s, 16);
+#pragma unroll
+                    for (int o = NW; o < 32; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
                     if (shared_groups) {
-                        if (es == 0) s_red[warp * CW_NW + w] = s;
+                        if (es == 0) s_red[warp * NW + w] = s;
                         __syncthreads();
                         s = 0.f;
-                        for (int i = 0; i < wpg; ++i) s += s_red[(g * wpg + i) * CW_NW + w];
+                        for (int i = 0; i < wpg; ++i) s += s_red[(g * wpg + i) * NW + w];
                         __syncthreads();
                     }
                     const float mean = s * inv;
@@ -312,17 +323,17 @@ __device__ __forceinline__ void cnn_fwd_wide(const CnnFwdArgs& a, const CnnWideP
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             const int e = el + u * estep;
-                            const float dd = e < n_el ? yg[e * CW_NW] - mean : 0.f;
+                            const float dd = e < n_el ? yg[e * NW] - mean : 0.f;
                             q = fmaf(dd, dd, q);
                         }
                     }
-                    q += __shfl_xor_sync(0xffffffffu, q, 8);
-                    q += __shfl_xor_sync(0xffffffffu, q, 16);
+#pragma unroll
+                    for (int o = NW; o < 32; o <<= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
                     if (shared_groups) {
-                        if (es == 0) s_red[warp * CW_NW + w] = q;
+                        if (es == 0) s_red[warp * NW + w] = q;
                         __syncthreads();
                         q = 0.f;
-                        for (int i = 0; i < wpg; ++i) q += s_red[(g * wpg + i) * CW_NW + w];
+                        for (int i = 0; i < wpg; ++i) q += s_red[(g * wpg + i) * NW + w];
                         __syncthreads();
                     }
                     const float rstd = 1.0f / sqrtf(q * inv + GN_EPS);
@@ -333,7 +344,7 @@ __device__ __forceinline__ void cnn_fwd_wide(const CnnFwdArgs& a, const CnnWideP
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             const int e = el + u * estep;
-                            x[u] = e < n_el ? yg[e * CW_NW] : 0.f;
+                            x[u] = e < n_el ? yg[e * NW] : 0.f;
                         }
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
@@ -344,7 +355,7 @@ __device__ __forceinline__ void cnn_fwd_wide(const CnnFwdArgs& a, const CnnWideP
                                 const float o = __fdividef(z, 1.0f + __expf(-z));  // SiLU
                                 if (!last) {
                                     const int oy = cw_div(pos, r_ho), ox = pos - oy * ho;
-                                    nxt[((c * hop + oy + 1) * hop + ox + 1) * CW_NW + w] = o;
+                                    nxt[((c * hop + oy + 1) * hop + ox + 1) * NW + w] = o;
                                 } else if (wok) {
                                     a.out[(long)(m0 + w) * a.ldo + e] = o;
                                     if (a.out_lo) a.out_lo[(long)(m0 + w) * a.ldo + e] = tf32_lo(o);
@@ -366,6 +377,13 @@ __device__ __forceinline__ void cnn_fwd_wide(const CnnFwdArgs& a, const CnnWideP
         printf(" | end %lld\n", clock64() - cw_t0);
     }
 #endif
+}
+
+// All CW_THREADS threads of CTA `cta` (of `n_cta` cooperating CTAs) must call.
+__device__ __forceinline__ void cnn_fwd_wide(const CnnFwdArgs& a, const CnnWidePlan& pl, const int cta, const int n_cta,
+                                             float* sm) {
+    if (pl.nw == 4) cnn_fwd_wide_t<4>(a, pl, cta, n_cta, sm);
+    else cnn_fwd_wide_t<8>(a, pl, cta, n_cta, sm);
 }
 
 }  // namespace marlc
