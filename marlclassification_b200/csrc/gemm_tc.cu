@@ -330,6 +330,11 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
     if (threadIdx.x == 0) TC_TRACE(0);  // setup done (barriers, TMEM)
+    // K split over a CTA pair: the odd CTA will write into the even CTA's shared memory (DSMEM).  A CTA of a
+    // cluster may only be written once it has STARTED executing: every thread arrives on the cluster barrier now
+    // (non-blocking) and waits for this phase right before the first remote store / before the final barrier
+    // (compute-sanitizer racecheck: "block that might not have entered yet", round 2).
+    if (ksp > 1) asm volatile("barrier.cluster.arrive.release;" ::: "memory");
 
     if (warp == 0) {
         // ============================ TMA producer ============================
@@ -640,6 +645,7 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
             // memory (distributed shared memory), one cluster barrier, the even CTA adds them.
             constexpr int PPITCH = BN + 4;
             float* part = reinterpret_cast<float*>(smem + (S::BYTES - 1024));  // [BM][PPITCH], after the ring
+            if (ksp > 1) asm volatile("barrier.cluster.wait.acquire;" ::: "memory");  // the partner CTA has entered
             if (ksp > 1 && kslice != 0) {
                 uint32_t remote;
                 asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(part)), "r"(0));
@@ -724,7 +730,8 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
         }
         }  // warp < 6
     }
-    if (ksp > 1 && !(warp >= 2 && warp < 6)) {  // every thread of the pair takes part in the cluster barrier
+    if (ksp > 1 && !(warp >= 2 && warp < 6)) {  // every thread of the pair takes part in the cluster barriers
+        asm volatile("barrier.cluster.wait.acquire;" ::: "memory");  // phase 1 ("entered"), see above
         asm volatile("barrier.cluster.arrive.release;" ::: "memory");
         asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
     }
