@@ -1122,7 +1122,13 @@ extern "C" int marlc_episode_backward(marlc_engine* e, const float* img, int acc
     MARLC_CUDA(cudaMemsetAsync(dc[0], 0, sizeof(float) * (size_t)M * c.n_b, s));
     MARLC_CUDA(cudaMemsetAsync(dcc[0], 0, sizeof(float) * (size_t)M * c.n_a, s));
     int cur = 0;
-    if (c.use_chains) {
+    // Fused chain kernels for the sweep while a step has fewer than 4096 rows (latency-bound: 3 launches per step).
+    // From 4096 rows per step on (config 4 on ONE GPU) the one-kernel-per-op sweep with its products on the
+    // tensor cores wins: the chains run 4 rows per CTA, one CTA per SM.  Measured (sweep of 16 steps): 4096 rows
+    // 2.72 vs 3.01 ms, 2048 rows 2.91 vs 2.48 ms -- hence the threshold (MARLC_SWEEP_UNFUSED_MIN_M).
+    static const int unfused_min_m = getenv("MARLC_SWEEP_UNFUSED_MIN_M") ? atoi(getenv("MARLC_SWEEP_UNFUSED_MIN_M")) : 4096;
+    const bool chain_sweep = c.use_chains && M < unfused_min_m;
+    if (chain_sweep) {
         float* dcoll = e->buf("dcoll");
         float* dh_hist = e->buf("dh_hist");
         float* dhc_hist = e->buf("dhc_hist");
@@ -1348,6 +1354,11 @@ extern "C" int marlc_episode_backward(marlc_engine* e, const float* img, int acc
         return 0;
     }
     if (!par) MARLC_TRY(batched(0, T, s, s, s));
+    if (par && !chain_sweep) {  // unfused sweep, batched gradients on the three streams as in the chain path
+        MARLC_TRY(e->chain(s, e->side[0]));
+        MARLC_TRY(e->chain(s, e->side[1]));
+        MARLC_TRY(batched(0, T, s, e->side[1], e->side[0]));
+    }
     if (par) MARLC_TRY(join_sides());
     e->last_launches = g_launch_count - start;
     return 0;
