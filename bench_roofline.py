@@ -226,10 +226,10 @@ def step_pre_wide(model, w: dict, nb: int, dev, reps: int = 20) -> dict:
 
 
 def roofline_for(model, w: dict, nb: int, dev) -> dict:
-    """The `roofline` object of bench.py's JSON line.  Main entry = the kernel with the LARGEST TIME SHARE of the
-    iteration among the kernels a roofline bounds (profiles/r2/launches_*.txt: the weight-gradient GEMM at
-    config c4; the fused LSTM pair at the batch-8 configurations), measured live here; `others` holds the rest of
-    the top of the launch list and the saturating micro-benchmarks of the HBM-bound kernels."""
+    """The `roofline` object of bench.py's JSON line.  Main entry = the tensor-bound kernel with the largest time
+    share of the iteration (profiles/r2/launches_*_summary.txt): the fused LSTM pair at the workload's row count,
+    measured live here; `others` holds the rest of the top of the launch list (weight-gradient GEMM, the fp32-FFMA
+    `pre` launch) and the saturating micro-benchmarks of the HBM-bound kernels."""
     pk, src = peaks()
     d = model.dims
     M = w["na"] * nb
@@ -273,18 +273,20 @@ def roofline_for(model, w: dict, nb: int, dev) -> dict:
 
     lstm_e = tensor_entry(lstm, lstm["kernel"] + f" @ M={M}", {"ncu": ncu_lstm} if (ncu_lstm and M == 4096) else None)
     dw_e = tensor_entry(dw, dw["kernel"] + f" @ R=T*M={TM}")
-    big = M >= 1024  # sharded-batch configurations: the weight gradients lead the launch list; else the LSTM pair
-    main = dict(dw_e if big else lstm_e)
+    big = M >= 1024
+    main = dict(lstm_e)
     main.update({
-        "traffic": None if big else traffic,
+        "traffic": traffic if M == 4096 else None,
         "peak_source": "cuBLAS TF32 8192^3 measured in this run (MEASURED_PEAKS.json holds bf16 only: "
                        f"{pk.get('bf16_tflops')} TFLOP/s burst, {src}; frac_of_half_bf16_peak uses half of it)",
         "precision": prec,
-        "time_share": ("largest single-kernel share of the iteration in the ncu launch list of this workload "
-                       "(profiles/r2/launches_c4_nb256_summary.txt)" if big else
-                       "largest tensor-kernel share at the batch-8 configurations (profiles/launches_r1_c2_summary.txt)"),
+        "time_share": ("largest share of the iteration among the tensor-bound kernels in the ncu launch list of this "
+                       "workload (profiles/r2/launches_c4_nb256_summary.txt: LSTM pair 11 %, input-gradient GEMMs 11 %, "
+                       "weight-gradient GEMMs 10.5 %); the largest share overall is step_pre_wide_kernel (20 %, fp32 FFMA: "
+                       "listed under others against the CUDA-core peak)" if big else
+                       "largest tensor-kernel share at the batch-8 configurations (profiles/r2/launches_c2_summary.txt)"),
         "others": [
-            lstm_e if big else dw_e,
+            dw_e,
             {"kernel": pre["kernel"] + " (gather + CNN | decoder + position features)", "bound": "fp32-ffma",
              "achieved": pre["tflops"], "peak": ffma_peak, "unit": "TFLOP/s", "frac": pre["tflops"] / ffma_peak,
              "launch_us": pre["us_per_launch"], "flops_per_launch": pre["flops_per_launch"], "shape": pre["shape"],
