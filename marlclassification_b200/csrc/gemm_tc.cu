@@ -974,7 +974,10 @@ int tc_lstm_pair(const TcLstmArgs& c0, const TcLstmArgs& c1, cudaStream_t s) {
     // SM, before the TMA writes and the 3xTF32 low-order tiles), 96 B/clk for 128 x 256 -- and the tile streams
     // 25 % fewer operand bytes per flop (MARLC_LSTM_HU64=0 switches it off)
     static const int hu64 = getenv("MARLC_LSTM_HU64") ? atoi(getenv("MARLC_LSTM_HU64")) : 1;
-    if (hu64 && c0.n % 64 == 0 && c1.n % 64 == 0 && 2 * mt * (c0.n / 64) >= MARLC_SMS) HU = 64;
+    // (measured, 16 steps at n = 256: M = 2048 -> 796 us with 64 units per tile vs 858 with 32; M = 1024 -> 673 vs 439)
+    if (hu64 && c0.n % 64 == 0 && c1.n % 64 == 0 && 2 * mt * (c0.n / 64) >= 120) HU = 64;
+    static const int hu_force = getenv("MARLC_LSTM_HU") ? atoi(getenv("MARLC_LSTM_HU")) : 0;  // A/B toggle
+    if (hu_force == 8 || hu_force == 16 || hu_force == 32 || hu_force == 64) HU = hu_force;
     while (HU > 8 && (c0.n % HU != 0 || c1.n % HU != 0)) HU >>= 1;
     MARLC_CHECK(c0.n % HU == 0 && c1.n % HU == 0, "tc_lstm_pair: hidden size not a multiple of %d", HU);
     TcKernelGroup kp;
