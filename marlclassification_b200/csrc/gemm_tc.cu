@@ -772,7 +772,7 @@ template <int BN, bool A_MN, bool B_MN, bool X3, int KS>
 static int launch_store(TcKernelGroup& kp, int gx, int gy, int gz, int max_kb, cudaStream_t s) {
     (void)max_kb;
     // KS == 1: <= 96 KB per CTA, two CTAs per SM (epilogue / main loop overlap); fat stages: 2-deep ring
-    constexpr int STAGES = KS > 1 ? 2 : (BN >= 128 ? 3 : 4);
+    constexpr int STAGES = BN >= 256 ? (X3 ? 2 : 4) : (KS > 1 ? 2 : (BN >= 128 ? 3 : 4));
     using S = TcSmem<BN, STAGES, X3, KS>;
     static_assert(S::BYTES <= 227 * 1024, "tile configuration exceeds shared memory");
     auto kern = tc_gemm_kernel<BN, A_MN, B_MN, EPI_STORE, STAGES, X3, KS>;
@@ -807,6 +807,21 @@ static int pick_bn(const TcGemmArgs* args, int count) {
     if (max_n <= 64 || ctas128 < MARLC_SMS / 2 || bn_cap < 128) return 64;
     if (!dw128 && args[0].A.mn_major && args[0].B.mn_major) return 64;
     if (!dx128 && !args[0].A.mn_major && args[0].B.mn_major && count > 1) return 64;
+    // Weight gradients (MN-major x MN-major, reductions of 10^4.. rows cut into chains): the launch is bound by the
+    // chip-wide L2 -> SM throughput (~6300 B/clk), every output tile re-streams its K range of both operands --
+    // 128 x 256 tiles read A once per 256 output columns instead of once per 128 (dW_ih at 65 536 rows: 1.58 ->
+    // 1.31 GB per cell).  MEASURED SLOWER (backward at c4: 8.14 vs 7.99 ms): the 96 KB stages leave room for a
+    // 2-deep ring only.  Off; MARLC_TC_BN256_DW=1 selects it.
+    static const int dw256 = getenv("MARLC_TC_BN256_DW") ? atoi(getenv("MARLC_TC_BN256_DW")) : 0;
+    if (dw256 && args[0].A.mn_major && args[0].B.mn_major && max_n > 128) {
+        long ctas256 = 0;
+        for (int i = 0; i < count; ++i) {
+            const TcGemmArgs& a = args[i];
+            const long chains = a.allow_split ? max(1L, ((long)a.K + a.K2 + TC_MAX_CHAIN - 1) / TC_MAX_CHAIN) : 1L;
+            ctas256 += (long)((a.M + BM - 1) / BM) * ((a.N + 255) / 256) * chains;
+        }
+        if (ctas256 >= MARLC_SMS) return 256;
+    }
     return 128;
 }
 
@@ -909,6 +924,10 @@ int tc_gemm_group(const TcGemmArgs* args, int count, cudaStream_t s) {
     else { DISPATCH3(BNv, false, KSv) }
     if (BN == 32) { if (KS == 2) { DISPATCH(32, 2) } DISPATCH(32, 1) }
     if (BN == 64) { if (KS == 2) { DISPATCH(64, 2) } DISPATCH(64, 1) }
+    if (BN == 256) {  // weight gradients only (pick_bn)
+        if (x3) return launch_store<256, true, true, true, 1>(kp, gx, gy, gz, max_kb, s);
+        return launch_store<256, true, true, false, 1>(kp, gx, gy, gz, max_kb, s);
+    }
     DISPATCH(128, 1)
 #undef DISPATCH
 #undef DISPATCH3
