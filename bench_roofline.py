@@ -226,9 +226,9 @@ def step_pre_wide(model, w: dict, nb: int, dev, reps: int = 20) -> dict:
 
 
 def roofline_for(model, w: dict, nb: int, dev) -> dict:
-    """The `roofline` object of bench.py's JSON line.  Main entry = the tensor-bound kernel with the largest time
-    share of the iteration (profiles/r2/launches_*_summary.txt): the fused LSTM pair at the workload's row count,
-    measured live here; `others` holds the rest of the top of the launch list (weight-gradient GEMM, the fp32-FFMA
+    """The `roofline` object of bench.py's JSON line.  Main entry = the fused LSTM pair at the workload's row count
+    (one of three tensor-bound kernel families with 9-12 % of the iteration each at c4, the largest tensor kernel
+    at the batch-8 configurations; profiles/r2/launches_*_summary.txt), measured live here; `others` holds the rest of the top of the launch list (weight-gradient GEMM, the fp32-FFMA
     `pre` launch) and the saturating micro-benchmarks of the HBM-bound kernels."""
     pk, src = peaks()
     d = model.dims
@@ -280,10 +280,11 @@ def roofline_for(model, w: dict, nb: int, dev) -> dict:
         "peak_source": "cuBLAS TF32 8192^3 measured in this run (MEASURED_PEAKS.json holds bf16 only: "
                        f"{pk.get('bf16_tflops')} TFLOP/s burst, {src}; frac_of_half_bf16_peak uses half of it)",
         "precision": prec,
-        "time_share": ("largest share of the iteration among the tensor-bound kernels in the ncu launch list of this "
-                       "workload (profiles/r2/launches_c4_nb256_summary.txt: LSTM pair 11 %, input-gradient GEMMs 11 %, "
-                       "weight-gradient GEMMs 10.5 %); the largest share overall is step_pre_wide_kernel (20 %, fp32 FFMA: "
-                       "listed under others against the CUDA-core peak)" if big else
+        "time_share": ("the tensor-bound kernels take 9-12 % of the iteration each in the ncu launch list of this workload "
+                       "(profiles/r2/launches_c4_nb256_summary.txt: input-gradient GEMMs 11.7 %, weight-gradient GEMMs 11.2 %, "
+                       "fused LSTM pair 9.3 %); the main entry is the LSTM pair (the one captured with ncu --set full), the "
+                       "weight-gradient GEMM is listed under others; the largest share overall is step_pre_wide_kernel "
+                       "(16 %, fp32 FFMA: under others against the CUDA-core peak)" if big else
                        "largest tensor-kernel share at the batch-8 configurations (profiles/r2/launches_c2_summary.txt)"),
         "others": [
             dw_e,
