@@ -803,8 +803,13 @@ static int pick_bn(const TcGemmArgs* args, int count) {
     //  splitter with odd ring depths -- fixed in tc_gemm_body, see the comment there.)
     static const int dw128 = getenv("MARLC_TC_BN128_DW") ? atoi(getenv("MARLC_TC_BN128_DW")) : 1;
     static const int dx128 = getenv("MARLC_TC_BN128_DX") ? atoi(getenv("MARLC_TC_BN128_DX")) : 1;
+    // The per-step input-gradient group (du | dh | dh^) is bound by the chip-wide L2 -> SM throughput: every tile
+    // re-streams its K range, so 128-wide tiles (split-K restores the CTA count) move a third fewer bytes.  Measured
+    // per 16 steps: 512 rows 320 -> 238 us, 1024 rows 590 -> 418 us, 128 rows 180 -> 181 us (kept at 64 there).
+    static const int dx_min_ctas = getenv("MARLC_TC_DX128_MIN_CTAS") ? atoi(getenv("MARLC_TC_DX128_MIN_CTAS")) : 16;
     if (max_n <= 32) return 32;
-    if (max_n <= 64 || ctas128 < MARLC_SMS / 2 || bn_cap < 128) return 64;
+    const bool dx_group = !args[0].A.mn_major && args[0].B.mn_major && count > 1;  // per-step input-gradient group
+    if (max_n <= 64 || ctas128 < (dx_group ? dx_min_ctas : MARLC_SMS / 2) || bn_cap < 128) return 64;
     if (!dw128 && args[0].A.mn_major && args[0].B.mn_major) return 64;
     if (!dx128 && !args[0].A.mn_major && args[0].B.mn_major && count > 1) return 64;
     // Weight gradients (MN-major x MN-major, reductions of 10^4.. rows cut into chains): the launch is bound by the
