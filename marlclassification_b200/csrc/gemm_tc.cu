@@ -790,12 +790,16 @@ static int launch_store(TcKernelGroup& kp, int gx, int gy, int gz, int max_kb, c
 // 128-wide tiles halve the operand bytes per flop once there is a wave of CTAs anyway.  K splits count as
 // CTAs (weight gradients: few output tiles, reductions of 10^4..10^6 rows cut into TC_MAX_CHAIN chains).
 static int pick_bn(const TcGemmArgs* args, int count) {
+    // (measured per iteration with / without: 512 rows per step 2415 vs 2515 us, 1024 rows 4002 vs 4068, 128 rows 1563 vs 1576)
+    static const int dw_split_potential = getenv("MARLC_TC_DW_SPLIT_POTENTIAL") ? atoi(getenv("MARLC_TC_DW_SPLIT_POTENTIAL")) : 1;
     int max_n = 0;
     long ctas128 = 0;
     for (int i = 0; i < count; ++i) {
         const TcGemmArgs& a = args[i];
         max_n = max(max_n, a.N);
-        const long chains = a.allow_split ? max(1L, ((long)a.K + a.K2 + TC_MAX_CHAIN - 1) / TC_MAX_CHAIN) : 1L;
+        long chains = a.allow_split ? max(1L, ((long)a.K + a.K2 + TC_MAX_CHAIN - 1) / TC_MAX_CHAIN) : 1L;
+        // weight gradients: split-K (>= 4 K blocks of 32 per split) restores the CTA count of wide tiles
+        if (dw_split_potential && a.allow_split == 1 && a.A.mn_major && a.B.mn_major) chains = max(chains, ((long)a.K + a.K2) / 128);
         ctas128 += (long)((a.M + BM - 1) / BM) * ((a.N + 127) / 128) * chains;
     }
     static const int bn_cap = getenv("MARLC_TC_BN_MAX") ? atoi(getenv("MARLC_TC_BN_MAX")) : 128;  // A/B toggles
