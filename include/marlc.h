@@ -174,6 +174,10 @@ int marlc_engine_debug_stop(marlc_engine* e, int phase);
 
 /* Number of kernels the last forward/backward call launched (for bench accounting). */
 int marlc_engine_last_launches(const marlc_engine* e);
+/* Launch counters of the two GEMM back ends since library load (no reference counterpart): launches of the
+ * tcgen05 kernel and of the exact-fp32 FFMA kernel.  Tests use the difference around a call to assert WHICH
+ * path a shape took (e.g. hidden_size_linear_action = 758: row pitch not TMA-addressable -> FFMA on purpose). */
+long marlc_gemm_launch_count(int ffma);
 
 #ifdef __cplusplus
 }

@@ -68,6 +68,7 @@ _SIGS = {
                                   _P, _P]),
     "marlc_engine_debug_stop": (C.c_int, [_P, C.c_int]),
     "marlc_engine_last_launches": (C.c_int, [_P]),
+    "marlc_gemm_launch_count": (C.c_long, [C.c_int]),
 }
 
 _lib = None

@@ -30,6 +30,7 @@ void set_error(const char* fmt, ...);
             MARLC_FAIL("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
     } while (0)
 extern int g_launch_count;  // kernels launched through this library (bench accounting)
+extern long g_simt_gemm_launches, g_tc_gemm_launches;  // per GEMM back end (marlc_gemm_launch_count)
 #define MARLC_LAUNCH_CHECK()             \
     do {                                 \
         ++marlc::g_launch_count;         \

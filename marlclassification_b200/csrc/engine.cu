@@ -19,6 +19,7 @@
 namespace marlc {
 
 int g_launch_count = 0;
+long g_simt_gemm_launches = 0, g_tc_gemm_launches = 0;
 static thread_local char g_err[512] = "";
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -1365,6 +1366,7 @@ extern "C" int marlc_episode_backward(marlc_engine* e, const float* img, int acc
 }
 
 extern "C" int marlc_engine_last_launches(const marlc_engine* e) { return e->last_launches; }
+extern "C" long marlc_gemm_launch_count(int ffma) { return ffma ? marlc::g_simt_gemm_launches : marlc::g_tc_gemm_launches; }
 
 // ---- standalone operators ----------------------------------------------------
 extern "C" int marlc_patch_gather(const float* img, const int64_t* pos, float* obs, int Na, int B, int C, int H, int W,

@@ -108,6 +108,7 @@ static int launch(const GemmLaunch& g, cudaStream_t s) {
     if (maxM <= 0 || maxN <= 0) return 0;
     dim3 grid((maxN + BN - 1) / BN, (maxM + BM - 1) / BM, g.count * g.splits);
     gemm_simt_kernel<<<grid, 256, 0, s>>>(g);
+    ++g_simt_gemm_launches;
     MARLC_LAUNCH_CHECK();
     return 0;
 }

@@ -782,6 +782,7 @@ static int launch_store(TcKernelGroup& kp, int gx, int gy, int gz, int max_kb, c
         attr_done = true;
     }
     kern<<<dim3(gx, gy, gz), X3 ? TC_THREADS_X3 : TC_THREADS, S::BYTES, s>>>(kp);
+    ++g_tc_gemm_launches;
     MARLC_LAUNCH_CHECK();
     return 0;
 }
@@ -978,9 +979,11 @@ static int launch_lstm(TcKernelGroup& kp, int gx, int gy, int nkb, cudaStream_t 
         cfg.attrs = at; cfg.numAttrs = 1;
         MARLC_CUDA(cudaLaunchKernelEx(&cfg, kern, kp));
         ++g_launch_count;
+        ++g_tc_gemm_launches;
         return 0;
     }
     kern<<<dim3(gx, gy, 2), X3 ? TC_THREADS_X3 : TC_THREADS, S::BYTES, s>>>(kp);
+    ++g_tc_gemm_launches;
     MARLC_LAUNCH_CHECK();
     return 0;
 }
