@@ -248,3 +248,54 @@ def test_tc_lstm_pair_vs_fp64(M, Kin, n, mode):
         if mode == "presplit":  # the kernel also emits the low-order part of h for the next step's operand
             hi = tf32_round(hn[k])
             assert torch.equal(hn_lo[k], hn[k] - hi)
+
+
+# ---- round-2 regressions ---------------------------------------------------------------------------------
+def test_tc_gemm_long_reduction_keeps_fp32_class_accuracy():
+    """Weight-gradient shape: both operands MN-major, reduction over 65 536 rows.  The tensor core adds into
+    its TMEM accumulator with truncation; without the 4096-element chain cap (TC_MAX_CHAIN, partial sums meeting
+    in the f32 reduce-add epilogue) this product was 6e-4 off -- the 3xTF32 path must stay fp32-class."""
+    R, N, K = 65536, 256, 368
+    g = torch.Generator(device=DEV).manual_seed(11)
+    dY = torch.randn(R, N, device=DEV, generator=g)
+    X = torch.randn(R, K, device=DEV, generator=g)
+    C = run_tc(dY, X, 1, 1, N, K, R, allow_split=1, x3=1)
+    ref = dY.double().t() @ X.double()
+    err = rel_l2(C.cpu(), ref.cpu())
+    print(f"dW[{N}x{K}] over {R} rows, 3xTF32: rel-L2 {err:.1e}")
+    assert err < 1e-4
+
+
+@pytest.mark.timeout(180)
+def test_tc_gemm_in_kernel_split_under_stream_concurrency():
+    """3-stage ring + in-kernel operand split (3xTF32 without pre-split twins), several launches in flight on
+    different streams next to an unrelated memory-bound kernel: the configuration in which the operand splitter's
+    barrier phases slipped (hang / unspecified launch failure) before round 2's fix.  Results must also be right."""
+    from marlclassification_b200 import _lib
+
+    L = _lib.lib()
+    R, N, K = 16384, 384, 256  # dW = dY^T X: 128-wide MN/MN tiles (3-stage ring), split-K chains
+    M2, N2, K2 = 4096, 368, 1024  # dX-like: K-major A, MN-major B, 128-wide (3-stage ring)
+    g = torch.Generator(device=DEV).manual_seed(5)
+    dY, X = torch.randn(R, N, device=DEV, generator=g), torch.randn(R, K, device=DEV, generator=g)
+    A2, B2 = torch.randn(M2, K2, device=DEV, generator=g), torch.randn(K2, N2, device=DEV, generator=g)
+    ref1 = (dY.double().t() @ X.double()).cpu()
+    ref2 = (A2.double() @ B2.double()).cpu()
+    streams = [torch.cuda.Stream() for _ in range(3)]
+    filler = torch.empty(64 << 20, device=DEV)
+    outs1 = [torch.zeros(N, K, device=DEV) for _ in range(3)]
+    outs2 = [torch.zeros(M2, N2, device=DEV) for _ in range(3)]
+    torch.cuda.synchronize()
+    for it in range(20):
+        for i, st in enumerate(streams):
+            with torch.cuda.stream(st):
+                _lib.check(L.marlc_tc_gemm(dY.data_ptr(), N, 1, X.data_ptr(), K, 1, None, 0, None, 0, 0, None,
+                                           outs1[i].data_ptr(), K, N, K, R, 0, 1, 1, st.cuda_stream))
+                filler.add_(1.0)
+                _lib.check(L.marlc_tc_gemm(A2.data_ptr(), K2, 0, B2.data_ptr(), N2, 1, None, 0, None, 0, 0, None,
+                                           outs2[i].data_ptr(), N2, M2, N2, K2, 0, 0, 1, st.cuda_stream))
+    torch.cuda.synchronize()
+    for o in outs1:
+        assert rel_l2(o.cpu(), ref1) < 1e-4
+    for o in outs2:
+        assert rel_l2(o.cpu(), ref2) < 1e-4
