@@ -225,6 +225,30 @@ def step_pre_wide(model, w: dict, nb: int, dev, reps: int = 20) -> dict:
             "us_per_launch": t * 1e6, "flops_per_launch": flops, "tflops": flops / t / 1e12}
 
 
+def step_post(model, w: dict, nb: int, dev, reps: int = 10) -> dict:
+    """The per-step 'post' launch (policy LayerNorm/SiLU + logits + softmax + sample + transition | encoder tail),
+    timed as the difference of two truncated forwards (with / without it).  Row-local, reads and writes each
+    activation once: HBM-bound nominally, latency-bound in practice (4 rows per CTA)."""
+    from marlclassification_b200.engine import get_engine
+
+    img = torch.rand(nb, w["C"], w["H"], w["W"], device=dev)
+    eng = get_engine(model, na=w["na"], nb=nb, T=w["T"], C=w["C"], H=w["H"], W=w["W"], actions=w["actions"], gamma=0.99)
+
+    def run(stop):
+        def f():
+            eng._L.marlc_engine_debug_stop(eng._h, stop)
+            eng.forward(img)
+            eng._L.marlc_engine_debug_stop(eng._h, 0)
+        return f
+
+    t = (_time(run(14), reps) - _time(run(13), reps)) / w["T"]
+    d = model.dims
+    M = w["na"] * nb
+    bytes_row = 4.0 * (2 * d["nl_a"] + 2 * 2 * d["n_m"] + 2 * d["n_m"] + d["nb_action"]) + 48
+    return {"kernel": "step_post_kernel", "shape": {"rows": M}, "us_per_launch": t * 1e6,
+            "bytes_per_launch": bytes_row * M, "gbs": bytes_row * M / t / 1e9}
+
+
 def roofline_for(model, w: dict, nb: int, dev) -> dict:
     """The `roofline` object of bench.py's JSON line.  Main entry = the fused LSTM pair at the workload's row count
     (one of three tensor-bound kernel families with 9-12 % of the iteration each at c4, the largest tensor kernel
@@ -242,6 +266,7 @@ def roofline_for(model, w: dict, nb: int, dev) -> dict:
     lstm = lstm_pair(M, Kin, d["n_b"], dev, x3=x3, reps=50 if M > 1024 else 200)
     dw = weight_grad_gemm(TM, 4 * d["n_b"], Kin, dev, reps=10 if TM > 16384 else 50, x3=x3)
     pre = step_pre_wide(model, w, nb, dev)
+    post = step_post(model, w, nb, dev)
     g_small = gather(w["na"], nb, w["C"], w["H"], w["W"], w["f"], dev)
     g_big = gather(256, 256, w["C"], w["H"], w["W"], w["f"], dev, reps=50)  # 65536 windows: saturating
     tr_big = transition(1 << 24, w["H"], w["W"], w["f"], dev, reps=20)
@@ -292,6 +317,10 @@ def roofline_for(model, w: dict, nb: int, dev) -> dict:
              "achieved": pre["tflops"], "peak": ffma_peak, "unit": "TFLOP/s", "frac": pre["tflops"] / ffma_peak,
              "launch_us": pre["us_per_launch"], "flops_per_launch": pre["flops_per_launch"], "shape": pre["shape"],
              "peak_source": "CUDA-core fp32: 148 SMs x 128 lanes x 2 flop x sm_max_mhz (no measured figure in MEASURED_PEAKS.json)"},
+            {"kernel": "step_post_kernel @ workload (policy tail + sample + transition | encoder tail)", "bound": "hbm",
+             "achieved": post["gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": post["gbs"] / pk["hbm_gbs"],
+             "launch_us": post["us_per_launch"], "bytes_per_launch": post["bytes_per_launch"],
+             "note": "row-local chain, 4 rows per CTA: latency-bound, not bandwidth-bound"},
             {"kernel": "patch_gather_kernel @ workload", "bound": "hbm", "achieved": g_small["gbs"],
              "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": g_small["gbs"] / pk["hbm_gbs"],
              "launch_us": g_small["us_per_launch"], "bytes_per_launch": g_small["bytes_per_launch"]},
