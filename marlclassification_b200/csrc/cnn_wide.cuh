@@ -36,7 +36,7 @@ struct CnnWidePlan {
     int p_off[MAX_CNN_LAYERS];       // bias | gamma | beta (3 * cout)
     int in_off[MAX_CNN_LAYERS];      // zero-bordered input of layer l: [cin][hin+2][hin+2][NW]
     int y_off;                       // pre-norm outputs, up to CW_MAX_KS partial planes of [cout][npos][NW]
-    int st_off;                      // GroupNorm: (unused) mean[G][NW] | rstd[G][NW] | cross-warp scratch [warps][NW]
+    int st_off;                      // GroupNorm: cross-warp partial sums [warps][NW]
     int ks[MAX_CNN_LAYERS];          // input-channel slices of layer l
     int smem_floats;
 };
@@ -60,7 +60,7 @@ inline CnnWidePlan cnn_wide_plan(const CnnDesc& d, bool have_img, int nw = CW_NW
     }
     // input-channel slices: as many as there are idle threads, within what is left of shared memory for the
     // partial planes (224 KB budget: one CTA per SM owns practically all of its shared memory)
-    const int st_floats = (2 * 32 + CW_THREADS / 32) * nw;
+    const int st_floats = (CW_THREADS / 32) * nw;
     const int ybudget = 224 * 256 - off - st_floats;
     int ymax = 0;
     for (int l = 0; l < d.L; ++l) {
@@ -171,9 +171,7 @@ __device__ __forceinline__ void cnn_fwd_wide_t(const CnnFwdArgs& a, const CnnWid
     }
     CW_TRACE();  // 0: zeroed, gather + weight staging issued
     float* ybuf = sm + pl.y_off;
-    float* s_mean = sm + pl.st_off;
-    float* s_rstd = s_mean + 32 * NW;
-    float* s_red = s_rstd + 32 * NW;
+    float* s_red = sm + pl.st_off;  // cross-warp partial sums of the GroupNorm statistics [warps][NW]
 
     int wbuf = 0;
     for (int batch = cta; batch < nbatch; batch += n_cta, wbuf ^= 1) {

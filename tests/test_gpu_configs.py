@@ -39,6 +39,10 @@ CONFIGS = {
     # config 4: RESISC45 net, global batch 256 -> per-GPU shards of 256 (1 GPU, M=4096 rows) and 32 (8 GPUs, M=512)
     "c4_shard32": dict(mc=C2_NET, na=16, nb=32, T=16, C=3, H=256, W=256),
     "c4_shard256": dict(mc=C2_NET, na=16, nb=256, T=16, C=3, H=256, W=256),
+    # the wide feature extractor (>= 256 windows per step) on the other CNN shapes: MNIST (1 input channel out of 3,
+    # f = 6, 2 layers) takes it; AID (392 KB of conv weights: not eligible) must fall back to one CTA per window
+    "c1_mnist_b128": dict(mc=_mc("mnist", 6, 64, 16, 24, 8, 96, 96, 10, MOVES1), na=3, nb=128, T=5, C=3, H=28, W=28),
+    "c3_aid_b16": dict(mc=_mc("aid", 24, 256, 64, 96, 16, 320, 320, 30, MOVES3), na=16, nb=16, T=4, C=3, H=200, W=200),
     # config 5: agent sweep, 32 steps
     "c5_na32": dict(mc=C2_NET, na=32, nb=8, T=32, C=3, H=256, W=256),
     "c5_na256": dict(mc=C2_NET, na=256, nb=8, T=32, C=3, H=256, W=256),
