@@ -103,18 +103,22 @@ __device__ __forceinline__ void cw_load_windows(const CnnFwdArgs& a, int* win, i
 template <int NW>
 __device__ __forceinline__ void cw_issue_gather(const CnnFwdArgs& a, float* in0, const int* win, int batch) {
     const CnnDesc& d = a.d;
-    const int f = d.f, c0 = d.cin[0], hp = f + 2;
+    const int f = d.f, c0 = d.cin[0], hp = f + 2, ff = f * f;
     const int nvalid = min(NW, a.M - batch * NW);
-    const int rows_per = c0 * f;
-    const float r_per = 1.0f / (float)rows_per, r_f = 1.0f / (float)f;
+    const int per_w = c0 * ff;
+    const float r_per = 1.0f / (float)per_w, r_ff = 1.0f / (float)ff, r_f = 1.0f / (float)f;
     const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(in0);
-    for (int r = threadIdx.x; r < nvalid * rows_per; r += CW_THREADS) {
-        const int w = cw_div(r, r_per), q = r - w * rows_per, c = cw_div(q, r_f), i = q - c * f;
+    // one 4-byte request per thread iteration, the lanes of a warp walk ALONG the rows of a window (f contiguous
+    // floats each), so a warp-wide request touches 32 / f + 1 cache lines.  (Round 2 trace: the earlier mapping,
+    // one thread per row issuing its f requests, made every warp-wide request touch 32 lines -- ~5000 cycles of
+    // load/store-unit time per batch of 8 windows, the largest single item of the batch.)
+    for (int q = threadIdx.x; q < nvalid * per_w; q += CW_THREADS) {
+        const int w = cw_div(q, r_per), r = q - w * per_w, c = cw_div(r, r_ff), r2 = r - c * ff;
+        const int i = cw_div(r2, r_f), j = r2 - i * f;
         const int py = win[w * 4], px = win[w * 4 + 1], b = win[w * 4 + 2];
-        const float* src = a.img + ((long)(b * d.img_c + c) * a.H + py + i) * a.W + px;
-        uint32_t dst = dst0 + 4u * (uint32_t)(((c * hp + i + 1) * hp + 1) * NW + w);
-        for (int j = 0; j < f; ++j, dst += 4u * NW)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src + j) : "memory");
+        const float* src = a.img + ((long)(b * d.img_c + c) * a.H + py + i) * a.W + px + j;
+        const uint32_t dst = dst0 + 4u * (uint32_t)(((c * hp + i + 1) * hp + 1 + j) * NW + w);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
@@ -314,6 +318,7 @@ __device__ __forceinline__ void cnn_fwd_wide_t(const CnnFwdArgs& a, const CnnWid
                         __syncthreads();
                     }
                     const float mean = s * inv;
+                    CW_TRACE();  // pass 1 done
                     // pass 2: centred second moment
                     float q = 0.f;
 #pragma unroll 1
@@ -335,6 +340,7 @@ __device__ __forceinline__ void cnn_fwd_wide_t(const CnnFwdArgs& a, const CnnWid
                         __syncthreads();
                     }
                     const float rstd = 1.0f / sqrtf(q * inv + GN_EPS);
+                    CW_TRACE();  // pass 2 done
                     // pass 3: normalise, SiLU, hand over (next layer's zero-bordered input, or the output rows)
 #pragma unroll 1
                     for (int el = el0; el < n_el; el += 4 * estep) {
