@@ -84,8 +84,9 @@ def lib() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB
-    if _build.needs_build():
+    # MARLC_LIB: an alternative build of the same sources (in-kernel trace / A-B variants; development aid)
+    path = os.environ.get("MARLC_LIB") or _build.LIB
+    if path == _build.LIB and _build.needs_build():
         try:
             _build.build()
         except Exception as exc:  # no nvcc on the box and no prebuilt library

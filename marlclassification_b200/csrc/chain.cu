@@ -294,11 +294,12 @@ static int maxw_of(std::initializer_list<int> v) {
 //   dec_blocks: PERSISTENT row-block CTAs: weights and LayerNorm affines are staged once per CTA, then the CTA
 //               walks row blocks rb = i, i + dec_blocks, ...  (At 4096 rows a step had 1024 CTAs that each
 //               re-staged 82 KB of decoder weights for 4 rows: 81 us per step, ncu launch list round 2.)
-struct StepPreWideArgs { StepPreArgs a; int maxw; int staged; int cnn_blocks; int dec_blocks; CnnWidePlan wide; };
+struct StepPreWideArgs { StepPreArgs a; int maxw; int staged; int cnn_blocks; int dec_blocks; int trig; CnnWidePlan wide; };
 
-__global__ void __launch_bounds__(CT) step_pre_wide_kernel(const StepPreWideArgs ka) {
+__global__ void __launch_bounds__(CT, 1) step_pre_wide_kernel(const StepPreWideArgs ka) {
     extern __shared__ __align__(16) float sm[];
     const StepPreArgs& a = ka.a;
+    if (ka.trig) pdl_trigger();  // step chain: the LSTM GEMM's CTAs may set up while this kernel runs (common.cuh)
     if ((int)blockIdx.x < ka.cnn_blocks) {
         cnn_fwd_wide(a.cnn, ka.wide, blockIdx.x, ka.cnn_blocks, sm);
         return;
@@ -321,9 +322,9 @@ __global__ void __launch_bounds__(CT) step_pre_wide_kernel(const StepPreWideArgs
         const int row0 = rb * RB;
         return (tid < RB * n_m && rb < nrb && row0 + mr < a.M) ? other_agents_mean(a.msg_in, row0 + mr, mj, a.Na, a.Nb, n_m) : 0.f;
     };
-    // ---- once per CTA.  Every global operand is requested up front, grouped ahead of any use (see bwd_pre):
-    //      the first row block's message mean and the affines, then the (synchronously staged) weights
-    float mv = fast ? load_mean(db) : 0.f;
+    // ---- once per CTA: the launch constants (affines, synchronously staged weights) first -- under a programmatic
+    //      dependent launch this part overlaps the previous kernel of the step chain -- then, after pdl_wait(), the
+    //      first row block's message mean (produced by that kernel)
     if (fast) {
         float g0 = 0.f, b0 = 0.f, g3 = 0.f, b3 = 0.f;
         if (tid < n1) { g0 = a.d0.g[tid]; b0 = a.d0.be[tid]; }
@@ -336,6 +337,8 @@ __global__ void __launch_bounds__(CT) step_pre_wide_kernel(const StepPreWideArgs
         stage_w(W0s, a.d0.W, n1, n_m, P0);
         stage_w(W3s, a.d3.W, n2, n1, P3);
     }
+    pdl_wait();
+    float mv = fast ? load_mean(db) : 0.f;
     for (int rb = db; rb < nrb; rb += ka.dec_blocks) {
         const int row0 = rb * RB;
         const int rows_valid = min(RB, a.M - row0);
@@ -447,18 +450,20 @@ int step_pre(const StepPreArgs& a, cudaStream_t s) {
     static const int prof = getenv("MARLC_PROFILE_PRE_ROLE") ? atoi(getenv("MARLC_PROFILE_PRE_ROLE")) : 0;
     if (prof == 2) ka.cnn_blocks = 0;
     const int grid = ka.cnn_blocks + (prof == 1 ? 0 : ka.dec_blocks);
-    step_pre_wide_kernel<<<grid, CT, smem, s>>>(ka);
+    ka.trig = pdl_trigger_early();
+    MARLC_CUDA(launch_pdl(step_pre_wide_kernel, dim3(grid), dim3(CT), smem, s, ka));
     MARLC_LAUNCH_CHECK();
     return 0;
 }
 
-struct StepPreKernelArgs { StepPreArgs a; int maxw; int staged; };
+struct StepPreKernelArgs { StepPreArgs a; int maxw; int staged; int trig; };
 
 __global__ void __launch_bounds__(CT) step_pre_kernel(const StepPreKernelArgs ka) {
     extern __shared__ __align__(16) float sm[];
     const StepPreArgs& a = ka.a;
+    if (ka.trig) pdl_trigger();  // step chain: the LSTM GEMM's CTAs may set up while this kernel runs (common.cuh)
     if ((int)blockIdx.x < a.M) {
-        cnn_fwd_block(a.cnn, blockIdx.x, sm);
+        cnn_fwd_block(a.cnn, blockIdx.x, sm);  // (waits for the previous kernel before it reads the window position)
         return;
     }
     const int row0 = ((int)blockIdx.x - a.M) * RB;
@@ -478,6 +483,7 @@ __global__ void __launch_bounds__(CT) step_pre_kernel(const StepPreKernelArgs ka
         const int tid = threadIdx.x;
         float mv = 0.f;
         const int r = tid / n_m, j = tid - r * n_m;
+        pdl_wait();  // the messages come from the previous kernel of the step chain
         if (tid < RB * n_m && r < rows_valid) mv = other_agents_mean(a.msg_in, row0 + r, j, a.Na, a.Nb, n_m);
         float g0 = 0.f, b0 = 0.f, g3 = 0.f, b3 = 0.f;
         if (tid < n1) { g0 = a.d0.g[tid]; b0 = a.d0.be[tid]; }
@@ -498,6 +504,7 @@ __global__ void __launch_bounds__(CT) step_pre_kernel(const StepPreKernelArgs ka
                    a.U_lo ? a.U_lo + a.F : nullptr);
     } else {
     if (ka.staged) { stage_w(W0s, a.d0.W, n1, n_m, P0); stage_w(W3s, a.d3.W, n2, n1, P3); }
+    pdl_wait();
     // collected message (mean of the other agents)                      message.py:5-17
     for (int e = threadIdx.x; e < RB * n_m; e += CT) {
         const int r = e / n_m, j = e % n_m;
@@ -562,7 +569,8 @@ static int step_pre_small(const StepPreArgs& a, cudaStream_t s) {
         attr = smem;
     }
     const int grid = a.M + (a.M + RB - 1) / RB;
-    step_pre_kernel<<<grid, CT, smem, s>>>(ka);
+    ka.trig = pdl_trigger_early();
+    MARLC_CUDA(launch_pdl(step_pre_kernel, dim3(grid), dim3(CT), smem, s, ka));
     MARLC_LAUNCH_CHECK();
     return 0;
 }
@@ -696,14 +704,16 @@ __device__ void policy_tail_row(const StepPostArgs& a, const int m, float* srow 
     }
 }
 
-struct StepPostKernelArgs { StepPostArgs a; int maxw; int pol_blocks; int staged; };
+struct StepPostKernelArgs { StepPostArgs a; int maxw; int pol_blocks; int staged; int trig; };
 
 __global__ void __launch_bounds__(CT) step_post_kernel(const StepPostKernelArgs ka) {
     extern __shared__ __align__(16) float sm[];
     const StepPostArgs& a = ka.a;
+    if (ka.trig) pdl_trigger();  // step chain: the next step's "pre" kernel may set up (stage its weights) while this one runs
     if ((int)blockIdx.x < ka.pol_blocks) {
         const int warp = threadIdx.x >> 5;
         const int m = blockIdx.x * (CT / 32) + warp;
+        pdl_wait();  // pol_y1 comes from the block-0 GEMMs
         if (m < a.M) policy_tail_row(a, m, sm + warp * a.act.nl);
         return;
     }
@@ -723,6 +733,7 @@ __global__ void __launch_bounds__(CT) step_post_kernel(const StepPostKernelArgs 
         int r1[2], k1[2];
 #pragma unroll
         for (int i = 0; i < 2; ++i) { const int e = tid + i * CT; r1[i] = e / n1; k1[i] = e - r1[i] * n1; }
+        pdl_wait();  // enc_y1 comes from the block-0 GEMMs
 #pragma unroll
         for (int i = 0; i < 2; ++i)
             if (r1[i] < rows_valid) y1v[i] = a.enc_y1[(long)(row0 + r1[i]) * n1 + k1[i]];
@@ -742,6 +753,7 @@ __global__ void __launch_bounds__(CT) step_post_kernel(const StepPostKernelArgs 
         return;
     }
     if (ka.staged) stage_w(S.wres, a.e3.W, n2, n1, P3);
+    pdl_wait();
     for (int e = threadIdx.x; e < RB * n1; e += CT) {
         const int r = e / n1, k = e % n1;
         S.bufA[r * ka.maxw + k] = r < rows_valid ? a.enc_y1[(long)(row0 + r) * n1 + k] : 0.f;
@@ -770,7 +782,8 @@ int step_post(const StepPostArgs& a, cudaStream_t s) {
         attr = smem;
     }
     const int grid = ka.pol_blocks + (a.M + RB - 1) / RB;
-    step_post_kernel<<<grid, CT, smem, s>>>(ka);
+    ka.trig = pdl_trigger_early();
+    MARLC_CUDA(launch_pdl(step_post_kernel, dim3(grid), dim3(CT), smem, s, ka));
     MARLC_LAUNCH_CHECK();
     return 0;
 }
@@ -876,7 +889,7 @@ __device__ __forceinline__ void cell_bwd_compute(const CellIn& c, const int row0
     }
 }
 
-struct BwdPreKernelArgs { BwdPreArgs a; int maxw; int staged; };
+struct BwdPreKernelArgs { BwdPreArgs a; int maxw; int staged;  int trig; };
 
 #ifdef MARLC_CHAIN_TRACE  // timeline of CTA 0 (cycles since entry), printed by thread 0
 #define CHAIN_TRACE_DECL() __shared__ long long ch_tr[24]; const long long ch_t0 = clock64(); int ch_i = 0
@@ -900,6 +913,8 @@ __global__ void __launch_bounds__(CT) bwd_pre_kernel(const BwdPreKernelArgs ka) 
     float* W0s = W3s + n_m * n1;     // encode_msg.0 weight [n1][nb]
     const bool enc = a.dcoll != nullptr;
     CHAIN_TRACE_DECL();
+    if (ka.trig) pdl_trigger();  // sweep chain: the input-gradient GEMM's CTAs may set up while this kernel runs (common.cuh)
+    pdl_wait();     // at entry: the operand loads must be queued AHEAD of the weight copies (see below)
     // ---- fast path: every global operand of the CTA is requested up front (cell inputs and encoder
     //      activations to registers, LayerNorm affines to shared memory), and only THEN the 164 KB of
     //      weights (cp.async): the load/store unit is in order, and with the weight copies queued
@@ -1040,7 +1055,8 @@ int bwd_pre(const BwdPreArgs& a, cudaStream_t s) {
         MARLC_CUDA(cudaFuncSetAttribute(bwd_pre_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = smem;
     }
-    bwd_pre_kernel<<<(a.M + RB - 1) / RB, CT, smem, s>>>(ka);
+    ka.trig = pdl_trigger_early();
+    MARLC_CUDA(launch_pdl(bwd_pre_kernel, dim3((a.M + RB - 1) / RB), dim3(CT), smem, s, ka));
     MARLC_LAUNCH_CHECK();
     return 0;
 }
@@ -1048,7 +1064,7 @@ int bwd_pre(const BwdPreArgs& a, cudaStream_t s) {
 // ---------------------------------------------------------------------------------
 // backward "post" (step t): decoder backward from du_t -> dcoll
 // ---------------------------------------------------------------------------------
-struct BwdPostKernelArgs { BwdPostArgs a; int maxw; int staged; };
+struct BwdPostKernelArgs { BwdPostArgs a; int maxw; int staged; int trig; };
 
 __global__ void __launch_bounds__(CT) bwd_post_kernel(const BwdPostKernelArgs ka) {
     extern __shared__ __align__(16) float sm[];
@@ -1058,6 +1074,8 @@ __global__ void __launch_bounds__(CT) bwd_post_kernel(const BwdPostKernelArgs ka
     const int n_m = a.n_m, n1 = a.d0.n_out, n2 = a.n_m_o;
     float* W3s = S.wres;           // decode_msg.3 weight [n2][n1]
     float* W0s = W3s + n2 * n1;    // decode_msg.0 weight [n1][n_m]
+    if (ka.trig) pdl_trigger();  // sweep chain: the next step's bwd_pre may become resident while this kernel runs
+    pdl_wait();     // at entry, as in bwd_pre
     // ---- fast path (as in bwd_pre): every global operand is requested up front, loads grouped ahead of
     //      any use, LayerNorm affines and the block-0 activations parked in the unused tile scratch
     const bool fast = ka.staged && RB * n2 <= 2 * CT && RB * n1 <= 2 * CT && n1 <= CT && n2 <= CT &&
@@ -1158,7 +1176,8 @@ int bwd_post(const BwdPostArgs& a, cudaStream_t s) {
         MARLC_CUDA(cudaFuncSetAttribute(bwd_post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = smem;
     }
-    bwd_post_kernel<<<(a.M + RB - 1) / RB, CT, smem, s>>>(ka);
+    ka.trig = pdl_trigger_early();
+    MARLC_CUDA(launch_pdl(bwd_post_kernel, dim3((a.M + RB - 1) / RB), dim3(CT), smem, s, ka));
     MARLC_LAUNCH_CHECK();
     return 0;
 }

@@ -109,6 +109,7 @@ __device__ __forceinline__ void cnn_fwd_block(const CnnFwdArgs& a, const int m, 
         const int hp = f + 2, c0 = d.cin[0];
         for (int e = tid; e < c0 * hp * hp; e += nt) in[e] = 0.f;
         __syncthreads();
+        pdl_wait();  // weights are launch constants; the window position / patch comes from the previous kernel
         if (a.patch) {
             const float* src = a.patch + (long)m * d.img_c * ff;
             for (int e = tid; e < c0 * ff; e += nt) {
@@ -315,6 +316,7 @@ __device__ __forceinline__ void cnn_fwd_block_t(const CnnFwdArgs& a, const int m
         const int hp = f + 2, c0 = d.cin[0];
         for (int e = tid; e < c0 * hp * hp; e += nt) in[e] = 0.f;
         __syncthreads();  // (also publishes the mbarrier initialisation to the waiting threads)
+        pdl_wait();  // weights are launch constants; the window position / patch comes from the previous kernel
         if (a.patch) {
             const float* src = a.patch + (long)m * d.img_c * ff;
             for (int e = tid; e < c0 * ff; e += nt) {

@@ -13,8 +13,8 @@
 //     window at a time -- and the lanes of a warp read distinct banks or broadcast;
 //   * splits the input channels of the narrow late layers over `ks` thread groups (partial
 //     planes, summed when the pre-norm outputs are saved for backward);
-//   * computes GroupNorm statistics two-pass (as the reference) with lanes = 4 elements x 8
-//     windows (conflict-free), and writes y_save / the output with 32-byte coalesced rows;
+//   * computes GroupNorm statistics two-pass (as the reference), a lane owning 4 windows of an
+//     element (128-bit shared accesses, branch-free loops, channel / scatter indices from a table);
 //   * prefetches the next batch's windows with cp.async as soon as layer 0 has consumed the
 //     current ones.
 // Same arithmetic as cnn_fwd_block_t (fp32 FFMA, fast SiLU); summation order differs (parity tests
@@ -34,6 +34,7 @@ struct CnnWidePlan {
     int nw;                          // windows per pass: 8 or 4
     int w_off[MAX_CNN_LAYERS];       // floats: transposed weights of layer l
     int p_off[MAX_CNN_LAYERS];       // bias | gamma | beta (3 * cout)
+    int lut_off[MAX_CNN_LAYERS];     // per output element e = c * npos + pos: (c << 16) | position in the next layer's input
     int in_off[MAX_CNN_LAYERS];      // zero-bordered input of layer l: [cin][hin+2][hin+2][NW]
     int y_off;                       // pre-norm outputs, up to CW_MAX_KS partial planes of [cout][npos][NW]
     int st_off;                      // GroupNorm: cross-warp partial sums [warps][NW]
@@ -45,7 +46,11 @@ inline CnnWidePlan cnn_wide_plan(const CnnDesc& d, bool have_img, int nw = CW_NW
     CnnWidePlan p;
     memset(&p, 0, sizeof(p));
     p.nw = nw;
+#ifdef MARLC_CW_NW4
     if (!have_img || !d.wT[0] || (nw != 8 && nw != 4)) return p;
+#else
+    if (!have_img || !d.wT[0] || nw != 8) return p;
+#endif
     int off = 0;
     for (int l = 0; l < d.L; ++l) {
         if (!d.wT[l] || (d.cout[l] & 3) || d.groups[l] > 32 || d.cout[l] % d.groups[l]) return p;
@@ -53,6 +58,11 @@ inline CnnWidePlan cnn_wide_plan(const CnnDesc& d, bool have_img, int nw = CW_NW
         off += d.cout[l] * d.cin[l] * 9;
     }
     for (int l = 0; l < d.L; ++l) { p.p_off[l] = off; off += 3 * d.cout[l]; }
+    for (int l = 0; l < d.L; ++l) {
+        if (d.cout[l] >= 32768 || d.cout[l] * (d.hout[l] + 2) * (d.hout[l] + 2) >= 65536) return p;  // packed in 16 + 16 bits
+        p.lut_off[l] = off;
+        off += d.cout[l] * d.hout[l] * d.hout[l];
+    }
     off = (off + 3) & ~3;
     for (int l = 0; l < d.L; ++l) {
         p.in_off[l] = off;
@@ -142,21 +152,13 @@ __device__ __forceinline__ void cnn_fwd_wide_t(const CnnFwdArgs& a, const CnnWid
     // ---- once per CTA: zero the activation buffers (their borders stay zero), stage weights + affines
     __shared__ __align__(8) uint64_t wbar[MAX_CNN_LAYERS];  // one per layer: layer 0 (1.7 KB at RESISC45) must not wait for layer 2 (73 KB)
     __shared__ int s_win[2][NW * 4];  // {py, px, image} of the current / next batch's windows
-    cw_load_windows<NW>(a, s_win[0], cta);
+    // (everything up to pdl_wait() reads launch constants only -- weights, biases, affines -- so under a programmatic
+    //  dependent launch it overlaps the previous kernel of the step chain; the window corners come from that kernel)
     if (tid == 0) {
         for (int l = 0; l < d.L; ++l)
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&wbar[l])));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    {
-        float4* z = reinterpret_cast<float4*>(sm + pl.in_off[0]);
-        const int n4 = (pl.y_off - pl.in_off[0]) >> 2;
-        for (int i = tid; i < n4; i += CW_THREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    __syncthreads();  // the gather below writes into the zeroed buffer
-    cw_issue_gather<NW>(a, sm + pl.in_off[0], s_win[0], cta);
-    // weights: ONE bulk copy per layer (the copy engine moves them while the threads go on), completion on wbar
-    if (tid == 0) {
+        // weights: ONE bulk copy per layer (the copy engine moves them while the threads go on), completion on wbar
         for (int l = 0; l < d.L; ++l) {
             const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&wbar[l]);
             const uint32_t bytes = (uint32_t)(d.cout[l] * d.cin[l] * 9 * 4);
@@ -164,6 +166,11 @@ __device__ __forceinline__ void cnn_fwd_wide_t(const CnnFwdArgs& a, const CnnWid
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                              (uint32_t)__cvta_generic_to_shared(sm + pl.w_off[l])), "l"(d.wT[l]), "r"(bytes), "r"(bar) : "memory");
         }
+    }
+    {
+        float4* z = reinterpret_cast<float4*>(sm + pl.in_off[0]);
+        const int n4 = (pl.y_off - pl.in_off[0]) >> 2;
+        for (int i = tid; i < n4; i += CW_THREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     for (int l = 0; l < d.L; ++l) {
         float* pp = sm + pl.p_off[l];
@@ -173,6 +180,19 @@ __device__ __forceinline__ void cnn_fwd_wide_t(const CnnFwdArgs& a, const CnnWid
             pp[2 * d.cout[l] + i] = d.gn_b[l][i];
         }
     }
+    for (int l = 0; l < d.L; ++l) {  // element -> (channel, slot in the next layer's zero-bordered input)
+        int* lut = reinterpret_cast<int*>(sm + pl.lut_off[l]);
+        const int ho = d.hout[l], npos = ho * ho, hop = ho + 2, total = d.cout[l] * npos;
+        const bool last = (l + 1 == d.L);
+        for (int e = tid; e < total; e += CW_THREADS) {
+            const int c = e / npos, pos = e - c * npos, oy = pos / ho, ox = pos - oy * ho;
+            lut[e] = (c << 16) | (last ? 0 : (c * hop + oy + 1) * hop + ox + 1);
+        }
+    }
+    pdl_wait();
+    cw_load_windows<NW>(a, s_win[0], cta);
+    __syncthreads();  // the gather below reads s_win and writes into the zeroed buffer; wbar is initialised for all
+    cw_issue_gather<NW>(a, sm + pl.in_off[0], s_win[0], cta);
     CW_TRACE();  // 0: zeroed, gather + weight staging issued
     float* ybuf = sm + pl.y_off;
     float* s_red = sm + pl.st_off;  // cross-warp partial sums of the GroupNorm statistics [warps][NW]
@@ -251,12 +271,13 @@ __device__ __forceinline__ void cnn_fwd_wide_t(const CnnFwdArgs& a, const CnnWid
             if (l == 0 && batch + n_cta < nbatch)  // layer 0's input buffer is free: prefetch the next batch's windows
                 cw_issue_gather<NW>(a, sm + pl.in_off[0], s_win[wbuf ^ 1], batch + n_cta);
             // ---- GroupNorm + SiLU.  Warps are bound to groups (nwarps / G warps share a group when G < nwarps,
-            //      their partial sums meet in shared memory); lane = (4 elements) x (8 windows): conflict-free
-            //      shared accesses, 16-byte rows per window in global memory.  Two-pass statistics as the
-            //      reference.  Three COMPACT loops over shared memory (4 elements in flight per lane each):
-            //      a version that kept the values in registers through fully unrolled loops was 96 KB of
-            //      straight-line code per layer and ran out of the instruction cache -- `no_instruction` was the
-            //      top stall reason in ncu, 35 % issue-active.
+            //      their partial sums meet in shared memory).  A lane owns FOUR windows of an element (one 128-bit
+            //      shared access; lane = (32 / WV elements) x (WV = NW / 4 window vectors)), U elements in flight,
+            //      and the loops are branch-free (clamped indices, predicated stores): the first version -- one
+            //      window per lane, per-element index divisions, `if (e < n_el)` bodies that serialised the 4
+            //      elements of an iteration -- took 24 000 of a batch's 44 000 cycles (in-kernel trace, round 2).
+            //      Two-pass statistics as the reference; the per-element channel / scatter index comes from a
+            //      table built once per CTA.
             {
 #ifdef CW_NO_YSAVE
                 float* ysave = nullptr;
@@ -265,104 +286,137 @@ __device__ __forceinline__ void cnn_fwd_wide_t(const CnnFwdArgs& a, const CnnWid
 #endif
                 const float* gam = prm + co_n;
                 const float* bet = prm + 2 * co_n;
-                constexpr int EPL = 32 / NW;  // elements a warp covers per step: lane = (EPL elements) x (NW windows)
-                const int w = lane & (NW - 1), es = lane / NW;
+                const int* lut = reinterpret_cast<const int*>(sm + pl.lut_off[l]);
+                constexpr int WV = NW / 4;    // 128-bit window vectors per element
+                constexpr int EPW = 32 / WV;  // elements a warp covers per step
+                constexpr int U = 4;          // element slots in flight per lane
+                const int wh = lane % WV, es = lane / WV;
                 constexpr int nwarps = CW_THREADS / 32;
                 const bool shared_groups = G < nwarps && nwarps % G == 0;
                 const int wpg = shared_groups ? nwarps / G : 1;
-                const int estep = EPL * wpg;
-                const float inv = 1.0f / (float)ng, r_npos = 1.0f / (float)npos, r_ho = 1.0f / (float)ho;
+                const int estep = EPW * wpg;
+                const float inv = 1.0f / (float)ng;
                 float* nxt = last ? nullptr : sm + pl.in_off[l + 1];
-                const int hop = ho + 2;
-                const bool wok = w < nvalid;
+                bool wok[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) wok[j] = 4 * wh + j < nvalid;
+                auto ld4 = [](const float* p) { return *reinterpret_cast<const float4*>(p); };
+                auto group_sum = [&](float4 v, int g) -> float4 {  // over the lanes' elements, then over the group's warps
+#pragma unroll
+                    for (int o = WV; o < 32; o <<= 1) {
+                        v.x += __shfl_xor_sync(0xffffffffu, v.x, o); v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+                        v.z += __shfl_xor_sync(0xffffffffu, v.z, o); v.w += __shfl_xor_sync(0xffffffffu, v.w, o);
+                    }
+                    if (shared_groups) {
+                        if (es == 0) *reinterpret_cast<float4*>(s_red + warp * NW + 4 * wh) = v;
+                        __syncthreads();
+                        v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int i = 0; i < wpg; ++i) {
+                            const float4 t = ld4(s_red + (g * wpg + i) * NW + 4 * wh);
+                            v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+                        }
+                        __syncthreads();
+                    }
+                    return v;
+                };
                 for (int g0 = 0; g0 < G; g0 += (shared_groups ? G : nwarps)) {
                     const int g = shared_groups ? warp / wpg : g0 + warp;
                     const int sub = shared_groups ? warp % wpg : 0;
-                    const int el0 = sub * EPL + es;
+                    const int el0 = sub * EPW + es;
                     const int n_el = (g < G) ? ng : 0;  // inactive warps run empty loops (they still meet the barriers)
-                    float* yg = ybuf + (g < G ? g : 0) * ng * NW + w;
-                    float* ys = ysave ? ysave + (long)(m0 + w) * total + g * ng : nullptr;
+                    const int gbase = (g < G ? g : 0) * ng;
+                    float* yg = ybuf + gbase * NW + 4 * wh;
+                    float* ys = ysave ? ysave + (long)(m0 + 4 * wh) * total + gbase : nullptr;
                     // pass 1: sum the input-channel slices (kept in plane 0), save for backward, accumulate the sum
-                    float s = 0.f;
+                    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
-                    for (int el = el0; el < n_el; el += 4 * estep) {
-                        float x[4];
+                    for (int el = el0; el < n_el; el += U * estep) {
+                        float4 x[U];
+                        int e[U];
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int e = el + u * estep;
-                            x[u] = e < n_el ? yg[e * NW] : 0.f;
+                        for (int u = 0; u < U; ++u) {
+                            e[u] = el + u * estep < n_el ? el + u * estep : el;  // idle slots re-read the lane's own first element
+                            x[u] = ld4(yg + e[u] * NW);
                         }
                         for (int p = 1; p < ks; ++p)
 #pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                const int e = el + u * estep;
-                                if (e < n_el) x[u] += yg[(p * total + e) * NW];
+                            for (int u = 0; u < U; ++u) {
+                                const float4 t = ld4(yg + (p * total + e[u]) * NW);
+                                x[u].x += t.x; x[u].y += t.y; x[u].z += t.z; x[u].w += t.w;
                             }
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int e = el + u * estep;
-                            if (e < n_el) {
-                                if (ks > 1) yg[e * NW] = x[u];
-                                if (ys && wok) ys[e] = x[u];
+                        for (int u = 0; u < U; ++u) {
+                            const bool ok = el + u * estep < n_el;
+                            if (ks > 1 && ok) *reinterpret_cast<float4*>(yg + e[u] * NW) = x[u];
+                            if (ys) {
+                                if (ok && wok[0]) ys[e[u]] = x[u].x;
+                                if (ok && wok[1]) ys[(long)total + e[u]] = x[u].y;
+                                if (ok && wok[2]) ys[2 * (long)total + e[u]] = x[u].z;
+                                if (ok && wok[3]) ys[3 * (long)total + e[u]] = x[u].w;
                             }
-                            s += x[u];
+                            if (ok) { s.x += x[u].x; s.y += x[u].y; s.z += x[u].z; s.w += x[u].w; }
                         }
                     }
-#pragma unroll
-                    for (int o = NW; o < 32; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                    if (shared_groups) {
-                        if (es == 0) s_red[warp * NW + w] = s;
-                        __syncthreads();
-                        s = 0.f;
-                        for (int i = 0; i < wpg; ++i) s += s_red[(g * wpg + i) * NW + w];
-                        __syncthreads();
-                    }
-                    const float mean = s * inv;
+                    s = group_sum(s, g);
+                    const float4 mean = make_float4(s.x * inv, s.y * inv, s.z * inv, s.w * inv);
                     CW_TRACE();  // pass 1 done
                     // pass 2: centred second moment
-                    float q = 0.f;
+                    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
-                    for (int el = el0; el < n_el; el += 4 * estep) {
+                    for (int el = el0; el < n_el; el += U * estep) {
+                        float4 x[U];
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int e = el + u * estep;
-                            const float dd = e < n_el ? yg[e * NW] - mean : 0.f;
-                            q = fmaf(dd, dd, q);
+                        for (int u = 0; u < U; ++u) x[u] = ld4(yg + (el + u * estep < n_el ? el + u * estep : el) * NW);
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            if (el + u * estep < n_el) {
+                                const float dx = x[u].x - mean.x, dy = x[u].y - mean.y, dz = x[u].z - mean.z, dw = x[u].w - mean.w;
+                                q.x = fmaf(dx, dx, q.x); q.y = fmaf(dy, dy, q.y); q.z = fmaf(dz, dz, q.z); q.w = fmaf(dw, dw, q.w);
+                            }
                         }
                     }
-#pragma unroll
-                    for (int o = NW; o < 32; o <<= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-                    if (shared_groups) {
-                        if (es == 0) s_red[warp * NW + w] = q;
-                        __syncthreads();
-                        q = 0.f;
-                        for (int i = 0; i < wpg; ++i) q += s_red[(g * wpg + i) * NW + w];
-                        __syncthreads();
-                    }
-                    const float rstd = 1.0f / sqrtf(q * inv + GN_EPS);
+                    q = group_sum(q, g);
+                    const float4 rstd = make_float4(1.0f / sqrtf(q.x * inv + GN_EPS), 1.0f / sqrtf(q.y * inv + GN_EPS),
+                                                    1.0f / sqrtf(q.z * inv + GN_EPS), 1.0f / sqrtf(q.w * inv + GN_EPS));
                     CW_TRACE();  // pass 2 done
                     // pass 3: normalise, SiLU, hand over (next layer's zero-bordered input, or the output rows)
+                    float* orow = a.out + (long)(m0 + 4 * wh) * a.ldo + gbase;
+                    float* orow_lo = a.out_lo ? a.out_lo + (long)(m0 + 4 * wh) * a.ldo + gbase : nullptr;
 #pragma unroll 1
-                    for (int el = el0; el < n_el; el += 4 * estep) {
-                        float x[4];
+                    for (int el = el0; el < n_el; el += U * estep) {
+                        float4 x[U];
+                        int e[U], lu[U];
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int e = el + u * estep;
-                            x[u] = e < n_el ? yg[e * NW] : 0.f;
+                        for (int u = 0; u < U; ++u) {
+                            e[u] = el + u * estep < n_el ? el + u * estep : el;  // idle slots re-read the lane's own first element
+                            x[u] = ld4(yg + e[u] * NW);
+                            lu[u] = lut[gbase + e[u]];
                         }
+                        float ga[U], be[U];
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int el_u = el + u * estep;
-                            if (el_u < n_el) {
-                                const int e = g * ng + el_u, c = cw_div(e, r_npos), pos = e - c * npos;
-                                const float z = (x[u] - mean) * rstd * gam[c] + bet[c];
-                                const float o = __fdividef(z, 1.0f + __expf(-z));  // SiLU
-                                if (!last) {
-                                    const int oy = cw_div(pos, r_ho), ox = pos - oy * ho;
-                                    nxt[((c * hop + oy + 1) * hop + ox + 1) * NW + w] = o;
-                                } else if (wok) {
-                                    a.out[(long)(m0 + w) * a.ldo + e] = o;
-                                    if (a.out_lo) a.out_lo[(long)(m0 + w) * a.ldo + e] = tf32_lo(o);
+                        for (int u = 0; u < U; ++u) { ga[u] = gam[lu[u] >> 16]; be[u] = bet[lu[u] >> 16]; }
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            const bool ok = el + u * estep < n_el;
+                            const float z0 = (x[u].x - mean.x) * rstd.x * ga[u] + be[u];
+                            const float z1 = (x[u].y - mean.y) * rstd.y * ga[u] + be[u];
+                            const float z2 = (x[u].z - mean.z) * rstd.z * ga[u] + be[u];
+                            const float z3 = (x[u].w - mean.w) * rstd.w * ga[u] + be[u];
+                            const float4 o = make_float4(__fdividef(z0, 1.0f + __expf(-z0)), __fdividef(z1, 1.0f + __expf(-z1)),
+                                                         __fdividef(z2, 1.0f + __expf(-z2)), __fdividef(z3, 1.0f + __expf(-z3)));  // SiLU
+                            if (!last) {
+                                if (ok) *reinterpret_cast<float4*>(nxt + (lu[u] & 0xffff) * NW + 4 * wh) = o;
+                            } else {
+                                const long ld = a.ldo;
+                                if (ok && wok[0]) orow[e[u]] = o.x;
+                                if (ok && wok[1]) orow[ld + e[u]] = o.y;
+                                if (ok && wok[2]) orow[2 * ld + e[u]] = o.z;
+                                if (ok && wok[3]) orow[3 * ld + e[u]] = o.w;
+                                if (orow_lo) {
+                                    if (ok && wok[0]) orow_lo[e[u]] = tf32_lo(o.x);
+                                    if (ok && wok[1]) orow_lo[ld + e[u]] = tf32_lo(o.y);
+                                    if (ok && wok[2]) orow_lo[2 * ld + e[u]] = tf32_lo(o.z);
+                                    if (ok && wok[3]) orow_lo[3 * ld + e[u]] = tf32_lo(o.w);
                                 }
                             }
                         }
@@ -386,8 +440,11 @@ __device__ __forceinline__ void cnn_fwd_wide_t(const CnnFwdArgs& a, const CnnWid
 // All CW_THREADS threads of CTA `cta` (of `n_cta` cooperating CTAs) must call.
 __device__ __forceinline__ void cnn_fwd_wide(const CnnFwdArgs& a, const CnnWidePlan& pl, const int cta, const int n_cta,
                                              float* sm) {
-    if (pl.nw == 4) cnn_fwd_wide_t<4>(a, pl, cta, n_cta, sm);
-    else cnn_fwd_wide_t<8>(a, pl, cta, n_cta, sm);
+#ifdef MARLC_CW_NW4  // A/B build: 4 windows per pass (measured slower); not compiled by default -- the second
+                     // instantiation doubles the role's code, and the kernel already runs close to the instruction cache
+    if (pl.nw == 4) { cnn_fwd_wide_t<4>(a, pl, cta, n_cta, sm); return; }
+#endif
+    cnn_fwd_wide_t<8>(a, pl, cta, n_cta, sm);
 }
 
 }  // namespace marlc

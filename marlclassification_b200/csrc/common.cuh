@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #define MARLC_SMS 148
 
@@ -41,6 +42,63 @@ extern long g_simt_gemm_launches, g_tc_gemm_launches;  // per GEMM back end (mar
         int r__ = (expr);      \
         if (r__) return r__;   \
     } while (0)
+
+// ---- programmatic dependent launch (PDL) ---------------------------------------
+// The per-step kernels of the rollout and of the BPTT sweep form one dependent chain per stream
+// (episode.py:70-78: step t+1 needs step t), ~1.9 us of launch / drain latency per edge.  A kernel launched
+// with the programmatic-stream-serialization attribute may become resident while its predecessor is still
+// running: its CTAs run their prologue (barrier init, TMEM allocation, descriptor prefetch, constant staging)
+// and block in pdl_wait() until the predecessor has completed and its writes are visible.  Contract for every
+// kernel launched through launch_pdl(): NOTHING but launch-constant memory (parameters, tensor maps, weights
+// of the current iteration) is read, and no global memory is written, before pdl_wait(); pdl_trigger() at
+// entry lets the NEXT kernel of the chain do the same.  g_pdl is set by the engine (PdlScope) only around
+// launches whose predecessor in the stream is a kernel of the same chain; everywhere else the launch is an
+// ordinary one and pdl_wait() returns immediately.  MARLC_PDL=0 switches the attribute off (A/B runs).
+extern thread_local int g_pdl, g_pdl_trig;
+struct PdlScope {  // on: the launches inside are programmatic dependents; trig: they trigger THEIR dependents at entry
+    int prev, prev_trig;
+    explicit PdlScope(int on, int trig = 0) : prev(g_pdl), prev_trig(g_pdl_trig) { g_pdl = on; g_pdl_trig = trig; }
+    ~PdlScope() { g_pdl = prev; g_pdl_trig = prev_trig; }
+};
+bool pdl_enabled();
+// Which edges, and where the trigger sits, is measured, not derived (profiles/README.md, round 2: 512 rows per step):
+//   * forward: step_pre, block-0 GEMMs and step_post as dependents with the trigger at kernel entry: -52 us per
+//     16 steps; the LSTM pair as a dependent: +15 us (left an ordinary launch);
+//   * BPTT sweep: an entry trigger makes every edge slower (+44 us for bwd_pre alone: the next kernel's CTAs pile
+//     onto the SMs the running kernel leaves free and start unevenly); without an explicit trigger (dependents
+//     launch when the last CTA exits, skipping only the drain) the three edges gain 26 us.
+// A/B switches: MARLC_PDL_MASK selects the edges (bit per consumer kernel: 1 step_pre, 2 LSTM pair, 4 block-0 GEMMs,
+// 8 step_post, 16 bwd_pre, 32 input-gradient GEMMs, 64 bwd_post; default 125); MARLC_PDL_TRIG: bit 0 = entry
+// trigger in the forward chain, bit 1 = in the sweep (default 1).
+enum { PDL_STEP_PRE = 1, PDL_LSTM = 2, PDL_G0 = 4, PDL_STEP_POST = 8, PDL_BWD_PRE = 16, PDL_DX = 32, PDL_BWD_POST = 64 };
+int pdl_edge(int bit);   // 1 if that edge is enabled
+int pdl_trigger_early(); // value for the kernels' `trig` argument (from the enclosing PdlScope)
+int pdl_trig_mode(int bwd);  // MARLC_PDL_TRIG bit for the forward chain (0) / the sweep (1)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// Launch `kern(arg)`; with g_pdl set (and PDL enabled) as a programmatic dependent of the previous kernel in `s`.
+// cluster_x > 1 adds a cluster dimension along x.
+template <typename KP, typename A>
+inline cudaError_t launch_pdl(void (*kern)(KP), dim3 grid, dim3 block, size_t smem, cudaStream_t s, const A& arg,
+                              int cluster_x = 1) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[2];
+    int n = 0;
+    if (cluster_x > 1) {
+        at[n].id = cudaLaunchAttributeClusterDimension;
+        at[n].val.clusterDim.x = (unsigned)cluster_x; at[n].val.clusterDim.y = 1; at[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    if (g_pdl && pdl_enabled()) {
+        at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    cfg.attrs = n ? at : nullptr; cfg.numAttrs = (unsigned)n;
+    return cudaLaunchKernelEx(&cfg, kern, arg);
+}
 
 // ---- math ------------------------------------------------------------------
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }

@@ -27,6 +27,21 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+// programmatic dependent launch: state and A/B switches (common.cuh)
+thread_local int g_pdl = 0, g_pdl_trig = 0;
+bool pdl_enabled() {
+    static const bool on = !(getenv("MARLC_PDL") && atoi(getenv("MARLC_PDL")) == 0);
+    return on;
+}
+int pdl_edge(int bit) {
+    static const int mask = getenv("MARLC_PDL_MASK") ? atoi(getenv("MARLC_PDL_MASK")) : 125;
+    return (mask & bit) ? 1 : 0;
+}
+int pdl_trig_mode(int bwd) {
+    static const int t = getenv("MARLC_PDL_TRIG") ? atoi(getenv("MARLC_PDL_TRIG")) : 1;
+    return (t >> (bwd ? 1 : 0)) & 1;
+}
+int pdl_trigger_early() { return g_pdl_trig; }
 
 struct ParamInfo {
     std::string name;
@@ -547,9 +562,13 @@ static int block_fwd(marlc_engine* e, const std::string& name, int i, const floa
 // slots) and the stand-alone ModelsWrapper.forward (caller tensors).
 static int step_networks(marlc_engine* e, int t, const float* img, const int* pos, const float* patch,
                          const float* msg_in, const float* npos_in, const float* h_in, const float* c_in,
-                         const float* hc_in, const float* cc_in, cudaStream_t s) {
+                         const float* hc_in, const float* cc_in, cudaStream_t s, int pdl = 0) {
+    // pdl (common.cuh, programmatic dependent launch): 0 = ordinary launches (stand-alone step), 1 = every launch but
+    // the first is a programmatic dependent of its predecessor, 2 = the first one too (its predecessor in `s` is the
+    // previous step's last kernel)
     const marlc_config& c = e->cfg;
     const int M = e->M, Kin = e->Kin, F = e->F;
+    const int pdl_rest = pdl >= 1;
     float* Ut = e->buf("U") + (size_t)t * M * Kin;
     float* H = e->buf("H");
     float* Cb = e->buf("Cb");
@@ -575,7 +594,10 @@ static int step_networks(marlc_engine* e, int t, const float* img, const int* po
         pa.pos = chain_lin(e, "map_pos", 0, 2, c.n_d, true);
         pa.pos_y = e->buf("pos_y") + (size_t)t * M * c.n_d;
         pa.U = Ut; pa.ldu = Kin; pa.F = F; pa.Na = c.na; pa.Nb = c.nb; pa.M = M;
-        MARLC_TRY(step_pre(pa, s));
+        {
+            PdlScope pdl_first(pdl >= 2 && pdl_edge(PDL_STEP_PRE), pdl >= 1 && pdl_trig_mode(0));
+            MARLC_TRY(step_pre(pa, s));
+        }
         if (e->debug_stop == 11) return 0;
     } else {
         // b_t: gather + CNN straight into u_t[:, 0:F]                (models.py:92-94)
@@ -628,6 +650,7 @@ static int step_networks(marlc_engine* e, int t, const float* img, const int* po
                 a.Wih_lo = e->lo_of(a.Wih); a.Whh_lo = e->lo_of(a.Whh);
                 a.h_new_lo = const_cast<float*>(e->lo_of(a.h_new));
             }
+            PdlScope pdl_lstm(pdl_rest && pdl_edge(PDL_LSTM), pdl_rest && pdl_trig_mode(0));
             MARLC_TRY(tc_lstm_pair(la[0], la[1], s));
         }
     }
@@ -673,6 +696,7 @@ static int step_networks(marlc_engine* e, int t, const float* img, const int* po
             g[0].allow_split = g[1].allow_split = 2;
             g[0].c_zeroed = g[1].c_zeroed = 1;
             if (tc_operand_ok(g[0].A) && tc_operand_ok(g[0].B) && tc_operand_ok(g[1].A) && tc_operand_ok(g[1].B)) {
+                PdlScope pdl_g0(pdl_rest && pdl_edge(PDL_G0), pdl_rest && pdl_trig_mode(0));
                 MARLC_TRY(tc_gemm_group(g, 2, s));
                 grouped = true;
             }
@@ -794,10 +818,12 @@ extern "C" int marlc_episode_forward(marlc_engine* e, const float* img, const in
 
     for (int t = 0; t < T; ++t) {
         NvtxRange nvtx_step("marlc/forward/step");
+        // the step chain pre -> LSTM -> block-0 GEMMs -> post -> pre(t+1) ... runs as programmatic dependent launches
         MARLC_TRY(step_networks(e, t, img, pos_hist + (size_t)t * M * 2, nullptr, msg + (size_t)t * M * c.n_m,
                                 npos + (size_t)t * M * 2, H + (size_t)t * M * c.n_b, Cb + (size_t)t * M * c.n_b,
-                                Hc + (size_t)t * M * c.n_a, Cc + (size_t)t * M * c.n_a, s));
+                                Hc + (size_t)t * M * c.n_a, Cc + (size_t)t * M * c.n_a, s, t > 0 ? 2 : 1));
         if (e->debug_stop >= 11 && e->debug_stop <= 13) continue;  // profiling: skip the tail
+        PdlScope pdl_post(c.use_chains && pdl_edge(PDL_STEP_POST), c.use_chains && pdl_trig_mode(0));
         MARLC_TRY(step_act(e, t, actions ? actions + (size_t)t * M : nullptr, s));
     }
     if (e->debug_stop >= 11 && e->debug_stop <= 14) { e->last_launches = g_launch_count - start; return 0; }
@@ -1175,7 +1201,10 @@ extern "C" int marlc_episode_backward(marlc_engine* e, const float* img, int acc
             bp.dc_prev[0] = dc[cur ^ 1]; bp.dc_prev[1] = dcc[cur ^ 1];
             bp.n[0] = c.n_b; bp.n[1] = c.n_a;
             bp.Na = c.na; bp.Nb = c.nb; bp.M = M; bp.n_m = c.n_m;
-            MARLC_TRY(bwd_pre(bp, sw));
+            {
+                PdlScope pdl(t < T - 1 && pdl_edge(PDL_BWD_PRE), pdl_trig_mode(1));  // predecessor in `sw`: bwd_post of step t+1 (an event wait at t = T-1)
+                MARLC_TRY(bwd_pre(bp, sw));
+            }
             cur ^= 1;
             if (e->debug_stop == 21) continue;
             // input gradients: du = dg_b Wih_b + dg_a Wih_a ; dh = dg_b Whh_b ; dh^ = dg_a Whh_a  (ONE grouped launch)
@@ -1199,6 +1228,7 @@ extern "C" int marlc_episode_backward(marlc_engine* e, const float* img, int acc
                 }
                 ok = ok && tc_operand_ok(g[0].A2) && tc_operand_ok(g[0].B2);
                 if (ok) {
+                    PdlScope pdl(pdl_edge(PDL_DX), pdl_trig_mode(1));
                     MARLC_TRY(tc_gemm_group(g, t > 0 ? 3 : 1, sw));  // at t == 0 nothing consumes dh / dh^
                     tc_dx = true;
                 }
@@ -1245,7 +1275,10 @@ extern "C" int marlc_episode_backward(marlc_engine* e, const float* img, int acc
             bq.d_dec_y2 = e->buf("d_dec_y2") + (size_t)t * M * c.n_m_o;
             bq.dcoll = t > 0 ? dcoll : nullptr;
             bq.M = M; bq.n_m = c.n_m; bq.n_m_o = c.n_m_o;
-            MARLC_TRY(bwd_post(bq, sw));
+            {
+                PdlScope pdl(pdl_edge(PDL_BWD_POST), pdl_trig_mode(1));
+                MARLC_TRY(bwd_post(bq, sw));
+            }
             if (next_chunk >= 0 && t == (int)((long)next_chunk * T / nch)) {  // steps [t, chunk_hi) are final
                 cudaEvent_t done = e->next_event();
                 MARLC_CUDA(cudaEventRecord(done, sw));

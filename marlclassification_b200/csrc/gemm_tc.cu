@@ -226,6 +226,7 @@ struct TcKernelGroup {  // up to 3 independent problems in one launch; blockIdx.
     TcKernelParams p[TC_MAX_GROUP];
     int zofs[TC_MAX_GROUP + 1];
     int count;
+    int trig;  // 1: griddepcontrol.launch_dependents at entry (common.cuh)
 };
 
 // KS = number of 32-float K sub-blocks per pipeline stage.  The single-thread producer / MMA loops
@@ -329,6 +330,9 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
     if (cl > 1) cluster_sync_all();  // every CTA's barriers exist before any peer multicasts into them
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
+    // Everything above touched only the kernel parameters and this CTA's shared memory / TMEM.  From here on the
+    // operands, c_prev and C are read / written: wait for the predecessor kernel (no-op for ordinary launches).
+    pdl_wait();
     if (threadIdx.x == 0) TC_TRACE(0);  // setup done (barriers, TMEM)
     // K split over a CTA pair: the odd CTA will write into the even CTA's shared memory (DSMEM).  A CTA of a
     // cluster may only be written once it has STARTED executing: every thread arrives on the cluster barrier now
@@ -753,6 +757,7 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
 
 template <int BN, bool A_MN, bool B_MN, int EPI, int STAGES, bool X3, int KS>
 __global__ void __launch_bounds__(X3 ? TC_THREADS_X3 : TC_THREADS, 1) tc_gemm_kernel(const __grid_constant__ TcKernelGroup pp) {
+    if (pp.trig) pdl_trigger();  // the next kernel of a dependent chain may start its prologue (common.cuh)
     const int z = blockIdx.z;
     if (pp.count >= 3 && z >= pp.zofs[2]) tc_gemm_body<BN, A_MN, B_MN, EPI, STAGES, 2, X3, KS>(pp, z - pp.zofs[2]);
     else if (pp.count >= 2 && z >= pp.zofs[1]) tc_gemm_body<BN, A_MN, B_MN, EPI, STAGES, 1, X3, KS>(pp, z - pp.zofs[1]);
@@ -781,7 +786,8 @@ static int launch_store(TcKernelGroup& kp, int gx, int gy, int gz, int max_kb, c
         MARLC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES));
         attr_done = true;
     }
-    kern<<<dim3(gx, gy, gz), X3 ? TC_THREADS_X3 : TC_THREADS, S::BYTES, s>>>(kp);
+    kp.trig = pdl_trigger_early();
+    MARLC_CUDA(launch_pdl(kern, dim3(gx, gy, gz), dim3(X3 ? TC_THREADS_X3 : TC_THREADS), S::BYTES, s, kp));
     ++g_tc_gemm_launches;
     MARLC_LAUNCH_CHECK();
     return 0;
@@ -843,6 +849,7 @@ int tc_gemm_group(const TcGemmArgs* args, int count, cudaStream_t s) {
     memset(&kp, 0, sizeof(kp));
     kp.count = count;
     int gx = 0, gy = 0, ctas = 0, min_k = 1 << 30;
+    int pdl_ok = g_pdl;
     for (int i = 0; i < count; ++i) {
         const TcGemmArgs& a = args[i];
         ctas += ((a.M + BM - 1) / BM) * ((a.N + BN - 1) / BN);
@@ -906,6 +913,7 @@ int tc_gemm_group(const TcGemmArgs* args, int count, cudaStream_t s) {
         }
         p.splits = splits;
         if (splits > 1 && !a.accumulate && !a.c_zeroed) {
+            pdl_ok = 0;  // the predecessor in the stream is a memset now: ordinary launch
             if (a.ldc == a.N) MARLC_CUDA(cudaMemsetAsync(a.C, 0, sizeof(float) * (size_t)a.M * a.N, s));
             else MARLC_CUDA(cudaMemset2DAsync(a.C, sizeof(float) * a.ldc, 0, sizeof(float) * a.N, a.M, s));
         }
@@ -914,6 +922,7 @@ int tc_gemm_group(const TcGemmArgs* args, int count, cudaStream_t s) {
         gy = max(gy, mt);
     }
     const int gz = kp.zofs[count];
+    PdlScope pdl_scope(pdl_ok, g_pdl_trig);
     int max_kb = 1;
     for (int i = 0; i < count; ++i) {
         const int nkb = kp.p[i].nk1 + kp.p[i].nk2;
@@ -966,23 +975,9 @@ static int launch_lstm(TcKernelGroup& kp, int gx, int gy, int nkb, cudaStream_t 
         MARLC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
         attr_sz = smem_bytes;
     }
-    if (cl > 1) {
-        cudaLaunchConfig_t cfg;
-        memset(&cfg, 0, sizeof(cfg));
-        cfg.gridDim = dim3(gx * ksp, gy, 2);
-        cfg.blockDim = dim3(X3 ? TC_THREADS_X3 : TC_THREADS);
-        cfg.dynamicSmemBytes = smem_bytes;
-        cfg.stream = s;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        MARLC_CUDA(cudaLaunchKernelEx(&cfg, kern, kp));
-        ++g_launch_count;
-        ++g_tc_gemm_launches;
-        return 0;
-    }
-    kern<<<dim3(gx, gy, 2), X3 ? TC_THREADS_X3 : TC_THREADS, S::BYTES, s>>>(kp);
+    kp.trig = pdl_trigger_early();
+    MARLC_CUDA(launch_pdl(kern, dim3(gx * ksp, gy, 2), dim3(X3 ? TC_THREADS_X3 : TC_THREADS), cl > 1 ? smem_bytes : (size_t)S::BYTES,
+                          s, kp, cl > 1 ? cl : 1));
     ++g_tc_gemm_launches;
     MARLC_LAUNCH_CHECK();
     return 0;
