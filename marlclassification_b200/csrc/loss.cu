@@ -82,14 +82,30 @@ __global__ void returns_kernel(const LossArgs a) {
     double s1 = 0.0, s2 = 0.0;
     if (m < M) {
         float G = 0.f;
-        for (int t = a.T - 1; t >= 0; --t) {
-            const long i = (long)t * M + m;
-            G = fmaf(a.gamma, G, a.rewards[i]);
-            a.returns[i] = G;
-            const float ad = G - a.values[i];
-            a.adv[i] = ad;
-            s1 += ad;
-            s2 += (double)ad * ad;
+        // 8 steps of operands in flight before the dependent scan touches them: with one load per iteration (the
+        // stores to returns / adv may alias, so the compiler cannot hoist it) every step paid an L2 round trip --
+        // 17 us for a 16-step scan (launch list, round 2)
+        for (int t1 = a.T; t1 > 0; t1 -= 8) {
+            float r[8], v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int t = t1 - 1 - k;
+                r[k] = t >= 0 ? a.rewards[(long)t * M + m] : 0.f;
+                v[k] = t >= 0 ? a.values[(long)t * M + m] : 0.f;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int t = t1 - 1 - k;
+                if (t >= 0) {
+                    const long i = (long)t * M + m;
+                    G = fmaf(a.gamma, G, r[k]);
+                    a.returns[i] = G;
+                    const float ad = G - v[k];
+                    a.adv[i] = ad;
+                    s1 += ad;
+                    s2 += (double)ad * ad;
+                }
+            }
         }
     }
     s1 = warp_sum_d(s1); s2 = warp_sum_d(s2);
