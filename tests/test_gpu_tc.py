@@ -203,7 +203,7 @@ def _lstm_ref64(u, h, c, wih, whh, bih, bhh):
     return torch.cat([i, f, gg, o], 1), cn, o * torch.tanh(cn)
 
 
-@pytest.mark.parametrize("M,Kin,n", [(128, 368, 256), (96, 96, 64), (4096, 368, 256), (20, 624, 256), (130, 100, 32)])
+@pytest.mark.parametrize("M,Kin,n", [(128, 368, 256), (96, 96, 64), (4096, 368, 256), (20, 624, 256), (130, 100, 32), (512, 368, 256)])
 @pytest.mark.parametrize("mode", ["tf32", "tf32x3", "presplit"])
 def test_tc_lstm_pair_vs_fp64(M, Kin, n, mode):
     import ctypes as ct
