@@ -220,6 +220,7 @@ struct TcKernelParams {
     float* h_new_lo;  // optional: lo part of h_new for the next consumer's pre-split A operand
     float* gates;
     int n_hidden;
+    int epi_staged;   // EPI_LSTM: cell outputs leave through a shared-memory transpose (row-coalesced stores)
 };
 constexpr int TC_MAX_GROUP = 3;
 struct TcKernelGroup {  // up to 3 independent problems in one launch; blockIdx.z -> (problem, K split)
@@ -673,6 +674,21 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
                 asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
             }
             const float* prow = part + (32 * q + lane) * PPITCH;
+            // The seven outputs of the cell (4 activated gates, c, h, low-order part of h) are row-major arrays in
+            // global memory while TMEM hands every lane ONE ROW of the tile: stored straight from the registers, each
+            // 128-bit store instruction touched 32 rows (32 half-sector requests), and the epilogue took 7 300 cycles
+            // of a 27 000-cycle launch at 512 rows -- the same with 4 or 8 warps sharing it, i.e. bound by the
+            // requests, not by the arithmetic (in-kernel trace, round 2).  Now a chunk of CH hidden units is staged in
+            // the (dead) pipeline ring, row per lane, and leaves with the lanes running ALONG the rows: 4 x CH bytes
+            // contiguous per row and array.  (K-split pairs keep the direct stores: their tile is 8 units wide.)
+            constexpr int RINGF = (S::BYTES - 1024) / 4;  // floats of the ring
+            constexpr int CH_FIT = 4 * 7 * 32 * (32 + 4) <= RINGF ? 32 : (4 * 7 * 32 * (16 + 4) <= RINGF ? 16 : 8);
+            constexpr int CH = HU < CH_FIT ? HU : CH_FIT;  // hidden units per staged chunk
+            constexpr int SP = CH + 4;             // staging row pitch: conflict-free 128-bit row-per-lane writes
+            constexpr int LPR = CH / 4, RPI = 32 / LPR;  // lanes per row / rows per store instruction on the way out
+            static_assert(EPI != EPI_LSTM || 4 * 7 * 32 * SP * 4 <= S::BYTES - 1024, "cell staging does not fit in the ring");
+            const bool staged = ksp == 1 && p.epi_staged != 0;
+            float* stg = reinterpret_cast<float*>(smem) + q * (7 * 32 * SP);  // [7 arrays][32 rows][SP] of this warp
             if (ksp == 1 || kslice == 0) {
 #pragma unroll 1
             for (int jb = 0; jb < HU; jb += 8) {
@@ -691,10 +707,14 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
                         ro[j] = __float_as_uint(__uint_as_float(ro[j]) + prow[3 * HU + jb + j]);
                     }
                 }
-                if (m < p.M) {
+                const bool row_ok = m < p.M;
+                if (row_ok || staged) {  // (staged: lanes past the last row compute on zero-filled operands, store nothing)
                     const long off = (long)m * n + j0 + jb;
                     float cp[8];
-                    if (jb == 0) {
+                    if (!row_ok) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) cp[j] = 0.f;
+                    } else if (jb == 0) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) cp[j] = cp_pref[j];
                     } else {
@@ -714,20 +734,46 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
                         cn[j] = gf[j] * cp[j] + gi[j] * gc[j];
                         hn[j] = go[j] * fast_tanh(cn[j]);
                     }
-                    float* g_row = p.gates + (long)m * 4 * n + j0 + jb;
                     auto st8 = [](float* dst, const float* v) {
                         *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
                         *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
                     };
-                    st8(g_row, gi); st8(g_row + n, gf); st8(g_row + 2 * n, gc); st8(g_row + 3 * n, go);
-                    st8(p.c_new + off, cn);
-                    st8(p.h_new + off, hn);
-                    if (p.h_new_lo) {
-                        float hl[8];
+                    float hl[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) hl[j] = hn[j] - __uint_as_float(__float_as_uint(hn[j]) & 0xFFFFE000u);
-                        st8(p.h_new_lo + off, hl);
+                    for (int j = 0; j < 8; ++j) hl[j] = hn[j] - __uint_as_float(__float_as_uint(hn[j]) & 0xFFFFE000u);
+                    if (staged) {
+                        float* srow = stg + lane * SP + (jb % CH);
+                        st8(srow, gi); st8(srow + 32 * SP, gf); st8(srow + 2 * 32 * SP, gc); st8(srow + 3 * 32 * SP, go);
+                        st8(srow + 4 * 32 * SP, cn); st8(srow + 5 * 32 * SP, hn); st8(srow + 6 * 32 * SP, hl);
+                    } else {
+                        float* g_row = p.gates + (long)m * 4 * n + j0 + jb;
+                        st8(g_row, gi); st8(g_row + n, gf); st8(g_row + 2 * n, gc); st8(g_row + 3 * n, go);
+                        st8(p.c_new + off, cn);
+                        st8(p.h_new + off, hn);
+                        if (p.h_new_lo) st8(p.h_new_lo + off, hl);
                     }
+                }
+                if (staged && (jb + 8) % CH == 0) {  // a chunk of CH units is complete: out, lanes along the rows
+                    __syncwarp();
+                    const int jc = jb + 8 - CH, rr = lane / LPR, c4 = (lane % LPR) * 4;
+#pragma unroll 1
+                    for (int a = 0; a < 7; ++a) {
+                        float* base;
+                        long ld = n;
+                        if (a < 4) { base = p.gates + a * n + j0 + jc; ld = 4L * n; }
+                        else if (a == 4) base = p.c_new + j0 + jc;
+                        else if (a == 5) base = p.h_new + j0 + jc;
+                        else { if (!p.h_new_lo) break; base = p.h_new_lo + j0 + jc; }
+                        const float* sa = stg + a * 32 * SP;
+#pragma unroll
+                        for (int r0 = 0; r0 < 32; r0 += RPI) {
+                            const int row = r0 + rr, mrow = m0 + 32 * q + row;
+                            if (mrow < p.M)
+                                *reinterpret_cast<float4*>(base + (long)mrow * ld + c4) =
+                                    *reinterpret_cast<const float4*>(sa + row * SP + c4);
+                        }
+                    }
+                    __syncwarp();  // the next chunk overwrites the staging rows
                 }
             }
             }  // receiving / only CTA
@@ -1059,6 +1105,8 @@ int tc_lstm_pair(const TcLstmArgs& c0, const TcLstmArgs& c1, cudaStream_t s) {
         p.bias = c.bih; p.bias2 = c.bhh;
         p.c_prev = c.c_prev; p.c_new = c.c_new; p.h_new = c.h_new; p.gates = c.gates;
         p.n_hidden = c.n;
+        static const int staged_env = getenv("MARLC_LSTM_STAGED") ? atoi(getenv("MARLC_LSTM_STAGED")) : 1;  // A/B toggle
+        p.epi_staged = staged_env;
         p.splits = 1;
         gx = max(gx, c.n / HU);
     }
