@@ -710,18 +710,16 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
                 const bool row_ok = m < p.M;
                 if (row_ok || staged) {  // (staged: lanes past the last row compute on zero-filled operands, store nothing)
                     const long off = (long)m * n + j0 + jb;
+                    // c_prev of this chunk was requested one chunk ago (the first one before the main loop ended);
+                    // the next chunk's request goes out now, ahead of this chunk's activations
                     float cp[8];
-                    if (!row_ok) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) cp[j] = 0.f;
-                    } else if (jb == 0) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) cp[j] = cp_pref[j];
-                    } else {
-                        const float4 cp0 = *reinterpret_cast<const float4*>(p.c_prev + off);
-                        const float4 cp1 = *reinterpret_cast<const float4*>(p.c_prev + off + 4);
-                        cp[0] = cp0.x; cp[1] = cp0.y; cp[2] = cp0.z; cp[3] = cp0.w;
-                        cp[4] = cp1.x; cp[5] = cp1.y; cp[6] = cp1.z; cp[7] = cp1.w;
+                    for (int j = 0; j < 8; ++j) cp[j] = row_ok ? cp_pref[j] : 0.f;
+                    if (row_ok && jb + 8 < HU) {
+                        const float4 cp0 = *reinterpret_cast<const float4*>(p.c_prev + off + 8);
+                        const float4 cp1 = *reinterpret_cast<const float4*>(p.c_prev + off + 12);
+                        cp_pref[0] = cp0.x; cp_pref[1] = cp0.y; cp_pref[2] = cp0.z; cp_pref[3] = cp0.w;
+                        cp_pref[4] = cp1.x; cp_pref[5] = cp1.y; cp_pref[6] = cp1.z; cp_pref[7] = cp1.w;
                     }
                     const float* sb = s_bias[q];
                     float gi[8], gf[8], gc[8], go[8], cn[8], hn[8];
