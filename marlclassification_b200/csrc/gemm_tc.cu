@@ -267,7 +267,7 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
     __shared__ __align__(8) uint64_t split_bar[STAGES];
     __shared__ __align__(8) uint64_t tmem_full_bar;
     __shared__ uint32_t tmem_base_smem;
-    __shared__ float s_bias[4][BN];  // per epilogue warp: bias (+ bias2) of this tile's columns
+    __shared__ float s_bias[8][BN];  // per epilogue warp (2..9): bias (+ bias2) of this tile's columns
 
     const TcKernelParams& p = pp.p[PI];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -275,7 +275,7 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
     const uint16_t cl_mask = (uint16_t)((1u << cl) - 1u);
     const uint32_t cl_rank = cl > 1 ? cluster_rank() : 0u;
 #ifdef MARLC_TC_TRACE  // in-kernel timeline of CTA (0,0,0): cycles since entry at each pipeline event
-    __shared__ long long trace[8];
+    __shared__ long long trace[12];
     const bool tr = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
     const long long t_entry = clock64();
 #define TC_TRACE(i) do { if (tr) trace[i] = clock64() - t_entry; } while (0)
@@ -439,9 +439,19 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
         // the tile's bias values go to shared memory (one copy per warp, so a __syncwarp suffices) and
         // the LSTM cell's c_prev to registers.  Loading them after the accumulator wait cost one
         // exposed L2 round trip per 8-column chunk (~2 us of a 4.7 us launch, in-kernel trace).
+        // EIGHT epilogue warps for wide LSTM tiles when the four splitter warps have nothing to split (both operands
+        // arrive pre-split) and the tile is not K-split over a CTA pair: warps 6..9 sit on the same TMEM lane quarters as
+        // warps 4, 5, 2, 3 (quarter = warp % 4) and take the upper half of the tile's hidden units.  The activations
+        // of 8 units take ~1 750 cycles for a warp that runs alone on its scheduler (dependent MUFU chains: in-kernel
+        // trace, round 2) -- 14 000 of the 22 500-cycle epilogue of a 128 x 256 tile; two warps per scheduler overlap them.
+        constexpr int HU_E = BN / 4;
+        const bool epi8 = EPI == EPI_LSTM && X3 && HU_E >= 32 && ksp == 1 && p.a_lo_g && p.b_lo_g && p.epi_staged != 0;
+        const bool epi_warp = warp < 6 || epi8;
+        const int jb_begin = (epi8 && warp >= 6) ? HU_E / 2 : 0;
+        const int jb_end = epi8 ? (warp >= 6 ? HU_E : HU_E / 2) : HU_E;
         float cp_pref[8];
-        if (warp < 6) {
-            float* sb = s_bias[q];
+        if (epi_warp) {
+            float* sb = s_bias[warp - 2];
             if (EPI == EPI_STORE) {
                 const bool first_split0 = (p.splits <= 1) || (split == 0);
                 for (int j = lane; j < BN; j += 32) {
@@ -461,7 +471,7 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
                     sb[j] = __ldg(p.bias + col) + __ldg(p.bias2 + col);
                 }
                 if (m < p.M) {
-                    const long off = (long)m * n + j0;
+                    const long off = (long)m * n + j0 + jb_begin;
                     const float4 c0 = *reinterpret_cast<const float4*>(p.c_prev + off);
                     const float4 c1 = *reinterpret_cast<const float4*>(p.c_prev + off + 4);
                     cp_pref[0] = c0.x; cp_pref[1] = c0.y; cp_pref[2] = c0.z; cp_pref[3] = c0.w;
@@ -507,7 +517,7 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
                 asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&split_bar[s])) : "memory");
             }
         }
-        if (warp < 6) {  // warps 2..5 own the four TMEM lane quarters
+        if (epi_warp) {  // warps 2..5 own the four TMEM lane quarters (wide LSTM tiles: + warps 6..9, see above)
         // Epilogue parameters are pulled into registers NOW (and made opaque to the compiler, which
         // would otherwise re-read them from the constant bank inside the store loop: the SASS had four
         // dependent LDCU -> compare -> branch chains per row, ~250 cycles per iteration in the trace).
@@ -548,7 +558,7 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
 #pragma unroll
                         for (int j = 0; j < 32; ++j) r[j] = 0u;
                     }
-                    const float* sb = s_bias[q] + c0;
+                    const float* sb = s_bias[warp - 2] + c0;
                     const uint32_t rowb = box0 + (uint32_t)(c0 >> 5) * 4096u + (uint32_t)lane * 128u;
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
@@ -588,7 +598,7 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
 #pragma unroll
                     for (int j = 0; j < 32; ++j) r[j] = 0u;
                 }
-                const float* sb = s_bias[q] + c0;
+                const float* sb = s_bias[warp - 2] + c0;
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     const float4 v = make_float4(__uint_as_float(r[j]) + sb[j], __uint_as_float(r[j + 1]) + sb[j + 1],
@@ -682,22 +692,26 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
             // the (dead) pipeline ring, row per lane, and leaves with the lanes running ALONG the rows: 4 x CH bytes
             // contiguous per row and array.  (K-split pairs keep the direct stores: their tile is 8 units wide.)
             constexpr int RINGF = (S::BYTES - 1024) / 4;  // floats of the ring
-            constexpr int CH_FIT = 4 * 7 * 32 * (32 + 4) <= RINGF ? 32 : (4 * 7 * 32 * (16 + 4) <= RINGF ? 16 : 8);
-            constexpr int CH = HU < CH_FIT ? HU : CH_FIT;  // hidden units per staged chunk
+            constexpr int NEW = (X3 && HU >= 32) ? 8 : 4;  // epilogue warps that may stage at once (see epi8)
+            constexpr int CH_FIT = NEW * 7 * 32 * (32 + 4) <= RINGF ? 32 : (NEW * 7 * 32 * (16 + 4) <= RINGF ? 16 : 8);
+            constexpr int CH = HU / (NEW / 4) < CH_FIT ? HU / (NEW / 4) : CH_FIT;  // hidden units per staged chunk
             constexpr int SP = CH + 4;             // staging row pitch: conflict-free 128-bit row-per-lane writes
             constexpr int LPR = CH / 4, RPI = 32 / LPR;  // lanes per row / rows per store instruction on the way out
-            static_assert(EPI != EPI_LSTM || 4 * 7 * 32 * SP * 4 <= S::BYTES - 1024, "cell staging does not fit in the ring");
+            static_assert(EPI != EPI_LSTM || NEW * 7 * 32 * SP * 4 <= S::BYTES - 1024, "cell staging does not fit in the ring");
             const bool staged = ksp == 1 && p.epi_staged != 0;
-            float* stg = reinterpret_cast<float*>(smem) + q * (7 * 32 * SP);  // [7 arrays][32 rows][SP] of this warp
+            float* stg = reinterpret_cast<float*>(smem) + (warp - 2) * (7 * 32 * SP);  // [7 arrays][32 rows][SP] of this warp
             if (ksp == 1 || kslice == 0) {
 #pragma unroll 1
-            for (int jb = 0; jb < HU; jb += 8) {
+            for (int jb = jb_begin; jb < jb_end; jb += 8) {
                 uint32_t ri[8], rf[8], rg[8], ro[8];
                 TMEM_LD8(trow + 0 * HU + jb, ri);
                 TMEM_LD8(trow + 1 * HU + jb, rf);
                 TMEM_LD8(trow + 2 * HU + jb, rg);
                 TMEM_LD8(trow + 3 * HU + jb, ro);
                 tmem_ld_wait();
+#ifdef MARLC_TC_TRACE
+                if (warp == 2 && lane == 0 && jb == 0) TC_TRACE(6);  // first chunk's accumulators in registers
+#endif
                 if (ksp > 1) {  // add the partner's half of K
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -715,13 +729,13 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
                     float cp[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) cp[j] = row_ok ? cp_pref[j] : 0.f;
-                    if (row_ok && jb + 8 < HU) {
+                    if (row_ok && jb + 8 < jb_end) {
                         const float4 cp0 = *reinterpret_cast<const float4*>(p.c_prev + off + 8);
                         const float4 cp1 = *reinterpret_cast<const float4*>(p.c_prev + off + 12);
                         cp_pref[0] = cp0.x; cp_pref[1] = cp0.y; cp_pref[2] = cp0.z; cp_pref[3] = cp0.w;
                         cp_pref[4] = cp1.x; cp_pref[5] = cp1.y; cp_pref[6] = cp1.z; cp_pref[7] = cp1.w;
                     }
-                    const float* sb = s_bias[q];
+                    const float* sb = s_bias[warp - 2];
                     float gi[8], gf[8], gc[8], go[8], cn[8], hn[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -739,6 +753,9 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
                     float hl[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) hl[j] = hn[j] - __uint_as_float(__float_as_uint(hn[j]) & 0xFFFFE000u);
+#ifdef MARLC_TC_TRACE
+                    if (warp == 2 && lane == 0 && jb == 0) TC_TRACE(7);  // first chunk's activations done
+#endif
                     if (staged) {
                         float* srow = stg + lane * SP + (jb % CH);
                         st8(srow, gi); st8(srow + 32 * SP, gf); st8(srow + 2 * 32 * SP, gc); st8(srow + 3 * 32 * SP, go);
@@ -751,6 +768,10 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
                         if (p.h_new_lo) st8(p.h_new_lo + off, hl);
                     }
                 }
+#ifdef MARLC_TC_TRACE
+                if (warp == 2 && lane == 0 && jb == 0) TC_TRACE(8);  // first chunk staged
+                if (warp == 2 && lane == 0 && jb == 8) TC_TRACE(10);  // second chunk staged
+#endif
                 if (staged && (jb + 8) % CH == 0) {  // a chunk of CH units is complete: out, lanes along the rows
                     __syncwarp();
                     const int jc = jb + 8 - CH, rr = lane / LPR, c4 = (lane % LPR) * 4;
@@ -772,6 +793,9 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
                         }
                     }
                     __syncwarp();  // the next chunk overwrites the staging rows
+#ifdef MARLC_TC_TRACE
+                    if (warp == 2 && lane == 0 && jb + 8 == CH) TC_TRACE(9);  // first staged chunk written out
+#endif
                 }
             }
             }  // receiving / only CTA
@@ -791,6 +815,9 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
         printf("tc trace BN=%d X3=%d KS=%d EPI=%d kb=%d: setup %lld | tma0 %lld | full0 %lld | mma_issued %lld | acc_done %lld | epi_done %lld | end %lld\n",
                BN, (int)X3, KS, EPI, my_kb, trace[0], trace[1], trace[2], trace[3], trace[4], trace[5], clock64() - t_entry);
     if (tr && threadIdx.x == 0 && EPI == EPI_STORE) printf("   staged at %lld, third store iteration at %lld\n", trace[6], trace[7]);
+    if (tr && threadIdx.x == 0 && EPI == EPI_LSTM)
+        printf("   cell: first 8 units loaded %lld | activated %lld | staged %lld | second 8 staged %lld | first chunk written out %lld\n",
+               trace[6], trace[7], trace[8], trace[10], trace[9]);
 #endif
     if (warp == 1) {
         tc_fence_after();
