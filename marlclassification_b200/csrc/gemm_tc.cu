@@ -174,9 +174,18 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
         : "r"(addr))
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// MUFU-based activations for the tensor-core epilogue (abs error ~1e-7, far below TF32's)
-__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-__device__ __forceinline__ float fast_tanh(float x) { return fmaf(2.0f, fast_sigmoid(2.0f * x), -1.0f); }
+// MUFU-based activations for the tensor-core epilogue (abs error ~1e-7, far below TF32's).  The cell epilogue is bound
+// by instruction throughput (in-kernel trace, round 2: ~1 750 cycles of a scheduler per 8 hidden units x 32 rows), so
+// the two special-function operations are issued directly (ex2 / rcp, flush-to-zero forms: __expf and __fdividef each
+// wrap theirs in range fix-ups) and the scale of the exponent is folded into the bias add:
+//   sigmoid(a + b) = rcp(1 + ex2(a * -log2(e) + b * -log2(e))),   tanh(x) = 2 * sigmoid(2x) - 1.
+constexpr float NEG_LOG2E = -1.4426950408889634f;
+__device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// t = x * -log2(e) for sigmoid(x), x * -2 log2(e) for tanh(x)
+__device__ __forceinline__ float sigmoid_of_scaled(float t) { return rcp_ftz(1.0f + ex2_ftz(t)); }
+__device__ __forceinline__ float tanh_of_scaled(float t) { return fmaf(2.0f, rcp_ftz(1.0f + ex2_ftz(t)), -1.0f); }
+__device__ __forceinline__ float fast_tanh(float x) { return tanh_of_scaled(2.0f * NEG_LOG2E * x); }
 
 // smem matrix descriptor (cute::UMMA::SmemDescriptor bit layout).
 // layout_type: 2 = SWIZZLE_128B (K-major tiles), 1 = SWIZZLE_128B_BASE32B (MN-major TF32 tiles)
@@ -468,7 +477,8 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
                 const int n = p.n_hidden, j0 = n_tile * HU;
                 for (int j = lane; j < BN; j += 32) {
                     const int g = j / HU, col = g * n + j0 + (j - g * HU);
-                    sb[j] = __ldg(p.bias + col) + __ldg(p.bias2 + col);
+                    // pre-scaled for the activation the gate goes through (i, f, o: sigmoid; g: tanh), see sigmoid_of_scaled
+                    sb[j] = (__ldg(p.bias + col) + __ldg(p.bias2 + col)) * (g == 2 ? 2.0f * NEG_LOG2E : NEG_LOG2E);
                 }
                 if (m < p.M) {
                     const long off = (long)m * n + j0 + jb_begin;
@@ -739,10 +749,10 @@ __device__ __forceinline__ void tc_gemm_body(const TcKernelGroup& pp, const int 
                     float gi[8], gf[8], gc[8], go[8], cn[8], hn[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        gi[j] = fast_sigmoid(__uint_as_float(ri[j]) + sb[0 * HU + jb + j]);
-                        gf[j] = fast_sigmoid(__uint_as_float(rf[j]) + sb[1 * HU + jb + j]);
-                        gc[j] = fast_tanh(__uint_as_float(rg[j]) + sb[2 * HU + jb + j]);
-                        go[j] = fast_sigmoid(__uint_as_float(ro[j]) + sb[3 * HU + jb + j]);
+                        gi[j] = sigmoid_of_scaled(fmaf(__uint_as_float(ri[j]), NEG_LOG2E, sb[0 * HU + jb + j]));
+                        gf[j] = sigmoid_of_scaled(fmaf(__uint_as_float(rf[j]), NEG_LOG2E, sb[1 * HU + jb + j]));
+                        gc[j] = tanh_of_scaled(fmaf(__uint_as_float(rg[j]), 2.0f * NEG_LOG2E, sb[2 * HU + jb + j]));
+                        go[j] = sigmoid_of_scaled(fmaf(__uint_as_float(ro[j]), NEG_LOG2E, sb[3 * HU + jb + j]));
                         cn[j] = gf[j] * cp[j] + gi[j] * gc[j];
                         hn[j] = go[j] * fast_tanh(cn[j]);
                     }
