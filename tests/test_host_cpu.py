@@ -183,3 +183,19 @@ def test_same_seed_gives_the_reference_initialisation(name, tmp_path):
     assert list(ours) == list(ref)
     for k in ref:
         assert torch.equal(ours[k], ref[k]), k
+
+
+def test_every_environment_switch_is_documented():
+    """Every MARLC_* variable the library or the Python package reads is listed in INTEGRATION.md section 3."""
+    import glob
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    names = set()
+    for path in glob.glob(os.path.join(root, "marlclassification_b200", "csrc", "*.cu*")):
+        names |= set(re.findall(r'getenv\("(MARLC_[A-Z0-9_]+)"\)', open(path).read()))
+    for path in glob.glob(os.path.join(root, "marlclassification_b200", "**", "*.py"), recursive=True) + [os.path.join(root, "bench.py")]:
+        names |= set(re.findall(r'environ(?:\.get)?[\(\[]"(MARLC_[A-Z0-9_]+)"', open(path).read()))
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    missing = sorted(n for n in names if n not in doc)
+    assert names and not missing, f"undocumented switches: {missing}"
