@@ -306,10 +306,11 @@ def roofline_for(model, w: dict, nb: int, dev) -> dict:
                        f"{pk.get('bf16_tflops')} TFLOP/s burst, {src}; frac_of_half_bf16_peak uses half of it)",
         "precision": prec,
         "time_share": ("the tensor-bound kernels take 9-12 % of the iteration each in the ncu launch list of this workload "
-                       "(profiles/r2/launches_c4_nb256_summary.txt: input-gradient GEMMs 11.7 %, weight-gradient GEMMs 11.2 %, "
-                       "fused LSTM pair 9.3 %); the main entry is the LSTM pair (the one captured with ncu --set full), the "
+                       "(profiles/r2/launches_c4_nb256_summary.txt: weight-gradient GEMMs 12.1 %, input-gradient GEMMs 12.0 %, "
+                       "fused LSTM pair 9.4 % -- list taken before the LSTM epilogue changes of the last commits); the main entry is "
+                       "the LSTM pair (the one captured with ncu --set full), the "
                        "weight-gradient GEMM is listed under others; the largest share overall is step_pre_wide_kernel "
-                       "(16 %, fp32 FFMA: under others against the CUDA-core peak)" if big else
+                       "(15 %, fp32 FFMA: under others against the CUDA-core peak)" if big else
                        "largest tensor-kernel share at the batch-8 configurations (profiles/r2/launches_c2_summary.txt)"),
         "others": [
             dw_e,
